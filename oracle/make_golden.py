@@ -1,0 +1,265 @@
+"""Generate `tests/golden/*.npz` by running the UNMODIFIED reference under `oracle/ref_shims` (O1).
+
+Run in the build container only (`python oracle/make_golden.py`); `/root/reference` does not exist on the GPU box.
+Each fixture stores the inputs, every parameter, a JSON description of the flow, and the reference's outputs:
+ELBO / ELL / KLD, q(f) marginals, every gradient of ELBO, test log-likelihood and predictive moments.
+`tests/test_oracle_golden.py` replays them through `oracle/tgp_oracle.py` (O2); `tests/test_gpu_parity.py`
+replays them through the CUDA path.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle.ref_loader import load_reference  # noqa: E402
+
+dsp = load_reference()
+import dsp.config as cg  # noqa: E402
+from dsp.models import instance_kernel, sparse_MF_SP, sparse_MF_GP  # noqa: E402
+from dsp.models.flow import (instance_flow, AffineFlow, StepFlow, TanhFlow, Sinh_ArcsinhFlow,  # noqa: E402
+                             IdentityFlow, CompositeFlow)
+from dsp.likelihoods import GaussianNonLinearMean, GaussianLinearMean, Bernoulli  # noqa: E402
+from dsp.flows import SAL, StepTanhL  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+UCI = os.path.join(os.environ.get('TGP_REFERENCE_ROOT', '/root/reference'), 'code', 'datasets', 'regression', 'uci')
+
+
+def load_uci(name, seed=1):
+    """Same preprocessing as reference data path (uci_datasets.py:72-97, data.py:260-299): split pickle,
+    standardise X and Y with training statistics."""
+    import pandas as pd
+    import pickle
+    arr = pd.read_csv(os.path.join(UCI, name + '.csv'), header=None).values.astype(np.float64)
+    with open(os.path.join(UCI, 'splits_idx_%s.pkl' % name), 'rb') as fh:
+        sp = pickle.load(fh)['seed_%d' % seed]
+    tr, te = np.asarray(sp['train']), np.asarray(sp['test'])
+    X, Y = arr[:, :-1], arr[:, -1:]
+    Xtr, Ytr, Xte, Yte = X[tr], Y[tr], X[te], Y[te]
+    xm, xs = Xtr.mean(0), Xtr.std(0)
+    xs[xs == 0] = 1.0
+    ym, ys = Ytr.mean(0), Ytr.std(0)
+    f = lambda a: torch.tensor(a, dtype=torch.float64)  # noqa: E731
+    return f((Xtr - xm) / xs), f((Ytr - ym) / ys), f((Xte - xm) / xs), f((Yte - ym) / ys), float(ys[0])
+
+
+def build(kind, X, M, N, flow=None, likelihood=None, seed=0):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    Dx = X.shape[1]
+    K = instance_kernel('scale_rbf', ard_num_dim=Dx, num_multioutput=1, kernel_is_shared=False,
+                        init_params={'length_scale': 2.0, 'kernel_scale': 2.0, 'noisy_variance': 1e-6})
+    Z = X[torch.randperm(X.shape[0])[:M]].clone()
+    ip = {'variational_distribution': {'variance_scale': 1e-5, 'mean_scale': 0.0}}
+    if kind == 'SVGP':
+        lik = GaussianLinearMean(out_dim=1, noise_init=0.05, noise_is_shared=False)
+        return sparse_MF_GP(['zero', K], X, Z, N, lik, 1, True, False, False, False, False, 0.0, ip)
+    lik = likelihood or GaussianNonLinearMean(out_dim=1, noise_init=0.05, noise_is_shared=False,
+                                              quadrature_points=cg.quad_points)
+    return sparse_MF_SP(['zero', K], X, Z, N, lik, 1, True, False, False, False, False, [flow], 'single', 0.0,
+                        False, ip)
+
+
+def randomise(model, seed):
+    """P1 'mid-training' state: nothing at its trivial initial value."""
+    g = torch.Generator().manual_seed(seed)
+    M = model.M
+    with torch.no_grad():
+        for n, prm in model.named_parameters():
+            if n == 'Z':
+                prm.add_(0.05 * torch.randn(prm.shape, generator=g))
+            elif n.endswith('raw_lengthscale'):
+                ls = 0.5 + 2.5 * torch.rand(prm.shape, generator=g)
+                prm.copy_(ls + torch.log(-torch.expm1(-ls)))
+            elif n.endswith('raw_outputscale'):
+                s = torch.full(prm.shape, 1.5)
+                prm.copy_(s + torch.log(-torch.expm1(-s)))
+            elif n.endswith('variational_mean'):
+                prm.copy_(torch.randn(prm.shape, generator=g))
+            elif n.endswith('chol_variational_covar'):
+                prm.copy_(0.5 * torch.eye(M).unsqueeze(0) + 0.05 * torch.randn(prm.shape, generator=g))
+            elif n.endswith('log_var_noise'):
+                prm.copy_(torch.log(torch.full(prm.shape, 0.2)))
+            elif 'G_matrix' in n and 'NNets' not in n:
+                prm.add_(0.3 * torch.randn(prm.shape, generator=g))
+            elif 'NNets' in n:
+                prm.add_(0.2 * torch.randn(prm.shape, generator=g))
+
+
+def flow_to_spec(flow, store, X=None, prefix='fl'):
+    """Walk a reference CompositeFlow and emit the oracle layer list (JSON-able; arrays go to `store`)."""
+    spec = []
+    idx = [0]
+
+    def put(t):
+        k = '%s_%d' % (prefix, idx[0])
+        idx[0] += 1
+        store[k] = t.detach().cpu().numpy().astype(np.float64)
+        return k
+
+    for fl in flow.flow_arr:
+        if isinstance(fl, IdentityFlow):
+            spec.append(['identity'])
+        elif isinstance(fl, AffineFlow):
+            spec.append(['affine', put(fl.a), put(fl.b), bool(fl.set_restrictions)])
+        elif isinstance(fl, StepFlow):
+            steps = []
+            for sw, sub in zip(fl.switch_off, fl.flow_arr):
+                assert isinstance(sub, TanhFlow) and not sw.is_trainable and sub.set_restrictions
+                assert not sub.add_init_f0 and not sub.input_dependent
+                steps.append([put(sub.a), put(sub.b), put(sub.c), put(sub.d)])
+            spec.append(['tanh_step', steps, bool(fl.add_init_f0)])
+        elif isinstance(fl, Sinh_ArcsinhFlow):
+            if fl.input_dependent:
+                a = fl.NNets_a(X).squeeze(-1)
+                b = fl.NNets_b(X).squeeze(-1)
+                spec.append(['sal', put(a), put(b), bool(fl.set_restrictions), bool(fl.add_init_f0)])
+            else:
+                spec.append(['sal', put(fl.a), put(fl.b), bool(fl.set_restrictions), bool(fl.add_init_f0)])
+        else:
+            raise NotImplementedError(type(fl))
+    return spec
+
+
+def dropout_off(model):
+    for m in model.modules():
+        if 'Dropout' in type(m).__name__:
+            m.eval()
+
+
+def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=None):
+    store = {}
+    model.set_is_training(True)
+    for prm in model.parameters():
+        prm.grad = None
+    E, ELL, KLD = model.ELBO(X, Y)
+    E.backward()
+    store['X'], store['Y'] = X.numpy(), Y.numpy()
+    store['Xte'], store['Yte'] = Xte.numpy(), Yte.numpy()
+    store['ELBO'], store['ELL'], store['KLD'] = E.item(), ELL.item(), KLD.item()
+    names = []
+    for n, prm in model.named_parameters():
+        store['param:' + n] = prm.detach().numpy().copy()
+        store['grad:' + n] = (torch.zeros_like(prm) if prm.grad is None else prm.grad).numpy().copy()
+        names.append(n)
+    with torch.no_grad():
+        mu, v = model.marginal_variational_qf_parameters(X, diagonal=True, is_duvenaud=False)
+        store['mu'], store['v'] = mu.view(-1).numpy(), v.view(-1).numpy()
+        flow = model.G_matrix[0]
+        comp = flow if isinstance(flow, CompositeFlow) else CompositeFlow([flow])
+        spec_tr = flow_to_spec(comp, store, X, 'fl')
+        spec_te = flow_to_spec(comp, store, Xte, 'flte')
+    model.set_is_training(False)
+    lp, mom = model.test_log_likelihood(Xte, Yte if likelihood != 'bernoulli' else Yte.long(),
+                                        return_moments=True, Y_std=torch.ones(1) * y_std, S_MC_NNet=None)
+    store['test_logp'] = float(lp.sum())
+    for i, mm in enumerate(mom):
+        if mm is not None:
+            store['test_moment%d' % i] = mm.detach().double().numpy().reshape(-1) if likelihood != 'bernoulli' \
+                else mm.detach().double().numpy()
+    model.set_is_training(True)
+    meta = {'name': name, 'likelihood': likelihood, 'N': float(model.N), 'M': int(model.M), 'y_std': y_std,
+            'n_quad': int(cg.quad_points), 'flow_train': spec_tr, 'flow_test': spec_te, 'param_names': names,
+            'id_flow': id_flow, 'dtype': 'float64'}
+    if extra:
+        meta.update(extra)
+    store['meta'] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **store)
+    print('%-34s ELBO % .12e  ELL % .12e  KLD % .12e  test_logp % .12e' % (name, store['ELBO'], store['ELL'],
+                                                                          store['KLD'], store['test_logp']))
+
+
+def synthetic_regression(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, d, generator=g)
+    w = torch.randn(d, generator=g)
+    y = torch.sinh(0.7 * (X @ w) / d ** 0.5) + 0.1 * torch.randn(n, generator=g)
+    y = (y - y.mean()) / y.std()
+    return X, y.view(-1, 1)
+
+
+def synthetic_classification(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, d, generator=g)
+    w = torch.randn(d, generator=g)
+    pr = 0.5 * (1 + torch.erf((X @ w) / d ** 0.5 / 2 ** 0.5))
+    y = (pr > torch.rand(n, generator=g)).double()
+    return X, y.view(-1, 1)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    Xb, Yb, Xbt, Ybt, ysb = load_uci('boston')
+    Xp, Yp, Xpt, Ypt, ysp = load_uci('power')
+    print('boston', tuple(Xb.shape), tuple(Xbt.shape), 'power', tuple(Xp.shape), tuple(Xpt.shape))
+    Nb, Np = Xb.shape[0], Xp.shape[0]
+
+    # cfg1: SVGP boston, init (P0) and mid-training (P1)
+    m = build('SVGP', Xb, 100, Nb)
+    record('boston_svgp_p0', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_linear')
+    randomise(m, 11)
+    record('boston_svgp_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_linear')
+
+    # identity-flow KAT: TGP with SAL(2) at init == SVGP closed form
+    m = build('TGP', Xb, 100, Nb, SAL(2))
+    record('boston_tgp_sal2_p0', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
+    randomise(m, 12)
+    record('boston_tgp_sal2_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
+
+    # cfg2: TGP StepTanhL(1,3); and the shipped boston architecture StepTanhL(10,2) (exp_config.py:31-41)
+    torch.manual_seed(3); np.random.seed(3)  # noqa: E702
+    m = build('TGP', Xb, 100, Nb, StepTanhL(1, 3, add_f0=True), seed=3)
+    randomise(m, 13)
+    record('boston_tgp_steptanh13_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
+    m = build('TGP', Xb, 100, Nb, StepTanhL(10, 2, add_f0=True), seed=4)
+    randomise(m, 14)
+    record('boston_tgp_steptanh102_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
+
+    # power: shipped TGP architecture SAL(2) (exp_config.py:45-55), first 2048 training rows as the minibatch
+    m = build('TGP', Xp, 100, Np, SAL(2), seed=5)
+    randomise(m, 15)
+    record('power_tgp_sal2_p1', m, Xp[:2048], Yp[:2048], Xpt[:256], Ypt[:256], ysp, 'gauss_nonlinear')
+
+    # cfg3: ID_TGP.  boston SAL(1)+MLP(13->25->1,tanh,p=.5); power SAL(3)+MLP(4->50->50->1,relu,p=.25)
+    for tag, (X, Y, Xt, Yt, ys), nb, cfgd, sd in (
+            ('boston', (Xb, Yb, Xbt, Ybt, ysb), 1,
+             dict(hidden_activation='tanh', num_hidden_layers=1, dropout=0.5, batch_norm=0, hidden_dim=25), 6),
+            ('power', (Xp[:1024], Yp[:1024], Xpt[:128], Ypt[:128], ysp), 3,
+             dict(hidden_activation='relu', num_hidden_layers=2, dropout=0.25, batch_norm=0, hidden_dim=50), 7)):
+        spec = SAL(nb, input_dependent=True, input_dim=X.shape[1], inference='MC_dropout', **cfgd)
+        torch.manual_seed(sd); np.random.seed(sd)  # noqa: E702
+        fl = instance_flow(spec)
+        fl.turn_off_initializer_parameters()
+        m = build('TGP', X, 100, float(X.shape[0]), fl, seed=sd)
+        randomise(m, 20 + sd)
+        dropout_off(m)     # deterministic MLP (dropout masks come from the global RNG)
+        record('%s_idtgp_nodrop_p1' % tag, m, X, Y, Xt, Yt, ys, 'gauss_nonlinear', id_flow=True)
+
+    # cfg4-like, small: D=8, M=64, StepTanhL(1,3)
+    Xs, Ys = synthetic_regression(768, 8, 1234)
+    m = build('TGP', Xs[:512], 64, 5000.0, StepTanhL(1, 3, add_f0=True), seed=8)
+    randomise(m, 18)
+    record('synth_reg_d8_m64_p1', m, Xs[:512], Ys[:512], Xs[512:], Ys[512:], 1.7, 'gauss_nonlinear')
+
+    # cfg5-like, small: Bernoulli, D=16, M=48, SAL(1)
+    Xc, Yc = synthetic_classification(640, 16, 4321)
+    cg.quad_points = 100
+    m = build('TGP', Xc[:512], 48, 3000.0, SAL(1), likelihood=Bernoulli(), seed=9)
+    randomise(m, 19)
+    record('synth_clf_d16_m48_p1', m, Xc[:512], Yc[:512], Xc[512:], Yc[512:], 1.0, 'bernoulli')
+
+    # jitter ladder: duplicated inducing rows make K_zz singular -> reference adds 1e-8 (utils.py:256-268)
+    m = build('SVGP', Xb, 40, Nb, seed=10)
+    randomise(m, 21)
+    with torch.no_grad():
+        m.Z[0, 1] = m.Z[0, 0]
+        m.Z[0, 3] = m.Z[0, 2]
+    record('boston_svgp_jitter', m, Xb[:128], Yb[:128], Xbt, Ybt, ysb, 'gauss_linear', extra={'expects_jitter': True})
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,104 @@
+"""Load `tests/golden/*.npz` (written by oracle/make_golden.py) into oracle-style parameter dicts."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False)
+        self.meta = json.loads(str(self.z['meta']))
+
+    def t(self, key, dtype=torch.float64):
+        return torch.tensor(np.asarray(self.z[key]), dtype=dtype)
+
+    def _flow(self, spec, dtype, leaf_cache):
+        def get(k):
+            if k not in leaf_cache:
+                leaf_cache[k] = self.t(k, dtype)
+            return leaf_cache[k]
+        layers = []
+        for lay in spec:
+            if lay[0] == 'identity':
+                layers.append(('identity',))
+            elif lay[0] == 'affine':
+                layers.append(('affine', get(lay[1]), get(lay[2]), lay[3]))
+            elif lay[0] == 'tanh_step':
+                layers.append(('tanh_step', [tuple(get(k) for k in st) for st in lay[1]], lay[2]))
+            elif lay[0] == 'sal':
+                layers.append(('sal', get(lay[1]), get(lay[2]), lay[3], lay[4]))
+        return layers
+
+    def oracle_params(self, which='train', dtype=torch.float64):
+        p = {}
+        for n in self.meta['param_names']:
+            a = self.t('param:' + n, dtype)
+            if n == 'Z':
+                p['Z'] = a[0]
+            elif n.endswith('raw_lengthscale'):
+                p['raw_lengthscale'] = a.view(-1)
+            elif n.endswith('raw_outputscale'):
+                p['raw_outputscale'] = a.view(())
+            elif n.endswith('variational_mean'):
+                p['m'] = a[0]
+            elif n.endswith('chol_variational_covar'):
+                p['L_raw'] = a[0]
+            elif n.endswith('log_var_noise'):
+                p['log_var_noise'] = a.view(())
+        if 'log_var_noise' not in p:       # Bernoulli has no noise parameter
+            p['log_var_noise'] = torch.zeros((), dtype=dtype)
+        self._leaf = {}
+        p['flow'] = self._flow(self.meta['flow_train' if which == 'train' else 'flow_test'], dtype, self._leaf)
+        return p
+
+    def ref_grads(self):
+        """name -> reference gradient, keyed like oracle.leaf_params (global scalars only)."""
+        g = {}
+        names = self.meta['param_names']
+        for n in names:
+            a = self.t('grad:' + n)
+            if n == 'Z':
+                g['Z'] = a[0]
+            elif n.endswith('raw_lengthscale'):
+                g['raw_lengthscale'] = a.view(-1)
+            elif n.endswith('raw_outputscale'):
+                g['raw_outputscale'] = a.view(())
+            elif n.endswith('variational_mean'):
+                g['m'] = a[0]
+            elif n.endswith('chol_variational_covar'):
+                g['L_raw'] = a[0]
+            elif n.endswith('log_var_noise'):
+                g['log_var_noise'] = a.view(())
+        # flow scalars, in module order == oracle layer order
+        if not self.meta['id_flow']:
+            flow_names = [n for n in names if n.startswith('G_matrix')]
+            vals = [self.t('grad:' + n).view(()) for n in flow_names]
+            keys = []
+            for i, lay in enumerate(self.meta['flow_train']):
+                if lay[0] == 'affine':
+                    keys += ['flow%d.a' % i, 'flow%d.b' % i]
+                elif lay[0] == 'tanh_step':
+                    for j in range(len(lay[1])):
+                        keys += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
+                elif lay[0] == 'sal':
+                    keys += ['flow%d.a' % i, 'flow%d.b' % i]
+            assert len(keys) == len(vals), (keys, flow_names)
+            g.update(dict(zip(keys, vals)))
+        return g
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).reshape(-1)
+    b = torch.as_tensor(b, dtype=torch.float64).reshape(-1)
+    den = float(b.norm())
+    return float((a - b).norm()) / (den if den > 0 else 1.0)

@@ -1,0 +1,67 @@
+"""O2 (oracle/tgp_oracle.py) must reproduce every fixture the unmodified reference produced (O1)."""
+import pytest
+import torch
+
+from oracle import tgp_oracle as O
+from tests.golden_util import Golden, golden_names, rel_err
+
+TOL = 1e-11      # L2-relative; the oracle replays the reference's own torch ops, so it should be ~1e-14
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_elbo_marginals_and_grads(name):
+    g = Golden(name)
+    p = g.oracle_params('train')
+    X, Y = g.t('X'), g.t('Y').view(-1)
+    lik, nq = g.meta['likelihood'], g.meta['n_quad']
+    mu, v = O.qf_marginals(X, p)
+    assert rel_err(mu, g.t('mu')) < TOL
+    assert rel_err(v, g.t('v')) < TOL
+    E, ELL, KLD, rows, grads = O.elbo_and_grads(X, Y, p, g.meta['N'], lik, nq)
+    assert rel_err(E, g.t('ELBO')) < TOL
+    assert rel_err(ELL, g.t('ELL')) < TOL
+    assert rel_err(KLD, g.t('KLD')) < TOL
+    ref = g.ref_grads()
+    for k, gr in ref.items():
+        assert rel_err(grads[k], gr) < 1e-9, k
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_test_log_likelihood_and_moments(name):
+    g = Golden(name)
+    p = g.oracle_params('test')
+    Xt, Yt = g.t('Xte'), g.t('Yte').view(-1)
+    lik = g.meta['likelihood']
+    lp, mom = O.test_log_likelihood(Xt, Yt, p, torch.tensor(g.meta['y_std'], dtype=torch.float64), lik,
+                                    g.meta['n_quad'])
+    assert rel_err(lp, g.t('test_logp')) < TOL
+    if lik == 'bernoulli':
+        assert rel_err(mom[0].double(), g.t('test_moment0')) < 1e-6      # reference computes these in FP32
+    else:
+        assert rel_err(mom[0], g.t('test_moment0')) < TOL
+        assert rel_err(mom[1], g.t('test_moment1')) < TOL
+
+
+def test_identity_flow_kat():
+    """SAL at its initial parameters is the identity: TGP quadrature ELBO == SVGP closed form."""
+    a, b = Golden('boston_svgp_p0'), Golden('boston_tgp_sal2_p0')
+    assert abs(float(a.z['ELBO']) - float(b.z['ELBO'])) < 1e-9 * abs(float(a.z['ELBO']))
+    assert abs(float(a.z['ELBO']) - (-6294.0125254488)) < 1e-6     # value recorded in BASELINE.md §4
+
+
+def test_jitter_fixture_takes_the_ladder():
+    g = Golden('boston_svgp_jitter')
+    p = g.oracle_params('train')
+    Kzz = O.rbf_ard(p['Z'], p['Z'], p['raw_lengthscale'], p['raw_outputscale'])
+    _, _, jit = O.psd_safe_cholesky(Kzz)
+    assert jit > 0
+
+
+def test_row_shards_sum_to_single():
+    g = Golden('synth_reg_d8_m64_p1')
+    p = g.oracle_params('train')
+    X, Y = g.t('X'), g.t('Y').view(-1)
+    E1 = O.elbo(X, Y, p, g.meta['N'], g.meta['likelihood'], g.meta['n_quad'])[0]
+    for world in (2, 4, 8):
+        Ew = O.elbo_rows_sharded(X, Y, p, g.meta['N'], world, g.meta['likelihood'], g.meta['n_quad'])[0]
+        assert rel_err(Ew, E1) < 1e-12
