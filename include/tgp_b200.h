@@ -1,0 +1,132 @@
+/* tgp_b200.h — C-ABI of the B200-native minibatch-ELBO / test-NLL path for SVGP / TGP / ID_TGP.
+ *
+ * The reference (jmaronas/TGP.pytorch) has no FFI: the path is plain Python method calls.  Each entry point
+ * below names the reference method (file:line under /root/reference/code/dsp) whose arithmetic it replaces; the
+ * Python host classes in tgp/pytorch_b200/dsp keep the reference's class surface and call these through ctypes
+ * (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain C, POD structs, raw DEVICE pointers unless a field says "host"; no torch types;
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *  - the caller owns every buffer; the library never allocates device memory.  Workspaces are sized by the
+ *    *_bytes() queries and carved deterministically, so the same workspace can be reused every step;
+ *  - return 0 = ok; < 0 = usage / launch error (text from tgp_last_error());
+ *  - one output GP per call (the reference's Dy > 1 case is a loop over outputs), whitened q(u);
+ *  - dtype: TGP_F64 is what the reference's main.py runs (set_maximum_precission, config.py:37-46).
+ */
+#ifndef TGP_B200_H
+#define TGP_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { TGP_F64 = 0, TGP_F32 = 1 };
+enum { TGP_LIK_GAUSS_LINEAR = 0,     /* likelihoods/GaussianLinearMean.py:60-87   (SVGP, closed form)      */
+       TGP_LIK_GAUSS_NONLINEAR = 1,  /* likelihoods/GaussianNonLinearMean.py:113-150 (Gauss-Hermite)       */
+       TGP_LIK_BERNOULLI = 2 };      /* likelihoods/Bernoulli.py:50-95                                      */
+enum { TGP_FLOW_IDENTITY = 0,        /* models/flow.py:296-307                                              */
+       TGP_FLOW_AFFINE = 1,          /* models/flow.py:330-340   params [a, b]                              */
+       TGP_FLOW_TANH_STEP = 2,       /* models/flow.py:1096-1103 over :755-773   params n_steps x [a,b,c,d] */
+       TGP_FLOW_SAL = 3 };           /* models/flow.py:904-905, 965-977   params [a, b]                     */
+enum { TGP_FLOW_RESTRICT = 1,        /* set_restrictions: softplus on a (affine) / b (sinh-arcsinh)         */
+       TGP_FLOW_ADD_F0 = 2,          /* add_init_f0                                                         */
+       TGP_FLOW_PER_ROW = 4 };       /* parameters come from the per-row matrix (input-dependent flow)      */
+#define TGP_MAX_LAYERS 64
+
+typedef struct TgpFlowLayer {
+    int kind;      /* TGP_FLOW_*                                                     */
+    int flags;     /* TGP_FLOW_RESTRICT | TGP_FLOW_ADD_F0 | TGP_FLOW_PER_ROW         */
+    int n_steps;   /* TANH_STEP: number of tanh terms                                */
+    int p0;        /* first parameter: index into theta, or column of the row matrix */
+} TgpFlowLayer;
+
+typedef struct TgpModel {            /* host struct; describes one output GP */
+    int dtype;                       /* TGP_F64 (TGP_F32 reserved)                                         */
+    int M, D;                        /* inducing points, input dimension                                   */
+    int likelihood;                  /* TGP_LIK_*                                                          */
+    int n_quad;                      /* Gauss-Hermite points (config.py:45,58: 100 in FP64, 50 in FP32)    */
+    int n_theta;                     /* global flow scalars                                                */
+    int n_rowparams;                 /* per-row flow parameters (ID_TGP), 0 otherwise                      */
+    int n_layers;
+    TgpFlowLayer layers[TGP_MAX_LAYERS];
+} TgpModel;
+
+typedef struct TgpParams {           /* device pointers to the model parameters (same shapes as the reference's) */
+    const void* Z;                   /* (M, D)     sparse_MF_SP.Z[dy]                                      */
+    const void* raw_lengthscale;     /* (D,)       covariance_function.base_kernel.raw_lengthscale[dy,0]   */
+    const void* raw_outputscale;     /* (1,)       covariance_function.raw_outputscale[dy]                 */
+    const void* m;                   /* (M,)       q_U.variational_mean[dy]                                */
+    const void* L_raw;               /* (M, M)     q_U.chol_variational_covar[dy] (lower-masked at use)    */
+    const void* log_var_noise;       /* (1,)       likelihood.log_var_noise[dy] (unused for Bernoulli)     */
+    const void* theta;               /* (n_theta,) flow scalars in descriptor order                        */
+} TgpParams;
+
+/* layout (in doubles) of the packed buffer that ranks all-reduce between tgp_qf_backward and tgp_chain_backward */
+typedef struct TgpReduceLayout {
+    long ell_sum, dlogvar, dos, dls, dtheta, dm, dZ, Gbar, Cbar, total;
+} TgpReduceLayout;
+
+const char* tgp_last_error(void);
+int tgp_version(void);
+
+size_t tgp_step_workspace_bytes(const TgpModel* model);
+size_t tgp_batch_workspace_bytes(const TgpModel* model, long R);
+int tgp_reduce_layout(const TgpModel* model, TgpReduceLayout* out);
+
+/* K_zz -> psd-safe Cholesky -> explicit L^-1, C = L_S^T L^-1, whitened KL.
+ * Replaces sparse_MF_SP.py:316,330,344-346 and KLD :406-431, utils.py:222-270 (the wrapper drives the jitter
+ * ladder: status[0] > 0 is the 1-based index of the first non-positive pivot).  kl_out, status: device. */
+int tgp_prepare(const TgpModel* model, const TgpParams* params, double jitter, void* step_ws, double* kl_out,
+                int* status, void* stream);
+
+/* q(f) marginals of R rows: mu, v (device, length R).  Saves A = K L^-T and B = K C^T in batch_ws for the backward.
+ * Replaces sparse_MF_SP.marginal_variational_qf_parameters (sparse_MF_SP.py:274-396, whitened diagonal branch). */
+int tgp_qf_forward(const TgpModel* model, const void* step_ws, void* batch_ws, const void* X, long R, void* mu,
+                   void* v, void* stream);
+
+/* Expected log-likelihood of R rows given (mu, v): flow o Gauss-Hermite o likelihood, with analytic gradients.
+ * Replaces likelihood.expected_log_prob (GaussianNonLinearMean.py:113-150, GaussianLinearMean.py:60-87,
+ * Bernoulli.py:50-95) and sparse_MF_SP.ELL's N/MB scaling (sparse_MF_SP.py:601-626; `scale` = N/MB_global).
+ * Outputs: ell_rows (R, unscaled), g_mu / g_v (R, scaled), drowparams (R, n_rowparams, scaled) and, ACCUMULATED
+ * into the caller-zeroed reduce buffer: ell_sum (unscaled), dlogvar, dtheta (scaled).  want_grad = 0 skips grads. */
+int tgp_ell_forward(const TgpModel* model, const TgpParams* params, const void* mu, const void* v, const void* Y,
+                    const void* rowparams, long R, double scale, const void* quad_t, const void* quad_w,
+                    int want_grad, void* ell_rows, void* g_mu, void* g_v, void* drowparams, double* reduce_buf,
+                    void* stream);
+
+/* Backward of tgp_qf_forward for upstream per-row gradients (g_mu, g_v): accumulates the pre-chain quantities
+ * (Gbar = dELL/dL^-1, Cbar = dELL/dC, dm, dZ, dlengthscale, doutputscale from the K_xz side) into reduce_buf.
+ * Replaces autograd through sparse_MF_SP.py:313-382 (trainer_base.py:341).  K_xz tiles are recomputed. */
+int tgp_qf_backward(const TgpModel* model, const TgpParams* params, const void* step_ws, void* batch_ws,
+                    const void* X, long R, const void* g_mu, const void* g_v, double* reduce_buf, void* stream);
+
+/* The replicated O(M^3) chain after the all-reduce: (Gbar, Cbar) -> L_S, L^-1 -> L -> K_zz -> Z, lengthscale,
+ * outputscale, plus the KL gradient.  Outputs are d(gE*ELL + gK*KL)/dparam in the raw parameterisation:
+ * dZ (M,D), draw_lengthscale (D), draw_outputscale (1), dm (M), dL_raw (M,M; upper triangle exactly 0),
+ * dlog_var_noise (1), dtheta (n_theta).  Replaces autograd's cholesky_backward / triangular_solve_backward.
+ * g_dev: optional DEVICE pointer to {gE, gK}; when non-NULL it overrides the host scalars (no host sync needed to
+ * read autograd's upstream gradients). */
+int tgp_chain_backward(const TgpModel* model, const TgpParams* params, void* step_ws, const double* reduce_buf,
+                       double gE, double gK, const double* g_dev, void* dZ, void* draw_lengthscale, void* draw_outputscale, void* dm,
+                       void* dL_raw, void* dlog_var_noise, void* dtheta, void* stream);
+
+/* Test log-likelihood rows and predictive moments given (mu, v) (sparse_MF_SP.py:637-825; marginal_moments of the
+ * three likelihoods).  rowparams: (R, n_mc, n_rowparams) for MC-dropout flows, n_mc = 1 otherwise.
+ * bern_std: device scalar, batch-wide std of v (Bernoulli.py:120 defect, kept for parity). */
+int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu, const void* v, const void* Y,
+                  const void* rowparams, long R, int n_mc, double y_std, const void* quad_t, const void* quad_w,
+                  const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream);
+
+/* Test hook: the FP64 DMMA GEMM that carries every contraction (C = alpha*Aop*Bop^T + beta*C). */
+int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_layout, const double* B, long ldb,
+                       int b_layout, double* C, long ldc, double alpha, double beta, int a_tri, int b_tri,
+                       int c_lower, void* stream);
+/* Test hook: copies L, L^-1, C (each M x M, row-major, ld = M) out of a prepared step workspace. */
+int tgp_debug_export_step(const TgpModel* model, const void* step_ws, double* L, double* Linv, double* C,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,49 @@
+"""Bridges oracle-style parameter dicts (tests/golden_util.Golden.oracle_params) to the CUDA engine."""
+import torch
+
+from tgp.pytorch_b200.engine import Engine, FlowLayout
+
+
+def flow_layout_and_params(layers, device):
+    """oracle layer list -> (FlowLayout, theta tensor, rowparams tensor or None, leaf-name list for theta)."""
+    desc, theta, rowcols, names = [], [], [], []
+    for i, lay in enumerate(layers):
+        if lay[0] == 'identity':
+            continue
+        if lay[0] == 'affine':
+            desc.append(dict(kind='affine', restrict=lay[3]))
+            theta += [lay[1].reshape(()), lay[2].reshape(())]
+            names += ['flow%d.a' % i, 'flow%d.b' % i]
+        elif lay[0] == 'tanh_step':
+            desc.append(dict(kind='tanh_step', n_steps=len(lay[1]), add_f0=lay[2]))
+            for j, st in enumerate(lay[1]):
+                theta += [t.reshape(()) for t in st]
+                names += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
+        elif lay[0] == 'sal':
+            per_row = lay[1].dim() > 0
+            desc.append(dict(kind='sal', restrict=lay[3], add_f0=lay[4], per_row=per_row))
+            if per_row:
+                rowcols += [lay[1], lay[2]]
+            else:
+                theta += [lay[1].reshape(()), lay[2].reshape(())]
+                names += ['flow%d.a' % i, 'flow%d.b' % i]
+    fl = FlowLayout(desc)
+    th = torch.stack(theta).to(device) if theta else torch.zeros(0, dtype=torch.float64, device=device)
+    rp = torch.stack(rowcols, dim=1).contiguous().to(device) if rowcols else None
+    return fl, th.double().contiguous(), rp, names
+
+
+def engine_inputs(p, device):
+    dev = torch.device(device)
+    f = lambda t: t.detach().to(dev).double().contiguous()  # noqa: E731
+    return dict(Z=f(p['Z']), raw_ls=f(p['raw_lengthscale'].reshape(-1)), raw_os=f(p['raw_outputscale'].reshape(1)),
+                m=f(p['m']), L_raw=f(p['L_raw']), log_var_noise=f(p['log_var_noise'].reshape(1)))
+
+
+def make_engine(p, likelihood, n_quad, device):
+    fl, theta, rowp, names = flow_layout_and_params(p['flow'], device)
+    if likelihood == 'gauss_linear':
+        fl = FlowLayout([])
+        theta = torch.zeros(0, dtype=torch.float64, device=device)
+    eng = Engine(p['Z'].shape[0], p['Z'].shape[1], likelihood, n_quad, fl, device)
+    return eng, theta, rowp, names

@@ -1,0 +1,82 @@
+"""ctypes binding of `libtgp_b200.so` (the C-ABI declared in include/tgp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtgp_b200.so')
+
+TGP_F64, TGP_F32 = 0, 1
+LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
+FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL = 0, 1, 2, 3
+FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
+MAX_LAYERS = 64
+
+
+class TgpFlowLayer(C.Structure):
+    _fields_ = [('kind', C.c_int), ('flags', C.c_int), ('n_steps', C.c_int), ('p0', C.c_int)]
+
+
+class TgpModel(C.Structure):
+    _fields_ = [('dtype', C.c_int), ('M', C.c_int), ('D', C.c_int), ('likelihood', C.c_int), ('n_quad', C.c_int),
+                ('n_theta', C.c_int), ('n_rowparams', C.c_int), ('n_layers', C.c_int),
+                ('layers', TgpFlowLayer * MAX_LAYERS)]
+
+
+class TgpParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('Z', 'raw_lengthscale', 'raw_outputscale', 'm', 'L_raw', 'log_var_noise',
+                                          'theta')]
+
+
+class TgpReduceLayout(C.Structure):
+    _fields_ = [(n, C.c_long) for n in ('ell_sum', 'dlogvar', 'dos', 'dls', 'dtheta', 'dm', 'dZ', 'Gbar', 'Cbar',
+                                        'total')]
+
+
+# name -> (restype, argtypes); the exported-symbol test walks this table against include/tgp_b200.h
+_P, _I, _L, _D = C.c_void_p, C.c_int, C.c_long, C.c_double
+SIGNATURES = {
+    'tgp_last_error': (C.c_char_p, []),
+    'tgp_version': (_I, []),
+    'tgp_step_workspace_bytes': (C.c_size_t, [C.POINTER(TgpModel)]),
+    'tgp_batch_workspace_bytes': (C.c_size_t, [C.POINTER(TgpModel), _L]),
+    'tgp_reduce_layout': (_I, [C.POINTER(TgpModel), C.POINTER(TgpReduceLayout)]),
+    'tgp_prepare': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _D, _P, _P, _P, _P]),
+    'tgp_qf_forward': (_I, [C.POINTER(TgpModel), _P, _P, _P, _L, _P, _P, _P]),
+    'tgp_ell_forward': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _P, _L, _D, _P, _P, _I, _P, _P, _P,
+                             _P, _P, _P]),
+    'tgp_qf_backward': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _L, _P, _P, _P, _P]),
+    'tgp_chain_backward': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _D, _D, _P, _P, _P, _P, _P, _P, _P,
+                                _P, _P]),
+    'tgp_test_rows': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _P, _L, _I, _D, _P, _P, _P, _P, _P,
+                           _P, _P]),
+    'tgp_debug_gemm_f64': (_I, [_I, _I, _I, _P, _L, _I, _P, _L, _I, _P, _L, _D, _D, _I, _I, _I, _P]),
+    'tgp_debug_export_step': (_I, [C.POINTER(TgpModel), _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library once; raises if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('%s not found: build it with __graft_entry__.build(); there is no CPU fallback' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().tgp_last_error().decode()
+        if rc == -1 or rc == -2:
+            raise ValueError('%s: %s' % (what, msg))
+        raise RuntimeError('%s failed (%d): %s' % (what, rc, msg))

@@ -1,0 +1,51 @@
+// Shared helpers for the tgp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#define TGP_WARP 32
+
+namespace tgp {
+
+// last error text, returned by tgp_last_error()
+extern char g_last_error[512];
+
+inline int set_error(int code, const char* msg) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+    return code;
+}
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+        return -100;
+    }
+    return 0;
+}
+
+#define TGP_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__host__ __device__ inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+
+// softplus and its derivative as torch.nn.functional.softplus (beta=1, threshold=20) evaluates them
+__device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
+__device__ __forceinline__ double sigmoid_d(double x) { return x > 20.0 ? 1.0 : 1.0 / (1.0 + exp(-x)); }
+
+}  // namespace tgp

@@ -1,0 +1,313 @@
+// C-ABI entry points (include/tgp_b200.h) — host-side orchestration of the sm_100a kernels.
+#include "../../../include/tgp_b200.h"
+#include "common.cuh"
+#include "gemm_f64.cuh"
+#include "step_kernels.cuh"
+#include "row_kernels.cuh"
+#include "backward_kernels.cuh"
+
+namespace tgp {
+char g_last_error[512] = "";
+
+constexpr long ROW_CHUNK = 8192;     // rows whose K / Kbar tiles are staged at once (L2-sized for M = 1024)
+
+struct BatchView { double *AB, *Kbuf, *Kbar; long Rc; };
+
+inline long chunk_rows(long R) { return R < ROW_CHUNK ? R : ROW_CHUNK; }
+inline long even(long x) { return (x + 1) / 2 * 2; }
+
+inline size_t batch_ws_doubles(int M, long R) {
+    const long Rc = chunk_rows(R);
+    return (size_t)even(R * 2 * M) + 2 * (size_t)even(Rc * M) + 16;
+}
+
+inline BatchView carve_batch(void* ws, int M, long R) {
+    BatchView b;
+    b.Rc = chunk_rows(R);
+    double* p = reinterpret_cast<double*>(ws);
+    b.AB = p; p += even(R * 2 * M);
+    b.Kbuf = p; p += even(b.Rc * M);
+    b.Kbar = p;
+    return b;
+}
+
+inline TgpReduceLayout reduce_layout(const TgpModel* md) {
+    TgpReduceLayout l;
+    const long Mp = pad_M(md->M);
+    l.ell_sum = 0; l.dlogvar = 1; l.dos = 2;
+    l.dls = 4;
+    l.dtheta = l.dls + even(md->D);
+    l.dm = l.dtheta + even(md->n_theta);
+    l.dZ = l.dm + even(md->M);
+    l.Gbar = l.dZ + even((long)md->M * md->D);
+    l.Cbar = l.Gbar + Mp * Mp;
+    l.total = l.Cbar + Mp * Mp;
+    return l;
+}
+
+inline int validate(const TgpModel* md) {
+    if (!md) return set_error(-1, "model is NULL");
+    if (md->dtype != TGP_F64) return set_error(-1, "only TGP_F64 is implemented in this build");
+    if (md->M < 1 || md->D < 1) return set_error(-1, "M and D must be positive");
+    if (md->n_layers < 0 || md->n_layers > TGP_MAX_LAYERS) return set_error(-1, "too many flow layers");
+    if (md->n_theta < 0 || md->n_theta > MAX_THETA) return set_error(-1, "too many global flow parameters");
+    if (md->n_rowparams < 0 || md->n_rowparams > MAX_ROWP) return set_error(-1, "too many per-row flow parameters");
+    if (md->likelihood < 0 || md->likelihood > 2) return set_error(-1, "unknown likelihood");
+    if (md->likelihood == TGP_LIK_GAUSS_LINEAR && md->n_layers != 0)
+        return set_error(-1, "the closed-form Gaussian likelihood takes an identity flow");
+    if (md->likelihood != TGP_LIK_GAUSS_LINEAR && (md->n_quad < 1 || md->n_quad > 4096))
+        return set_error(-1, "n_quad out of range");
+    return 0;
+}
+
+inline void fill_flow(FlowDesc& fd, const TgpModel* md) {
+    fd.n_layers = md->n_layers;
+    for (int i = 0; i < md->n_layers; ++i) fd.layers[i] = md->layers[i];
+}
+
+inline int row_grid(long R) {
+    const long blocks = cdiv(R, ROW_THREADS / 32);
+    return (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+}
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" {
+
+const char* tgp_last_error(void) { return g_last_error; }
+int tgp_version(void) { return 100; }
+
+size_t tgp_step_workspace_bytes(const TgpModel* md) {
+    if (validate(md)) return 0;
+    return step_ws_doubles(md->M, md->D) * sizeof(double);
+}
+
+size_t tgp_batch_workspace_bytes(const TgpModel* md, long R) {
+    if (validate(md) || R < 0) return 0;
+    return batch_ws_doubles(md->M, R) * sizeof(double);
+}
+
+int tgp_reduce_layout(const TgpModel* md, TgpReduceLayout* out) {
+    TGP_TRY(validate(md));
+    if (!out) return set_error(-1, "out is NULL");
+    *out = reduce_layout(md);
+    return 0;
+}
+
+int tgp_prepare(const TgpModel* md, const TgpParams* p, double jitter, void* step_ws, double* kl_out, int* status,
+                void* stream) {
+    TGP_TRY(validate(md));
+    if (!p || !step_ws || !kl_out || !status) return set_error(-1, "NULL argument to tgp_prepare");
+    StepView v = carve_step(step_ws, md->M, md->D);
+    return run_prepare(v, (const double*)p->Z, (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale,
+                       (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, (cudaStream_t)stream);
+}
+
+int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, const void* X, long R, void* mu, void* v,
+                   void* stream) {
+    TGP_TRY(validate(md));
+    if (R <= 0) return 0;
+    if (!step_ws || !batch_ws || !X || !mu || !v) return set_error(-1, "NULL argument to tgp_qf_forward");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = md->M, D = md->D;
+    StepView s = carve_step(const_cast<void*>(step_ws), M, D);
+    BatchView b = carve_batch(batch_ws, M, R);
+    const double* Xd = (const double*)X;
+    for (long r0 = 0; r0 < R; r0 += b.Rc) {
+        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
+        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf, M, rc, M, 0.0, st));
+        // A = K L^-T   (Bop[n,k] = Linv[n,k], nonzero k <= n)
+        GemmArgs ga = make_gemm(rc, M, M, b.Kbuf, M, 0, s.Linv, s.Mp, 0, b.AB + r0 * 2 * M, 2 * M);
+        ga.b_tri = 1;
+        TGP_TRY(gemm_f64(ga, st));
+        // B = K C^T
+        GemmArgs gb = make_gemm(rc, M, M, b.Kbuf, M, 0, s.Cm, s.Mp, 0, b.AB + r0 * 2 * M + M, 2 * M);
+        TGP_TRY(gemm_f64(gb, st));
+    }
+    k_row_stats<<<row_grid(R), ROW_THREADS, 0, st>>>(b.AB, s.mvec, s.os, (int)R, M, (double*)mu, (double*)v);
+    return check_launch("k_row_stats");
+}
+
+int tgp_ell_forward(const TgpModel* md, const TgpParams* p, const void* mu, const void* v, const void* Y,
+                    const void* rowparams, long R, double scale, const void* quad_t, const void* quad_w, int want_grad,
+                    void* ell_rows, void* g_mu, void* g_v, void* drowparams, double* reduce_buf, void* stream) {
+    TGP_TRY(validate(md));
+    if (R <= 0) return 0;
+    if (!p || !mu || !v || !Y || !ell_rows || !reduce_buf) return set_error(-1, "NULL argument to tgp_ell_forward");
+    if (want_grad && (!g_mu || !g_v)) return set_error(-1, "g_mu / g_v required when want_grad");
+    if (md->n_rowparams > 0 && (!rowparams || (want_grad && !drowparams)))
+        return set_error(-1, "rowparams / drowparams required for input-dependent flows");
+    if (md->likelihood != TGP_LIK_GAUSS_LINEAR && (!quad_t || !quad_w)) return set_error(-1, "quadrature rule missing");
+    const TgpReduceLayout l = reduce_layout(md);
+    RowQuadArgs a;
+    a.R = (int)R; a.likelihood = md->likelihood; a.n_quad = md->n_quad; a.n_theta = md->n_theta;
+    a.n_rowp = md->n_rowparams; a.want_grad = want_grad; a.scale = scale;
+    a.mu = (const double*)mu; a.v = (const double*)v; a.y = (const double*)Y;
+    a.log_var_noise = (const double*)p->log_var_noise; a.theta = (const double*)p->theta;
+    a.rowp = md->n_rowparams > 0 ? (const double*)rowparams : nullptr;
+    a.qt = (const double*)quad_t; a.qw = (const double*)quad_w;
+    a.ell_rows = (double*)ell_rows; a.g_mu = (double*)g_mu; a.g_v = (double*)g_v;
+    a.ell_sum = reduce_buf + l.ell_sum; a.dlogvar = reduce_buf + l.dlogvar; a.dtheta = reduce_buf + l.dtheta;
+    a.drowp = (double*)drowparams;
+    fill_flow(a.flow, md);
+    k_row_quad<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("k_row_quad");
+}
+
+int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws, void* batch_ws, const void* X,
+                    long R, const void* g_mu, const void* g_v, double* reduce_buf, void* stream) {
+    TGP_TRY(validate(md));
+    if (R <= 0) return 0;
+    if (!p || !step_ws || !batch_ws || !X || !g_mu || !g_v || !reduce_buf)
+        return set_error(-1, "NULL argument to tgp_qf_backward");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = md->M, D = md->D;
+    StepView s = carve_step(const_cast<void*>(step_ws), M, D);
+    BatchView b = carve_batch(batch_ws, M, R);
+    const TgpReduceLayout l = reduce_layout(md);
+    const double* Xd = (const double*)X;
+    double* Gbar = reduce_buf + l.Gbar;
+    double* Cbar = reduce_buf + l.Cbar;
+    {
+        dim3 grid((unsigned)cdiv(M, ABB_COLS), (unsigned)cdiv(R, ABB_ROWS));
+        k_make_abbar<<<grid, ABB_COLS, 0, st>>>(b.AB, (const double*)g_mu, (const double*)g_v, s.mvec, R, M,
+                                                reduce_buf + l.dm, reduce_buf + l.dos);
+        TGP_TRY(check_launch("k_make_abbar"));
+    }
+    for (long r0 = 0; r0 < R; r0 += b.Rc) {
+        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
+        const double* ABc = b.AB + r0 * 2 * M;
+        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf, M, rc, M, 0.0, st));
+        // Kbar = Abar * Linv + Bbar * C     (Bop[n,k] = Linv[k,n], nonzero k >= n)
+        GemmArgs g1 = make_gemm(rc, M, M, ABc, 2 * M, 0, s.Linv, s.Mp, 1, b.Kbar, M);
+        g1.b_tri = 2;
+        TGP_TRY(gemm_f64(g1, st));
+        GemmArgs g2 = make_gemm(rc, M, M, ABc + M, 2 * M, 0, s.Cm, s.Mp, 1, b.Kbar, M, 1.0, 1.0);
+        TGP_TRY(gemm_f64(g2, st));
+        TGP_TRY(launch_kernel_grads(b.Kbar, M, Xd + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, reduce_buf + l.dZ,
+                                    reduce_buf + l.dls, reduce_buf + l.dos, st));
+        // Gbar += tril(Abar^T K),  Cbar += Bbar^T K      (reduction over the rows of the chunk)
+        GemmArgs g3 = make_gemm(M, M, rc, ABc, 2 * M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
+        g3.c_lower = 1;
+        TGP_TRY(gemm_f64(g3, st));
+        GemmArgs g4 = make_gemm(M, M, rc, ABc + M, 2 * M, 1, b.Kbuf, M, 1, Cbar, s.Mp, 1.0, 1.0);
+        TGP_TRY(gemm_f64(g4, st));
+    }
+    return 0;
+}
+
+int tgp_chain_backward(const TgpModel* md, const TgpParams* p, void* step_ws, const double* reduce_buf, double gE,
+                       double gK, const double* g_dev, void* dZ, void* draw_ls, void* draw_os, void* dm, void* dL_raw, void* dlogvar,
+                       void* dtheta, void* stream) {
+    TGP_TRY(validate(md));
+    if (!p || !step_ws || !reduce_buf || !dZ || !draw_ls || !draw_os || !dm || !dL_raw)
+        return set_error(-1, "NULL argument to tgp_chain_backward");
+    if (md->n_theta > 0 && !dtheta) return set_error(-1, "dtheta required");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = md->M, D = md->D, Mp = pad_M(md->M);
+    const size_t mm = (size_t)Mp * Mp;
+    StepView s = carve_step(step_ws, M, D);
+    const TgpReduceLayout l = reduce_layout(md);
+    const double* Cbar = reduce_buf + l.Cbar;
+    double* Gtot = s.Kzz;                          // K_zz's buffer is free after the factorisation
+    double* dZacc = s.S3;                          // (M*D) accumulators live at the head of S3 until Phi needs it
+
+    // dLS = tril(Linv * Cbar^T)
+    GemmArgs a1 = make_gemm(M, M, M, s.Linv, Mp, 0, Cbar, Mp, 0, s.S0, Mp);
+    a1.a_tri = 1; a1.c_lower = 1;
+    cudaMemsetAsync(s.S0, 0, mm * sizeof(double), st);
+    TGP_TRY(gemm_f64(a1, st));
+    // Gtot = Gbar + tril(LS * Cbar)
+    cudaMemcpyAsync(Gtot, reduce_buf + l.Gbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    GemmArgs a2 = make_gemm(M, M, M, s.LS, Mp, 0, Cbar, Mp, 1, Gtot, Mp, 1.0, 1.0);
+    a2.a_tri = 1; a2.c_lower = 1;
+    TGP_TRY(gemm_f64(a2, st));
+    // T1 = Gtot * Linv^T
+    GemmArgs a3 = make_gemm(M, M, M, Gtot, Mp, 0, s.Linv, Mp, 0, s.S1, Mp);
+    a3.a_tri = 1; a3.b_tri = 1;
+    TGP_TRY(gemm_f64(a3, st));
+    // Lbar = -tril(Linv^T * T1)
+    cudaMemsetAsync(s.S2, 0, mm * sizeof(double), st);
+    GemmArgs a4 = make_gemm(M, M, M, s.Linv, Mp, 1, s.S1, Mp, 1, s.S2, Mp, -1.0, 0.0);
+    a4.a_tri = 2; a4.c_lower = 1;
+    TGP_TRY(gemm_f64(a4, st));
+    // Phi = tril(L^T * Lbar), diagonal halved      (Murray 2016; equals torch's cholesky_backward)
+    cudaMemsetAsync(s.S3, 0, mm * sizeof(double), st);
+    GemmArgs a5 = make_gemm(M, M, M, s.L, Mp, 1, s.S2, Mp, 1, s.S3, Mp);
+    a5.a_tri = 2; a5.b_tri = 2; a5.c_lower = 1;
+    TGP_TRY(gemm_f64(a5, st));
+    k_halve_diag<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(s.S3, Mp, M);
+    // S1 = Phi * Linv ;  Kbar_zz = Linv^T * S1  (symmetrised on the fly by the gradient kernel)
+    GemmArgs a6 = make_gemm(M, M, M, s.S3, Mp, 0, s.Linv, Mp, 1, s.S1, Mp);
+    a6.a_tri = 1; a6.b_tri = 2;
+    TGP_TRY(gemm_f64(a6, st));
+    GemmArgs a7 = make_gemm(M, M, M, s.Linv, Mp, 1, s.S1, Mp, 1, s.S2, Mp);
+    a7.a_tri = 2;
+    TGP_TRY(gemm_f64(a7, st));
+    // K_zz -> Z (both index roles: factor 2 on the symmetrised matrix), lengthscale, outputscale.
+    // accumulators: start from the K_xz-side sums of the reduce buffer
+    dZacc = s.S3;   // Phi is dead now
+    cudaMemcpyAsync(dZacc, reduce_buf + l.dZ, (size_t)M * D * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    double* dls_acc = dZacc + even((long)M * D);
+    double* dos_acc = dls_acc + even(D);
+    cudaMemcpyAsync(dls_acc, reduce_buf + l.dls, (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(dos_acc, reduce_buf + l.dos, sizeof(double), cudaMemcpyDeviceToDevice, st);
+    TGP_TRY(launch_kernel_grads(s.S2, Mp, s.Zs, 1, s.Zs, s.ls, s.os, M, M, D, 1, 2.0, dZacc, dls_acc, dos_acc, st));
+    {
+        const int n = M * D > M ? M * D : M;
+        const int nn = n > md->n_theta ? n : md->n_theta;
+        k_finalize_small<<<(unsigned)cdiv(nn, 256), 256, 0, st>>>(
+            (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale, (const double*)p->m, M, D,
+            md->n_theta, gE, gK, g_dev, dls_acc, dos_acc, reduce_buf + l.dm, dZacc, reduce_buf + l.dlogvar,
+            reduce_buf + l.dtheta, (double*)dZ, (double*)draw_ls, (double*)draw_os, (double*)dm, (double*)dlogvar,
+            (double*)dtheta);
+        TGP_TRY(check_launch("k_finalize_small"));
+        k_finalize_LS<<<M, 256, 0, st>>>(s.S0, s.LS, Mp, M, gE, gK, g_dev, (double*)dL_raw);
+        TGP_TRY(check_launch("k_finalize_LS"));
+    }
+    return 0;
+}
+
+int tgp_test_rows(const TgpModel* md, const TgpParams* p, const void* mu, const void* v, const void* Y,
+                  const void* rowparams, long R, int n_mc, double y_std, const void* quad_t, const void* quad_w,
+                  const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream) {
+    TGP_TRY(validate(md));
+    if (R <= 0) return 0;
+    if (!p || !mu || !v || !logp_rows || !m1 || !m2) return set_error(-1, "NULL argument to tgp_test_rows");
+    if (n_mc < 1) return set_error(-1, "n_mc must be >= 1");
+    if (md->n_rowparams > 0 && !rowparams) return set_error(-1, "rowparams required for input-dependent flows");
+    if (md->likelihood == TGP_LIK_BERNOULLI && md->n_layers > 0 && !bern_std)
+        return set_error(-1, "bern_std required for Bernoulli with a non-identity flow");
+    RowTestArgs a;
+    a.R = (int)R; a.likelihood = md->likelihood; a.n_quad = md->n_quad; a.n_rowp = md->n_rowparams; a.n_mc = n_mc;
+    a.y_std = y_std;
+    a.mu = (const double*)mu; a.v = (const double*)v; a.y = (const double*)Y;
+    a.log_var_noise = (const double*)p->log_var_noise; a.theta = (const double*)p->theta;
+    a.rowp = md->n_rowparams > 0 ? (const double*)rowparams : nullptr;
+    a.qt = (const double*)quad_t; a.qw = (const double*)quad_w; a.bern_std = bern_std;
+    a.logp_rows = (double*)logp_rows; a.m1 = (double*)m1; a.m2 = (double*)m2;
+    fill_flow(a.flow, md);
+    k_row_test<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("k_row_test");
+}
+
+int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_layout, const double* B, long ldb,
+                       int b_layout, double* C, long ldc, double alpha, double beta, int a_tri, int b_tri, int c_lower,
+                       void* stream) {
+    GemmArgs g = make_gemm(M, N, K, A, lda, a_layout, B, ldb, b_layout, C, ldc, alpha, beta);
+    g.a_tri = a_tri; g.b_tri = b_tri; g.c_lower = c_lower;
+    return gemm_f64(g, (cudaStream_t)stream);
+}
+
+int tgp_debug_export_step(const TgpModel* md, const void* step_ws, double* L, double* Linv, double* C, void* stream) {
+    TGP_TRY(validate(md));
+    StepView s = carve_step(const_cast<void*>(step_ws), md->M, md->D);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (L) k_copy_strided<<<md->M, 256, 0, st>>>(s.L, s.Mp, L, md->M, md->M);
+    if (Linv) k_copy_strided<<<md->M, 256, 0, st>>>(s.Linv, s.Mp, Linv, md->M, md->M);
+    if (C) k_copy_strided<<<md->M, 256, 0, st>>>(s.Cm, s.Mp, C, md->M, md->M);
+    return check_launch("k_copy_strided");
+}
+
+}  // extern "C"

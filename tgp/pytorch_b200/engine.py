@@ -1,0 +1,232 @@
+"""Thin torch-facing wrapper over the C-ABI: owns workspaces, passes raw device pointers and the current stream.
+
+One `Engine` per (output GP, device).  Nothing here computes: every method enqueues kernels of
+`libtgp_b200.so` on `torch.cuda.current_stream()` and returns device tensors.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_KIND = {'identity': _lib.FLOW_IDENTITY, 'affine': _lib.FLOW_AFFINE, 'tanh_step': _lib.FLOW_TANH_STEP,
+         'sal': _lib.FLOW_SAL}
+_LIK = {'gauss_linear': _lib.LIK_GAUSS_LINEAR, 'gauss_nonlinear': _lib.LIK_GAUSS_NONLINEAR,
+        'bernoulli': _lib.LIK_BERNOULLI}
+
+
+class FlowLayout:
+    """Flat description of a composed flow G for the kernels.
+
+    `layers`: list of dicts {kind, restrict, add_f0, n_steps, per_row}.  Global parameters of all layers are packed
+    in descriptor order into `theta`; per-row (input-dependent) parameters into the columns of a (R, n_rowparams)
+    matrix.  Parameter order inside a layer: affine [a, b]; tanh_step n_steps x [a, b, c, d]; sal [a, b]
+    (reference code/dsp/models/flow.py:330-340, 755-773, 965-977).
+    """
+
+    def __init__(self, layers):
+        self.layers = []
+        self.n_theta = 0
+        self.n_rowparams = 0
+        for lay in layers:
+            kind = lay['kind']
+            if kind == 'identity':
+                continue
+            npar = 4 * lay.get('n_steps', 0) if kind == 'tanh_step' else 2
+            per_row = bool(lay.get('per_row', False))
+            p0 = self.n_rowparams if per_row else self.n_theta
+            if per_row:
+                self.n_rowparams += npar
+            else:
+                self.n_theta += npar
+            self.layers.append(dict(kind=kind, restrict=bool(lay.get('restrict', False)),
+                                    add_f0=bool(lay.get('add_f0', False)), n_steps=int(lay.get('n_steps', 0)),
+                                    per_row=per_row, p0=p0, npar=npar))
+        if len(self.layers) > _lib.MAX_LAYERS:
+            raise ValueError('flow has %d layers; the fused epilogue supports %d' % (len(self.layers), _lib.MAX_LAYERS))
+
+    def fill(self, model):
+        model.n_layers = len(self.layers)
+        model.n_theta = self.n_theta
+        model.n_rowparams = self.n_rowparams
+        for i, lay in enumerate(self.layers):
+            L = model.layers[i]
+            L.kind = _KIND[lay['kind']]
+            L.flags = (_lib.FLOW_RESTRICT if lay['restrict'] else 0) | (_lib.FLOW_ADD_F0 if lay['add_f0'] else 0) | \
+                      (_lib.FLOW_PER_ROW if lay['per_row'] else 0)
+            L.n_steps = lay['n_steps']
+            L.p0 = lay['p0']
+
+
+_GH_CACHE = {}
+
+
+def gauss_hermite(n, device):
+    """numpy hermgauss(n), as gpytorch's GaussHermiteQuadrature1D builds its rule (FP64 build)."""
+    key = (n, str(device))
+    if key not in _GH_CACHE:
+        t, w = np.polynomial.hermite.hermgauss(n)
+        _GH_CACHE[key] = (torch.tensor(t, dtype=torch.float64, device=device),
+                          torch.tensor(w, dtype=torch.float64, device=device))
+    return _GH_CACHE[key]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, shape=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise ValueError('%s must be a CUDA tensor (there is no CPU path)' % name)
+    if t.dtype != torch.float64:
+        raise ValueError('%s must be float64, got %s' % (name, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError('%s has shape %s, expected %s' % (name, tuple(t.shape), tuple(shape)))
+
+
+class Engine:
+    def __init__(self, M, D, likelihood, n_quad, flow_layout, device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('tgp.pytorch_b200 runs on CUDA devices only (no CPU fallback)')
+        self.M, self.D = int(M), int(D)
+        self.likelihood = likelihood
+        self.flow = flow_layout
+        self.model = _lib.TgpModel()
+        self.model.dtype = _lib.TGP_F64
+        self.model.M, self.model.D = self.M, self.D
+        self.model.likelihood = _LIK[likelihood]
+        self.model.n_quad = int(n_quad)
+        flow_layout.fill(self.model)
+        self.n_quad = int(n_quad)
+        nbytes = self.lib.tgp_step_workspace_bytes(self.model)
+        if nbytes == 0:
+            raise ValueError('invalid model description: ' + self.lib.tgp_last_error().decode())
+        self.step_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.layout = _lib.TgpReduceLayout()
+        _lib.check(self.lib.tgp_reduce_layout(self.model, self.layout), 'tgp_reduce_layout')
+        self.kl = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._batch_ws = None
+        self._batch_rows = -1
+        self._params = None
+        self._keep = None
+        self.generation = 0          # bumped by every prepare(); backward passes check it
+        self.qt, self.qw = gauss_hermite(self.n_quad, self.device) if likelihood != 'gauss_linear' else (None, None)
+
+    # -- helpers ------------------------------------------------------------------------------------------------
+    def batch_ws(self, R):
+        if self._batch_ws is None or self._batch_rows < R:
+            nbytes = self.lib.tgp_batch_workspace_bytes(self.model, R)
+            self._batch_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._batch_rows = R
+        return self._batch_ws
+
+    def new_reduce_buffer(self):
+        return torch.zeros(self.layout.total, dtype=torch.float64, device=self.device)
+
+    def set_params(self, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta):
+        M, D = self.M, self.D
+        _chk(Z, 'Z', (M, D)); _chk(raw_ls, 'raw_lengthscale', (D,)); _chk(raw_os, 'raw_outputscale', (1,))
+        _chk(m, 'm', (M,)); _chk(L_raw, 'L_raw', (M, M)); _chk(log_var_noise, 'log_var_noise', (1,))
+        _chk(theta, 'theta', (self.flow.n_theta,))
+        p = _lib.TgpParams()
+        p.Z, p.raw_lengthscale, p.raw_outputscale = Z.data_ptr(), raw_ls.data_ptr(), raw_os.data_ptr()
+        p.m, p.L_raw = m.data_ptr(), L_raw.data_ptr()
+        p.log_var_noise = log_var_noise.data_ptr() if log_var_noise is not None else None
+        p.theta = theta.data_ptr() if theta is not None and theta.numel() > 0 else None
+        self._params = p
+        self._keep = (Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta)     # keep the storage alive
+
+    # -- the C-ABI stages ---------------------------------------------------------------------------------------
+    def prepare(self, jitter=0.0):
+        self.generation += 1
+        _lib.check(self.lib.tgp_prepare(self.model, self._params, float(jitter), _ptr(self.step_ws), _ptr(self.kl),
+                                        _ptr(self.status), _stream()), 'tgp_prepare')
+        return self.kl, self.status
+
+    def qf_forward(self, X):
+        R = X.shape[0]
+        _chk(X, 'X', (R, self.D))
+        mu = torch.empty(R, dtype=torch.float64, device=self.device)
+        v = torch.empty(R, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.tgp_qf_forward(self.model, _ptr(self.step_ws), _ptr(self.batch_ws(R)), _ptr(X), R, _ptr(mu),
+                                           _ptr(v), _stream()), 'tgp_qf_forward')
+        return mu, v
+
+    def ell_forward(self, mu, v, Y, rowparams, scale, reduce_buf, want_grad=True):
+        R = mu.shape[0]
+        _chk(mu, 'mu', (R,)); _chk(v, 'v', (R,)); _chk(Y, 'Y', (R,))
+        nrp = self.flow.n_rowparams
+        if nrp:
+            _chk(rowparams, 'rowparams', (R, nrp))
+        ell_rows = torch.empty(R, dtype=torch.float64, device=self.device)
+        g_mu = torch.empty(R, dtype=torch.float64, device=self.device) if want_grad else None
+        g_v = torch.empty(R, dtype=torch.float64, device=self.device) if want_grad else None
+        drow = torch.empty(R, nrp, dtype=torch.float64, device=self.device) if (want_grad and nrp) else None
+        _lib.check(self.lib.tgp_ell_forward(self.model, self._params, _ptr(mu), _ptr(v), _ptr(Y),
+                                            _ptr(rowparams) if nrp else None, R, float(scale), _ptr(self.qt),
+                                            _ptr(self.qw), 1 if want_grad else 0, _ptr(ell_rows), _ptr(g_mu), _ptr(g_v),
+                                            _ptr(drow), _ptr(reduce_buf), _stream()), 'tgp_ell_forward')
+        return ell_rows, g_mu, g_v, drow
+
+    def qf_backward(self, X, g_mu, g_v, reduce_buf):
+        R = X.shape[0]
+        _chk(g_mu, 'g_mu', (R,)); _chk(g_v, 'g_v', (R,))
+        _lib.check(self.lib.tgp_qf_backward(self.model, self._params, _ptr(self.step_ws), _ptr(self.batch_ws(R)),
+                                            _ptr(X), R, _ptr(g_mu), _ptr(g_v), _ptr(reduce_buf), _stream()),
+                   'tgp_qf_backward')
+
+    def chain_backward(self, reduce_buf, gE=1.0, gK=-1.0, g_dev=None):
+        M, D, dev = self.M, self.D, self.device
+        f64 = torch.float64
+        out = dict(Z=torch.empty(M, D, dtype=f64, device=dev), raw_ls=torch.empty(D, dtype=f64, device=dev),
+                   raw_os=torch.empty(1, dtype=f64, device=dev), m=torch.empty(M, dtype=f64, device=dev),
+                   L_raw=torch.empty(M, M, dtype=f64, device=dev), log_var_noise=torch.zeros(1, dtype=f64, device=dev),
+                   theta=torch.zeros(self.flow.n_theta, dtype=f64, device=dev))
+        _lib.check(self.lib.tgp_chain_backward(self.model, self._params, _ptr(self.step_ws), _ptr(reduce_buf), float(gE),
+                                               float(gK), _ptr(g_dev), _ptr(out['Z']), _ptr(out['raw_ls']), _ptr(out['raw_os']),
+                                               _ptr(out['m']), _ptr(out['L_raw']), _ptr(out['log_var_noise']),
+                                               _ptr(out['theta']) if self.flow.n_theta else None, _stream()),
+                   'tgp_chain_backward')
+        return out
+
+    def test_rows(self, mu, v, Y, rowparams, n_mc, y_std, bern_std=None):
+        R = mu.shape[0]
+        _chk(mu, 'mu', (R,)); _chk(v, 'v', (R,)); _chk(Y, 'Y', (R,))
+        nrp = self.flow.n_rowparams
+        if nrp:
+            _chk(rowparams, 'rowparams', (R, n_mc, nrp))
+        f64 = torch.float64
+        logp = torch.empty(R, dtype=f64, device=self.device)
+        m1 = torch.empty(R, dtype=f64, device=self.device)
+        m2 = torch.empty(R, dtype=f64, device=self.device)
+        _lib.check(self.lib.tgp_test_rows(self.model, self._params, _ptr(mu), _ptr(v), _ptr(Y),
+                                          _ptr(rowparams) if nrp else None, R, int(n_mc), float(y_std), _ptr(self.qt),
+                                          _ptr(self.qw), _ptr(bern_std), _ptr(logp), _ptr(m1), _ptr(m2), _stream()),
+                   'tgp_test_rows')
+        return logp, m1, m2
+
+    def export_step(self):
+        M = self.M
+        L, Li, Cm = (torch.empty(M, M, dtype=torch.float64, device=self.device) for _ in range(3))
+        _lib.check(self.lib.tgp_debug_export_step(self.model, _ptr(self.step_ws), _ptr(L), _ptr(Li), _ptr(Cm), _stream()),
+                   'tgp_debug_export_step')
+        return L, Li, Cm
+
+
+def debug_gemm(A, B, C_out, M, N, K, lda, ldb, ldc, a_layout, b_layout, alpha=1.0, beta=0.0, a_tri=0, b_tri=0,
+               c_lower=0):
+    lib = _lib.load()
+    _lib.check(lib.tgp_debug_gemm_f64(M, N, K, _ptr(A), lda, a_layout, _ptr(B), ldb, b_layout, _ptr(C_out), ldc,
+                                      float(alpha), float(beta), a_tri, b_tri, c_lower, _stream()), 'tgp_debug_gemm_f64')

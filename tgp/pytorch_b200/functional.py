@@ -1,0 +1,135 @@
+"""The seam between the reference-shaped host classes and the C-ABI kernels.
+
+`elbo_terms` is what `sparse_MF_SP.ELBO` calls (reference code/dsp/models/sparse_MF_SP.py:552-598): it returns the
+(N/MB)-scaled expected log-likelihood, the whitened KL and the per-row expected log-likelihoods, differentiable
+w.r.t. every parameter through hand-written backward kernels (no autograd graph over the batch).
+
+Row sharding: when `torch.distributed` is initialised each rank passes its contiguous row slice of
+the global minibatch and the GLOBAL scale N/MB_global; the packed pre-chain buffer is all-reduced once per backward
+(NCCL over NVLink), the O(M^3) chain runs replicated.
+"""
+import warnings
+
+import torch
+
+from . import _lib  # noqa: F401  (fails loudly when the library has not been built)
+
+
+class NanError(RuntimeError):
+    """Stand-in for gpytorch.utils.errors.NanError (raised by the reference at code/dsp/utils.py:241-254)."""
+
+
+class NumericalWarning(RuntimeWarning):
+    """Stand-in for gpytorch.utils.warnings.NumericalWarning (code/dsp/utils.py:266)."""
+
+
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def prepare_with_jitter_ladder(engine, base_jitter=None, check=True):
+    """Reference semantics of psd_safe_cholesky (code/dsp/utils.py:222-270): factorise without jitter; only on
+    failure add 1e-8 * 10^i (FP64), i = 0..2, warning each time; raise after the third failure.
+    `check=False` skips the 4-byte status read-back (no host sync; a failed factorisation then surfaces as NaNs)."""
+    kl, status = engine.prepare(0.0)
+    if not check:
+        return kl, 0.0
+    fail = int(status.item())
+    if fail == 0:
+        return kl, 0.0
+    Z = engine._keep[0]
+    if torch.isnan(Z).any() or torch.isnan(engine._keep[1]).any() or torch.isnan(engine._keep[2]).any():
+        raise NanError('cholesky: the kernel matrix has NaN entries')
+    jitter = 1e-8 if base_jitter is None else base_jitter
+    for i in range(3):
+        j = jitter * (10 ** i)
+        kl, status = engine.prepare(j)
+        if int(status.item()) == 0:
+            warnings.warn('A not p.d., added jitter of %g to the diagonal' % j, NumericalWarning)
+            return kl, j
+    raise RuntimeError('cholesky: matrix not positive definite after 3 jitter escalations (first bad pivot %d)' % fail)
+
+
+def _check_generation(ctx):
+    if ctx.generation != ctx.engine.generation:
+        raise RuntimeError('the model was evaluated again before backward(): the saved per-step workspace (L^-1, A, B) '
+                           'has been overwritten; call backward() before the next ELBO / marginal evaluation')
+
+
+class _ElboTerms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, X, Y, scale, check_status, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta, rowparams):
+        need_grad = any(ctx.needs_input_grad[5:])
+        engine.set_params(Z.detach(), raw_ls.detach(), raw_os.detach(), m.detach(), L_raw.detach(),
+                          None if log_var_noise is None else log_var_noise.detach(),
+                          None if theta is None else theta.detach())
+        kl, jitter = prepare_with_jitter_ladder(engine, check=check_status)
+        mu, v = engine.qf_forward(X)
+        rb = engine.new_reduce_buffer()
+        rp = None if rowparams is None else rowparams.detach().contiguous()
+        ell_rows, g_mu, g_v, drow = engine.ell_forward(mu, v, Y, rp, scale, rb, want_grad=need_grad)
+        ell = rb[engine.layout.ell_sum:engine.layout.ell_sum + 1].clone()
+        dist = _world()
+        if dist is not None:
+            dist.all_reduce(ell)
+        ctx.engine, ctx.X, ctx.rb, ctx.g = engine, X, rb, (g_mu, g_v, drow)
+        ctx.generation = engine.generation
+        ctx.has = (log_var_noise is not None, theta is not None, rowparams is not None)
+        ctx.mark_non_differentiable(ell_rows, mu, v)
+        return (ell * scale).reshape(()), kl.clone().reshape(()), ell_rows, mu, v
+
+    @staticmethod
+    def backward(ctx, g_ell, g_kl, _g_rows, _g_mu, _g_v):
+        engine, X, rb = ctx.engine, ctx.X, ctx.rb
+        g_mu, g_v, drow = ctx.g
+        if g_mu is None:
+            raise RuntimeError('backward called on an ELBO evaluated without gradients')
+        _check_generation(ctx)
+        engine.qf_backward(X, g_mu, g_v, rb)
+        dist = _world()
+        if dist is not None:
+            dist.all_reduce(rb)                    # the one collective of the step
+        zero = torch.zeros((), dtype=torch.float64, device=rb.device)
+        g_dev = torch.stack([g_ell if g_ell is not None else zero, g_kl if g_kl is not None else zero]).contiguous()
+        out = engine.chain_backward(rb, 0.0, 0.0, g_dev=g_dev)
+        has_noise, has_theta, has_rowp = ctx.has
+        g_rowp = drow * g_dev[0] if (has_rowp and drow is not None) else None
+        return (None, None, None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw'],
+                out['log_var_noise'] if has_noise else None, out['theta'] if has_theta else None, g_rowp)
+
+
+def elbo_terms(engine, X, Y, scale, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta, rowparams=None,
+               check_status=True):
+    """Returns (ELL, KLD, ell_rows, mu, v): ELL = scale * sum_n ell_n (summed over ranks when distributed)."""
+    return _ElboTerms.apply(engine, X, Y, float(scale), bool(check_status), Z, raw_ls, raw_os, m, L_raw, log_var_noise,
+                            theta, rowparams)
+
+
+class _QfMarginals(torch.autograd.Function):
+    """mu, v of q(f) with a hand-written backward (used by marginal_variational_qf_parameters when called alone)."""
+
+    @staticmethod
+    def forward(ctx, engine, X, check_status, Z, raw_ls, raw_os, m, L_raw):
+        engine.set_params(Z.detach(), raw_ls.detach(), raw_os.detach(), m.detach(), L_raw.detach(), None, None)
+        prepare_with_jitter_ladder(engine, check=check_status)
+        mu, v = engine.qf_forward(X)
+        ctx.engine, ctx.X = engine, X
+        ctx.generation = engine.generation
+        return mu, v
+
+    @staticmethod
+    def backward(ctx, g_mu, g_v):
+        engine, X = ctx.engine, ctx.X
+        _check_generation(ctx)
+        rb = engine.new_reduce_buffer()
+        zeros = torch.zeros(X.shape[0], dtype=torch.float64, device=X.device)
+        engine.qf_backward(X, zeros if g_mu is None else g_mu.contiguous(), zeros if g_v is None else g_v.contiguous(), rb)
+        out = engine.chain_backward(rb, 1.0, 0.0)
+        return None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw']
+
+
+def qf_marginals(engine, X, Z, raw_ls, raw_os, m, L_raw, check_status=True):
+    return _QfMarginals.apply(engine, X, bool(check_status), Z, raw_ls, raw_os, m, L_raw)
