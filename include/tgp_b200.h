@@ -118,6 +118,14 @@ int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu
                   const void* rowparams, long R, int n_mc, double y_std, const void* quad_t, const void* quad_w,
                   const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream);
 
+/* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
+long tgp_launch_count(void);
+/* Live per-launch timing of the GEMM kernel with CUDA events on the launching stream (bench.py's roofline).
+ * Returns the accumulated milliseconds / launch counts per class ([0] per-step O(M^3) work, [1] batch contractions)
+ * since the last reset into ms_out[2] / launches_out[2] (host pointers, may be NULL), then enable = 1 / 0 switches the
+ * instrumentation on / off and resets the accumulators; enable < 0 only reads.  Synchronises on the recorded events. */
+int tgp_gemm_timing(int enable, double* ms_out, long* launches_out);
+
 /* Test hook: the FP64 DMMA GEMM that carries every contraction (C = alpha*Aop*Bop^T + beta*C). */
 int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_layout, const double* B, long ldb,
                        int b_layout, double* C, long ldc, double alpha, double beta, int a_tri, int b_tri,

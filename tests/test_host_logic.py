@@ -1,0 +1,98 @@
+"""CPU tests of the host side: the dsp mirror builds reference-shaped modules (same parameter names), flow
+descriptors pack as the kernels expect, the C-ABI library loads and exports every declared symbol, and the product
+refuses to run without a GPU instead of falling back."""
+import os
+import re
+
+import pytest
+import torch
+
+from tests.golden_util import Golden, golden_names
+from tests.model_util import build_from_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from tgp.pytorch_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'tgp_b200.h')).read()
+    declared = set(re.findall(r'\b(tgp_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    for name in declared:
+        assert hasattr(lib, name), 'library does not export %s' % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert lib.tgp_version() >= 100
+
+
+def test_cabi_rejects_bad_descriptions_without_a_gpu():
+    from tgp.pytorch_b200 import _lib
+    lib = _lib.load()
+    m = _lib.TgpModel()
+    m.M, m.D, m.likelihood, m.n_quad = 0, 3, 1, 100
+    assert lib.tgp_step_workspace_bytes(m) == 0
+    assert b'positive' in lib.tgp_last_error()
+    m.M = 16
+    m.dtype = _lib.TGP_F32
+    assert lib.tgp_step_workspace_bytes(m) == 0
+    m.dtype = _lib.TGP_F64
+    assert lib.tgp_step_workspace_bytes(m) > 0
+    lay = _lib.TgpReduceLayout()
+    assert lib.tgp_reduce_layout(m, lay) == 0
+    assert lay.total == lay.Cbar + 64 * 64 and lay.Gbar % 2 == 0
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_models_reproduce_reference_parameter_names(name):
+    g = Golden(name)
+    model = build_from_golden(g, 'cpu')          # asserts the name sets are identical
+    assert model.M == g.meta['M'] and model.out_dim == 1
+
+
+def test_flow_descriptor_packing():
+    from tgp.pytorch_b200.dsp import config as cg
+    cg.set_maximum_precission()
+    from tgp.pytorch_b200.dsp.flows import StepTanhL, SAL
+    from tgp.pytorch_b200.dsp.models.flow import instance_flow
+    from tgp.pytorch_b200.engine import FlowLayout
+    fl = instance_flow(StepTanhL(2, 3, add_f0=True))
+    layers, glob, rows = fl.describe()
+    lay = FlowLayout(layers)
+    assert [l['kind'] for l in lay.layers] == ['tanh_step', 'affine', 'tanh_step', 'affine']
+    assert lay.n_theta == len(glob) == 2 * (3 * 4 + 2) and lay.n_rowparams == 0 and not rows
+    assert [l['p0'] for l in lay.layers] == [0, 12, 14, 26]
+    idf = instance_flow(SAL(2, input_dependent=True, input_dim=4, hidden_dim=5, dropout=0.25, num_hidden_layers=2))
+    idf.turn_off_initializer_parameters()
+    layers, glob, rows = idf.describe(torch.randn(7, 4, dtype=torch.float64))
+    lay = FlowLayout(layers)
+    assert lay.n_rowparams == 4 and lay.n_theta == 4 and len(rows) == 4 and rows[0].shape == (7,)
+    assert [(l['per_row'], l['p0']) for l in lay.layers] == [(True, 0), (False, 0), (True, 2), (False, 2)]
+
+
+def test_flow_modules_match_oracle_forward():
+    """The torch `forward` of the flow modules (used by initialisers / sampling) agrees with the oracle's flows."""
+    from oracle import tgp_oracle as O
+    from tgp.pytorch_b200.dsp import config as cg
+    cg.set_maximum_precission()
+    from tgp.pytorch_b200.dsp.flows import StepTanhL, SAL
+    from tgp.pytorch_b200.dsp.models.flow import instance_flow
+    f = torch.linspace(-3, 3, 41, dtype=torch.float64)
+    for spec in (StepTanhL(2, 3, add_f0=True), SAL(2, init_random=True)):
+        fl = instance_flow(spec)
+        layers = []
+        for sub in fl.flow_arr:
+            kind = type(sub).__name__
+            if kind == 'AffineFlow':
+                layers.append(('affine', sub.a, sub.b, sub.set_restrictions))
+            elif kind == 'StepFlow':
+                layers.append(('tanh_step', [(s.a, s.b, s.c, s.d) for s in sub.flow_arr], sub.add_init_f0))
+            else:
+                layers.append(('sal', sub.a, sub.b, sub.set_restrictions, sub.add_init_f0))
+        assert torch.allclose(fl(f), O.apply_flow(layers, f), rtol=1e-14, atol=1e-14)
+
+
+def test_no_cpu_fallback():
+    g = Golden('boston_svgp_p1')
+    model = build_from_golden(g, 'cpu')
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        model.ELBO(g.t('X'), g.t('Y'))

@@ -52,6 +52,8 @@ SIGNATURES = {
                                 _P, _P]),
     'tgp_test_rows': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _P, _L, _I, _D, _P, _P, _P, _P, _P,
                            _P, _P]),
+    'tgp_launch_count': (_L, []),
+    'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'tgp_debug_gemm_f64': (_I, [_I, _I, _I, _P, _L, _I, _P, _L, _I, _P, _L, _D, _D, _I, _I, _I, _P]),
     'tgp_debug_export_step': (_I, [C.POINTER(TgpModel), _P, _P, _P, _P, _P]),
 }

@@ -17,7 +17,10 @@ inline int set_error(int code, const char* msg) {
     return code;
 }
 
+extern long g_launch_count;      // kernels launched by this library (tgp_launch_count())
+
 inline int check_launch(const char* what) {
+    ++g_launch_count;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));

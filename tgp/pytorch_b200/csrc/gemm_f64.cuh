@@ -30,7 +30,37 @@ struct GemmArgs {
     int b_tri;      // 0 dense, 1: Bop[n,k] != 0 only for k <= n, 2: only for k >= n
     int c_lower;    // 1: write only elements with n <= m (tiles strictly above the diagonal are skipped)
     int batch;
+    int tag;        // profiling class: 0 = per-step O(M^3) work, 1 = batch contraction (rows x M x M)
 };
+
+// Optional in-stream timing of every GEMM launch (bench.py's live roofline measurement): a pair of CUDA events per
+// launch on the launching stream, resolved at query time.  Off by default.
+struct GemmTimer {
+    bool enabled = false;
+    static constexpr int MAXEV = 8192;
+    cudaEvent_t ev[2 * MAXEV];
+    int tagv[MAXEV];
+    int n = 0, created = 0;
+    double ms[2] = {0, 0};
+    long launches[2] = {0, 0};
+    void begin(int tag, cudaStream_t st) {
+        if (n >= MAXEV) flush();
+        while (created < 2 * (n + 1)) { cudaEventCreate(&ev[created]); ++created; }
+        tagv[n] = tag;
+        cudaEventRecord(ev[2 * n], st);
+    }
+    void end(cudaStream_t st) { cudaEventRecord(ev[2 * n + 1], st); ++n; }
+    void flush() {
+        for (int i = 0; i < n; ++i) {
+            float t = 0.f;
+            cudaEventSynchronize(ev[2 * i + 1]);
+            cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+            ms[tagv[i]] += t; ++launches[tagv[i]];
+        }
+        n = 0;
+    }
+};
+extern GemmTimer g_gemm_timer;
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GPAD = 4, GLD = GBK + GPAD;
 constexpr int GEMM_THREADS = 256;
@@ -191,10 +221,13 @@ inline int gemm_f64(const GemmArgs& g, cudaStream_t st) {
         cudaFuncSetAttribute(gemm_f64_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         attr_set = true;
     }
+    const bool timed = g_gemm_timer.enabled;
+    if (timed) g_gemm_timer.begin(g.tag, st);
     if (g.a_layout == 0 && g.b_layout == 0) gemm_f64_kernel<0, 0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
     else if (g.a_layout == 0 && g.b_layout == 1) gemm_f64_kernel<0, 1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
     else if (g.a_layout == 1 && g.b_layout == 0) gemm_f64_kernel<1, 0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
     else gemm_f64_kernel<1, 1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+    if (timed) g_gemm_timer.end(st);
     return check_launch("gemm_f64");
 }
 
@@ -208,7 +241,7 @@ inline GemmArgs make_gemm(int M, int N, int K, const double* A, long lda, int al
     g.C = C; g.ldc = ldc; g.strideC = 0;
     g.alpha = alpha; g.beta = beta;
     g.a_layout = al; g.b_layout = bl;
-    g.a_tri = 0; g.b_tri = 0; g.c_lower = 0; g.batch = 1;
+    g.a_tri = 0; g.b_tri = 0; g.c_lower = 0; g.batch = 1; g.tag = 0;
     return g;
 }
 

@@ -119,7 +119,8 @@ __device__ __forceinline__ int layer_nparams(const TgpFlowLayer& L) {
     return L.kind == TGP_FLOW_TANH_STEP ? 4 * L.n_steps : (L.kind == TGP_FLOW_IDENTITY ? 0 : 2);
 }
 
-__device__ __forceinline__ double norm_cdf_ref(double x) { return 0.5 * (1.0 + erf(x * 0.7071067811865476)); }
+// torch.distributions.Normal(0,1).cdf: 0.5 * (1 + erf(x / sqrt(2)))
+__device__ __forceinline__ double norm_cdf_ref(double x) { return 0.5 * (1.0 + erf(x / 1.4142135623730951)); }
 
 struct RowQuadArgs {
     int R, likelihood, n_quad, n_theta, n_rowp, want_grad;

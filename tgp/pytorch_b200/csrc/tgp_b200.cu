@@ -8,6 +8,8 @@
 
 namespace tgp {
 char g_last_error[512] = "";
+long g_launch_count = 0;
+GemmTimer g_gemm_timer;
 
 constexpr long ROW_CHUNK = 8192;     // rows whose K / Kbar tiles are staged at once (L2-sized for M = 1024)
 
@@ -120,9 +122,11 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
         // A = K L^-T   (Bop[n,k] = Linv[n,k], nonzero k <= n)
         GemmArgs ga = make_gemm(rc, M, M, b.Kbuf, M, 0, s.Linv, s.Mp, 0, b.AB + r0 * 2 * M, 2 * M);
         ga.b_tri = 1;
+        ga.tag = 1;
         TGP_TRY(gemm_f64(ga, st));
         // B = K C^T
         GemmArgs gb = make_gemm(rc, M, M, b.Kbuf, M, 0, s.Cm, s.Mp, 0, b.AB + r0 * 2 * M + M, 2 * M);
+        gb.tag = 1;
         TGP_TRY(gemm_f64(gb, st));
     }
     k_row_stats<<<row_grid(R), ROW_THREADS, 0, st>>>(b.AB, s.mvec, s.os, (int)R, M, (double*)mu, (double*)v);
@@ -182,16 +186,20 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
         // Kbar = Abar * Linv + Bbar * C     (Bop[n,k] = Linv[k,n], nonzero k >= n)
         GemmArgs g1 = make_gemm(rc, M, M, ABc, 2 * M, 0, s.Linv, s.Mp, 1, b.Kbar, M);
         g1.b_tri = 2;
+        g1.tag = 1;
         TGP_TRY(gemm_f64(g1, st));
         GemmArgs g2 = make_gemm(rc, M, M, ABc + M, 2 * M, 0, s.Cm, s.Mp, 1, b.Kbar, M, 1.0, 1.0);
+        g2.tag = 1;
         TGP_TRY(gemm_f64(g2, st));
         TGP_TRY(launch_kernel_grads(b.Kbar, M, Xd + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, reduce_buf + l.dZ,
                                     reduce_buf + l.dls, reduce_buf + l.dos, st));
         // Gbar += tril(Abar^T K),  Cbar += Bbar^T K      (reduction over the rows of the chunk)
         GemmArgs g3 = make_gemm(M, M, rc, ABc, 2 * M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
         g3.c_lower = 1;
+        g3.tag = 1;
         TGP_TRY(gemm_f64(g3, st));
         GemmArgs g4 = make_gemm(M, M, rc, ABc + M, 2 * M, 1, b.Kbuf, M, 1, Cbar, s.Mp, 1.0, 1.0);
+        g4.tag = 1;
         TGP_TRY(gemm_f64(g4, st));
     }
     return 0;
@@ -290,6 +298,19 @@ int tgp_test_rows(const TgpModel* md, const TgpParams* p, const void* mu, const 
     fill_flow(a.flow, md);
     k_row_test<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(a);
     return check_launch("k_row_test");
+}
+
+long tgp_launch_count(void) { return g_launch_count; }
+
+int tgp_gemm_timing(int enable, double* ms_out, long* launches_out) {
+    g_gemm_timer.flush();
+    if (ms_out) { ms_out[0] = g_gemm_timer.ms[0]; ms_out[1] = g_gemm_timer.ms[1]; }
+    if (launches_out) { launches_out[0] = g_gemm_timer.launches[0]; launches_out[1] = g_gemm_timer.launches[1]; }
+    if (enable >= 0) {
+        g_gemm_timer.enabled = enable != 0;
+        g_gemm_timer.ms[0] = g_gemm_timer.ms[1] = 0; g_gemm_timer.launches[0] = g_gemm_timer.launches[1] = 0;
+    }
+    return 0;
 }
 
 int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_layout, const double* B, long ldb,

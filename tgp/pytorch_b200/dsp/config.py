@@ -1,0 +1,44 @@
+"""Global mutable configuration, same names as the reference's code/dsp/config.py:37-71 (minus the
+torch/gpytorch version gate, which cannot hold on a B200 software stack)."""
+import math
+import platform
+
+import numpy
+import torch
+
+
+def check_device():
+    return 'cuda' if torch.cuda.is_available() else 'cpu'
+
+
+def set_seed(seed):
+    torch.manual_seed(seed)
+    numpy.random.seed(seed)
+
+
+def set_maximum_precission():
+    """FP64 + 100 Gauss-Hermite points — what the reference's main.py always runs (main.py:124)."""
+    global dtype, maximum_precision, quad_points
+    maximum_precision = True
+    dtype = torch.float64
+    torch.set_default_dtype(dtype)
+    quad_points = 100
+
+
+config_seed = 0
+dtype = torch.float32
+maximum_precision = False
+is_linux = 'linux' in platform.platform().lower()
+quad_points = 50
+S_train = 1
+S_test = 100
+positive_transform = 'exp'
+strict_flag = True
+constant_jitter = None
+global_jitter = None
+check_cholesky_status = True    # False: skip the 4-byte status read-back after the factorisation (no host sync)
+
+device = check_device()
+# the reference keeps pi as a float32 tensor even in FP64 mode (config.py:71); the kernels bake in the resulting
+# constants (row_kernels.cuh: LOG_2PI_F32PI), this tensor serves the host-side test-NLL constant
+pi = torch.tensor(math.pi, dtype=torch.float32)

@@ -1,0 +1,66 @@
+"""Flow *specification* generators — lists of `(name, init_dict)` consumed by `instance_flow`
+(reference code/dsp/flows.py: common_config :11-32, set_input_dependent_config :34-69, SAL :115-136,
+StepTanhL :239-277).  Draws from numpy's global RNG in the same order as the reference so that a seeded run
+starts from the same flow parameters.
+"""
+import numpy
+import torch
+
+from .models.flow import *  # noqa: F401,F403  (the reference re-exports the flow classes from here)
+from .utils import inv_softplus
+
+_ID_KEYS = ('batch_norm', 'dropout', 'hidden_dim', 'hidden_activation', 'num_hidden_layers', 'inference')
+
+
+def common_config(options):
+    return (options.get('set_res', False), options.get('add_f0', False), options.get('init_random', False),
+            options.get('constraint', None))
+
+
+def set_input_dependent_config(options):
+    input_dependent = bool(options.get('input_dependent', False))
+    if input_dependent:
+        assert 'input_dim' in options, 'You set to use input_dependent flows but the input dimension is not provided.'
+    cfg = {k: options[k] for k in _ID_KEYS if k in options}
+    return input_dependent, options.get('input_dim', -1), cfg
+
+
+def SAL(num_blocks, **kwargs):
+    """num_blocks x [sinh_arcsinh, affine]; the default initialisation is the identity map."""
+    set_res, addf0, init_random, _ = common_config(kwargs)
+    input_dependent, input_dim, id_cfg = set_input_dependent_config(kwargs)
+    blocks = []
+    for _ in range(num_blocks):
+        if init_random:
+            a_aff, b_aff = numpy.random.randn(2)
+            a_sal, b_sal = numpy.random.randn(2)
+        else:
+            a_aff, b_aff, a_sal, b_sal = 1.0, 0.0, 0.0, 1.0
+        blocks.append(('sinh_arcsinh', {'init_a': a_sal, 'init_b': b_sal, 'add_init_f0': addf0,
+                                        'set_restrictions': set_res, 'input_dependent': input_dependent,
+                                        'input_dim': input_dim, 'input_dependent_config': id_cfg}))
+        blocks.append(('affine', {'init_a': a_aff, 'init_b': b_aff, 'set_restrictions': set_res}))
+    return blocks
+
+
+def StepTanhL(num_blocks, num_steps, **kwargs):
+    """num_blocks x [step_flow(num_steps tanh terms), affine]; tanh steps are always restricted (b, d > 0)."""
+    _, addf0, init_random, _ = common_config(kwargs)
+    if 'set_res' in kwargs:
+        assert kwargs['set_res'] is True, 'In the step tanh flow set_res has to be True for num_steps > 1'
+    input_dependent, input_dim, id_cfg = set_input_dependent_config(kwargs)
+    blocks = []
+    for _ in range(num_blocks):
+        steps = []
+        for _s in range(num_steps):
+            e1, e2, e3, e4 = numpy.multiply(numpy.random.randn(4, ), numpy.array([1.0, 1.0, 1.0, 1.0]))
+            if not init_random:
+                e2 = inv_softplus(torch.abs(torch.tensor((e2 + 1.0) / float(num_steps)))).item()
+                e4 = inv_softplus(torch.abs(torch.tensor((e4 + 1.0) / float(num_steps)))).item()
+            steps.append(('tanh', {'init_a': e1, 'init_b': e2, 'init_c': e3, 'init_d': e4, 'add_init_f0': False,
+                                   'set_restrictions': True, 'input_dependent': input_dependent,
+                                   'input_dim': input_dim, 'input_dependent_config': id_cfg}))
+        a_aff, b_aff = numpy.random.randn(2) if init_random else (1.0, 0.0)
+        blocks.append(('step_flow', {'flow_arr': steps, 'add_init_f0': addf0}))
+        blocks.append(('affine', {'init_a': a_aff, 'init_b': b_aff, 'set_restrictions': False}))
+    return blocks

@@ -1,0 +1,82 @@
+"""Shared launcher for the likelihood classes: (mu, v) rows -> fused epilogue kernels.
+
+`expected_log_prob` of every likelihood is differentiable w.r.t. (gauss_mean, gauss_cov, noise, flow parameters)
+through the analytic gradients the kernel emits (tgp_ell_forward), with no autograd graph over the S x MB
+quadrature grid the reference materialises.
+"""
+import torch
+
+from ...engine import Engine, FlowLayout
+
+_ENGINES = {}
+
+
+def flow_pack(flow, X, n_mc=1):
+    """flow module -> (FlowLayout, theta tensor or None, rowparams (R, n_rowparams) or None)."""
+    layers, glob, rows = flow.describe(X, n_mc) if flow is not None else ([], [], [])
+    layout = FlowLayout(layers)
+    theta = torch.stack([g.reshape(()) for g in glob]) if glob else None
+    rowp = torch.stack(rows, dim=-1) if rows else None
+    return layout, theta, rowp
+
+
+def row_engine(likelihood, n_quad, layout, device):
+    """An Engine used only for its per-row kernels (M and D are irrelevant there)."""
+    key = (likelihood, n_quad, tuple((l['kind'], l['restrict'], l['add_f0'], l['n_steps'], l['per_row'], l['p0'])
+                                     for l in layout.layers), str(device))
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(1, 1, likelihood, n_quad, layout, device)
+    return _ENGINES[key]
+
+
+class _EllRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, y, mu, v, log_var_noise, theta, rowp):
+        dev = mu.device
+        z = torch.zeros(1, dtype=torch.float64, device=dev)
+        eng.set_params(torch.zeros(1, 1, dtype=torch.float64, device=dev), z, z, z, torch.ones(1, 1, dtype=torch.float64, device=dev),
+                       None if log_var_noise is None else log_var_noise.detach().reshape(1).contiguous(),
+                       None if theta is None else theta.detach().contiguous())
+        rb = eng.new_reduce_buffer()
+        rows, g_mu, g_v, drow = eng.ell_forward(mu.detach().contiguous(), v.detach().contiguous(), y.contiguous(),
+                                                None if rowp is None else rowp.detach().contiguous(), 1.0, rb)
+        ctx.save_for_backward(g_mu, g_v, drow if drow is not None else z)
+        ctx.rb, ctx.layout, ctx.has = rb, eng.layout, (log_var_noise is not None, theta is not None, rowp is not None)
+        ctx.n_theta, ctx.lv_shape = eng.flow.n_theta, None if log_var_noise is None else log_var_noise.shape
+        ctx.mark_non_differentiable(rows)
+        return rb[eng.layout.ell_sum].clone(), rows
+
+    @staticmethod
+    def backward(ctx, g_sum, _g_rows):
+        g_mu, g_v, drow = ctx.saved_tensors
+        lay, rb = ctx.layout, ctx.rb
+        has_noise, has_theta, has_rowp = ctx.has
+        d_lv = (rb[lay.dlogvar] * g_sum).reshape(ctx.lv_shape) if has_noise else None
+        d_th = rb[lay.dtheta:lay.dtheta + ctx.n_theta] * g_sum if has_theta else None
+        return (None, None, g_mu * g_sum, g_v * g_sum, d_lv, d_th, drow * g_sum if has_rowp else None)
+
+
+def expected_log_prob_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X):
+    """Sum over the rows of E_q(f)[log p(y | G(f))] for ONE output GP, and the per-row terms."""
+    layout, theta, rowp = flow_pack(flow, X) if likelihood != 'gauss_linear' else (FlowLayout([]), None, None)
+    eng = row_engine(likelihood, n_quad, layout, mu.device)
+    return _EllRows.apply(eng, y, mu, v, log_var_noise, theta, rowp)
+
+
+def test_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X, y_std=1.0, n_mc=1, bern_std=None):
+    """Per-row test log-likelihood and predictive moments (forward only)."""
+    with torch.no_grad():
+        layout, theta, rowp = flow_pack(flow, X, n_mc) if likelihood != 'gauss_linear' else (FlowLayout([]), None, None)
+        eng = row_engine(likelihood, n_quad, layout, mu.device)
+        dev = mu.device
+        z = torch.zeros(1, dtype=torch.float64, device=dev)
+        eng.set_params(torch.zeros(1, 1, dtype=torch.float64, device=dev), z, z, z, torch.ones(1, 1, dtype=torch.float64, device=dev),
+                       None if log_var_noise is None else log_var_noise.detach().reshape(1).contiguous(),
+                       None if theta is None else theta.detach().contiguous())
+        R = mu.shape[0]
+        if rowp is not None:
+            # rows of X were laid out as (n_mc, R): the kernel wants (R, n_mc, n_rowparams)
+            rowp = rowp.reshape(n_mc, R, -1).permute(1, 0, 2).contiguous()
+        if y is None:
+            y = torch.zeros(R, dtype=torch.float64, device=dev)
+        return eng.test_rows(mu.contiguous(), v.contiguous(), y.contiguous(), rowp, n_mc, y_std, bern_std)
