@@ -30,6 +30,7 @@ struct GemmArgs {
     int b_tri;      // 0 dense, 1: Bop[n,k] != 0 only for k <= n, 2: only for k >= n
     int c_lower;    // 1: write only elements with n <= m (tiles strictly above the diagonal are skipped)
     int batch;
+    int splitk;     // > 1: blockIdx.z splits the k-range; partial sums are atomically ADDED to C (beta must be 1, batch 1)
     int tag;        // profiling class: 0 = per-step O(M^3) work, 1 = batch contraction (rows x M x M)
 };
 
@@ -124,9 +125,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
     const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
     if (g.c_lower && n0 > m0 + GBM - 1) return;
 
-    const double* A = g.A + (long)blockIdx.z * g.strideA;
-    const double* B = g.B + (long)blockIdx.z * g.strideB;
-    double* C = g.C + (long)blockIdx.z * g.strideC;
+    const int zb = g.splitk > 1 ? 0 : blockIdx.z;
+    const double* A = g.A + (long)zb * g.strideA;
+    const double* B = g.B + (long)zb * g.strideB;
+    double* C = g.C + (long)zb * g.strideC;
 
     int kb = 0, ke = g.K;
     if (g.a_tri == 1) ke = min(ke, m0 + GBM);
@@ -134,7 +136,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
     if (g.b_tri == 1) ke = min(ke, n0 + GBN);
     if (g.b_tri == 2) kb = max(kb, n0);
     kb = (kb / GBK) * GBK;
-    const int nk = ke > kb ? (ke - kb + GBK - 1) / GBK : 0;
+    int nk = ke > kb ? (ke - kb + GBK - 1) / GBK : 0;
+    if (g.splitk > 1) {            // this CTA's share of the k-tiles
+        const int per = (nk + g.splitk - 1) / g.splitk;
+        const int t0 = min(nk, (int)blockIdx.z * per), t1 = min(nk, t0 + per);
+        kb += t0 * GBK;
+        ke = min(ke, kb + (t1 - t0) * GBK);
+        nk = t1 - t0;
+        if (nk == 0) return;
+    }
 
     const bool vecA = ((g.lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool vecB = ((g.ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
@@ -199,7 +209,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
             double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
             const bool ok0 = !g.c_lower || n <= m;
             const bool ok1 = (n + 1 < g.N) && (!g.c_lower || n + 1 <= m);
-            if (ok0 && ok1 && vecC) {
+            if (g.splitk > 1) {
+                if (ok0) atomicAdd(cp, v0);
+                if (ok1) atomicAdd(cp + 1, v1);
+            } else if (ok0 && ok1 && vecC) {
                 if (g.beta != 0.0) { double2 o = *reinterpret_cast<double2*>(cp); v0 += g.beta * o.x; v1 += g.beta * o.y; }
                 *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
             } else {
@@ -212,7 +225,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
 
 inline int gemm_f64(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
-    dim3 grid((unsigned)cdiv(g.N, GBN), (unsigned)cdiv(g.M, GBM), (unsigned)g.batch);
+    if (g.splitk > 1 && (g.batch != 1 || g.beta != 1.0)) return set_error(-3, "split-k GEMM needs batch == 1 and beta == 1");
+    dim3 grid((unsigned)cdiv(g.N, GBN), (unsigned)cdiv(g.M, GBM), (unsigned)(g.splitk > 1 ? g.splitk : g.batch));
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_f64_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
@@ -241,7 +255,7 @@ inline GemmArgs make_gemm(int M, int N, int K, const double* A, long lda, int al
     g.C = C; g.ldc = ldc; g.strideC = 0;
     g.alpha = alpha; g.beta = beta;
     g.a_layout = al; g.b_layout = bl;
-    g.a_tri = 0; g.b_tri = 0; g.c_lower = 0; g.batch = 1; g.tag = 0;
+    g.a_tri = 0; g.b_tri = 0; g.c_lower = 0; g.batch = 1; g.splitk = 1; g.tag = 0;
     return g;
 }
 

@@ -67,6 +67,16 @@ inline void fill_flow(FlowDesc& fd, const TgpModel* md) {
     for (int i = 0; i < md->n_layers; ++i) fd.layers[i] = md->layers[i];
 }
 
+// The weight-gradient GEMMs have only (M/128)^2 output tiles but a reduction over thousands of rows: split the
+// reduction so that about two waves of CTAs are in flight on the 148 SMs.
+inline int weight_splitk(int M, int rc) {
+    const long tiles = cdiv(M, GBM) * cdiv(M, GBN);
+    long want = cdiv(2 * 148, tiles);
+    const long max_split = rc / (4 * GBK) > 0 ? rc / (4 * GBK) : 1;
+    if (want > max_split) want = max_split;
+    return (int)(want < 1 ? 1 : want);
+}
+
 inline int row_grid(long R) {
     const long blocks = cdiv(R, ROW_THREADS / 32);
     return (int)(blocks < 148 * 16 ? blocks : 148 * 16);
@@ -196,9 +206,11 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
         // Gbar += tril(Abar^T K),  Cbar += Bbar^T K      (reduction over the rows of the chunk)
         GemmArgs g3 = make_gemm(M, M, rc, ABc, 2 * M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
         g3.c_lower = 1;
+        g3.splitk = weight_splitk(M, rc);
         g3.tag = 1;
         TGP_TRY(gemm_f64(g3, st));
         GemmArgs g4 = make_gemm(M, M, rc, ABc + M, 2 * M, 1, b.Kbuf, M, 1, Cbar, s.Mp, 1.0, 1.0);
+        g4.splitk = weight_splitk(M, rc);
         g4.tag = 1;
         TGP_TRY(gemm_f64(g4, st));
     }
