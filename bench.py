@@ -189,7 +189,7 @@ def run_ours(args):
     global_batch = BATCH * world
     scale = float(N_DATA) / global_batch
 
-    eng, theta, _, _ = make_engine(p, 'gauss_nonlinear', N_QUAD, dev)
+    eng, theta, _, _ = make_engine(p, 'gauss_nonlinear', N_QUAD, dev, compute=args.compute)
     ei = engine_inputs(p, dev)
     leaves = [ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta]
     for t in leaves:
@@ -370,6 +370,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--compute', default='f64', choices=['f64', 'tf32x3'], help='f64: DMMA path (what main.py runs); tf32x3: tcgen05 mode')
     ap.add_argument('--no-gemm-timing', action='store_true', help='(diagnostic) do not instrument GEMM launches with events')
     ap.add_argument('--no-clocks', action='store_true', help='(diagnostic) do not sample nvidia-smi during the timed region')
     args = ap.parse_args()

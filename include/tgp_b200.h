@@ -42,7 +42,9 @@ typedef struct TgpFlowLayer {
 } TgpFlowLayer;
 
 typedef struct TgpModel {            /* host struct; describes one output GP */
-    int dtype;                       /* TGP_F64 (TGP_F32 reserved)                                         */
+    int dtype;                       /* TGP_F64: all FP64 (DMMA).  TGP_F32: batch contractions as 3xTF32 on
+                                      * tcgen05 with FP32 TMEM accumulators; per-step factorisation, chain and the
+                                      * row epilogue stay FP64; inputs / outputs are FP64 in both modes          */
     int M, D;                        /* inducing points, input dimension                                   */
     int likelihood;                  /* TGP_LIK_*                                                          */
     int n_quad;                      /* Gauss-Hermite points (config.py:45,58: 100 in FP64, 50 in FP32)    */
@@ -130,6 +132,11 @@ int tgp_gemm_timing(int enable, double* ms_out, long* launches_out);
 int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_layout, const double* B, long ldb,
                        int b_layout, double* C, long ldc, double alpha, double beta, int a_tri, int b_tri,
                        int c_lower, void* stream);
+/* Test hook: the tcgen05 3xTF32 GEMM of the FP32 mode.  D[m,n] (+)= sum_k A[m,k] B[n,k]; operands are K-major FP32 plane
+ * pairs (x, x - tf32_trunc(x)); out_mode 0 stores FP32 into Cf, out_mode 1 atomically adds into FP64 Cd. */
+int tgp_debug_gemm_tf32x3(int Mrows, int Ncols, int K, const float* Ahi, const float* Alo, long lda, const float* Bhi,
+                          const float* Blo, long ldb, float* Cf, double* Cd, long ldc, int out_mode, int tri_mode,
+                          int tri_rows, int lower_rows, int splitk, void* stream);
 /* Test hook: copies L, L^-1, C (each M x M, row-major, ld = M) out of a prepared step workspace. */
 int tgp_debug_export_step(const TgpModel* model, const void* step_ws, double* L, double* Linv, double* C,
                           void* stream);

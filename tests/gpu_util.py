@@ -40,10 +40,10 @@ def engine_inputs(p, device):
                 m=f(p['m']), L_raw=f(p['L_raw']), log_var_noise=f(p['log_var_noise'].reshape(1)))
 
 
-def make_engine(p, likelihood, n_quad, device):
+def make_engine(p, likelihood, n_quad, device, compute='f64'):
     fl, theta, rowp, names = flow_layout_and_params(p['flow'], device)
     if likelihood == 'gauss_linear':
         fl = FlowLayout([])
         theta = torch.zeros(0, dtype=torch.float64, device=device)
-    eng = Engine(p['Z'].shape[0], p['Z'].shape[1], likelihood, n_quad, fl, device)
+    eng = Engine(p['Z'].shape[0], p['Z'].shape[1], likelihood, n_quad, fl, device, compute=compute)
     return eng, theta, rowp, names

@@ -33,8 +33,10 @@ def test_cabi_rejects_bad_descriptions_without_a_gpu():
     assert lib.tgp_step_workspace_bytes(m) == 0
     assert b'positive' in lib.tgp_last_error()
     m.M = 16
-    m.dtype = _lib.TGP_F32
+    m.dtype = 7
     assert lib.tgp_step_workspace_bytes(m) == 0
+    m.dtype = _lib.TGP_F32
+    assert lib.tgp_step_workspace_bytes(m) > 0
     m.dtype = _lib.TGP_F64
     assert lib.tgp_step_workspace_bytes(m) > 0
     lay = _lib.TgpReduceLayout()

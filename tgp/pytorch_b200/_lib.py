@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtgp_b200.so')
+LIB_PATH = os.environ.get('TGP_B200_LIB', os.path.join(_HERE, 'libtgp_b200.so'))
 
 TGP_F64, TGP_F32 = 0, 1
 LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
@@ -55,6 +55,7 @@ SIGNATURES = {
     'tgp_launch_count': (_L, []),
     'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'tgp_debug_gemm_f64': (_I, [_I, _I, _I, _P, _L, _I, _P, _L, _I, _P, _L, _D, _D, _I, _I, _I, _P]),
+    'tgp_debug_gemm_tf32x3': (_I, [_I, _I, _I, _P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     'tgp_debug_export_step': (_I, [C.POINTER(TgpModel), _P, _P, _P, _P, _P]),
 }
 

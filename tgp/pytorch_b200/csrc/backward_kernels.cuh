@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(ABB_COLS) k_make_abbar(double* __restrict__ AB
 //   dos      += sum_{n,j} t / os
 // sym = 1 reads Kbar symmetrised, 0.5*(Kbar[n,j] + Kbar[j,n]) (the K_zz case, where X = Zs and R = M).
 constexpr int KG_TC = 64, KG_TR = 4, KG_THREADS = KG_TC * KG_TR, KG_ROWS = 64;
-template <int MAXD>
-__global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const double* __restrict__ Kbar, long ldk,
+template <int MAXD, typename KBT>
+__global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restrict__ Kbar, long ldk,
                                                              const double* __restrict__ X, int x_scaled,
                                                              const double* __restrict__ Zs, const double* __restrict__ ls,
                                                              const double* __restrict__ os, long R, int M, int D, int sym,
@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const double* __res
     if (j < M) {
         for (long n = n0 + ry; n < n1; n += KG_TR) {
             const int r = (int)(n - n0);
-            double kb = Kbar[n * ldk + j];
-            if (sym) kb = 0.5 * (kb + Kbar[(long)j * ldk + n]);
+            double kb = (double)Kbar[n * ldk + j];
+            if (sym) kb = 0.5 * (kb + (double)Kbar[(long)j * ldk + n]);
             double q = 0.0;
 #pragma unroll
             for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
@@ -113,11 +113,12 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const double* __res
     }
 }
 
-inline int launch_kernel_grads(const double* Kbar, long ldk, const double* X, int x_scaled, const double* Zs,
+template <typename KBT>
+inline int launch_kernel_grads(const KBT* Kbar, long ldk, const double* X, int x_scaled, const double* Zs,
                                const double* ls, const double* os, long R, int M, int D, int sym, double zscale,
                                double* dZ, double* dls, double* dos, cudaStream_t st) {
     dim3 grid((unsigned)cdiv(M, KG_TC), (unsigned)cdiv(R, KG_ROWS));
-#define TGP_KG(MD) k_kernel_grads<MD><<<grid, KG_THREADS, 0, st>>>(Kbar, ldk, X, x_scaled, Zs, ls, os, R, M, D, sym, \
+#define TGP_KG(MD) k_kernel_grads<MD, KBT><<<grid, KG_THREADS, 0, st>>>(Kbar, ldk, X, x_scaled, Zs, ls, os, R, M, D, sym, \
                                                                   zscale, dZ, dls, dos)
     if (D <= 4) TGP_KG(4);
     else if (D <= 8) TGP_KG(8);

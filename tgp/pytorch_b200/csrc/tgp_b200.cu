@@ -5,6 +5,7 @@
 #include "step_kernels.cuh"
 #include "row_kernels.cuh"
 #include "backward_kernels.cuh"
+#include "tc_driver.cuh"
 
 namespace tgp {
 char g_last_error[512] = "";
@@ -49,7 +50,7 @@ inline TgpReduceLayout reduce_layout(const TgpModel* md) {
 
 inline int validate(const TgpModel* md) {
     if (!md) return set_error(-1, "model is NULL");
-    if (md->dtype != TGP_F64) return set_error(-1, "only TGP_F64 is implemented in this build");
+    if (md->dtype != TGP_F64 && md->dtype != TGP_F32) return set_error(-1, "dtype must be TGP_F64 or TGP_F32");
     if (md->M < 1 || md->D < 1) return set_error(-1, "M and D must be positive");
     if (md->n_layers < 0 || md->n_layers > TGP_MAX_LAYERS) return set_error(-1, "too many flow layers");
     if (md->n_theta < 0 || md->n_theta > MAX_THETA) return set_error(-1, "too many global flow parameters");
@@ -92,11 +93,12 @@ int tgp_version(void) { return 100; }
 
 size_t tgp_step_workspace_bytes(const TgpModel* md) {
     if (validate(md)) return 0;
-    return step_ws_doubles(md->M, md->D) * sizeof(double);
+    return step_ws_doubles(md->M, md->D) * sizeof(double) + tc::step_plane_floats(md->M) * sizeof(float);
 }
 
 size_t tgp_batch_workspace_bytes(const TgpModel* md, long R) {
     if (validate(md) || R < 0) return 0;
+    if (md->dtype == TGP_F32) return tc::batch_plane_floats(md->M, R) * sizeof(float);
     return batch_ws_doubles(md->M, R) * sizeof(double);
 }
 
@@ -112,8 +114,10 @@ int tgp_prepare(const TgpModel* md, const TgpParams* p, double jitter, void* ste
     TGP_TRY(validate(md));
     if (!p || !step_ws || !kl_out || !status) return set_error(-1, "NULL argument to tgp_prepare");
     StepView v = carve_step(step_ws, md->M, md->D);
-    return run_prepare(v, (const double*)p->Z, (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale,
-                       (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, (cudaStream_t)stream);
+    TGP_TRY(run_prepare(v, (const double*)p->Z, (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale,
+                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, (cudaStream_t)stream));
+    if (md->dtype == TGP_F32) TGP_TRY(tc::make_step_planes(v, step_ws, (cudaStream_t)stream));
+    return 0;
 }
 
 int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, const void* X, long R, void* mu, void* v,
@@ -124,6 +128,8 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
     cudaStream_t st = (cudaStream_t)stream;
     const int M = md->M, D = md->D;
     StepView s = carve_step(const_cast<void*>(step_ws), M, D);
+    if (md->dtype == TGP_F32)
+        return tc::qf_forward(s, const_cast<void*>(step_ws), batch_ws, (const double*)X, R, (double*)mu, (double*)v, st);
     BatchView b = carve_batch(batch_ws, M, R);
     const double* Xd = (const double*)X;
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
@@ -183,6 +189,9 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
     const double* Xd = (const double*)X;
     double* Gbar = reduce_buf + l.Gbar;
     double* Cbar = reduce_buf + l.Cbar;
+    if (md->dtype == TGP_F32)
+        return tc::qf_backward(s, const_cast<void*>(step_ws), batch_ws, Xd, R, (const double*)g_mu, (const double*)g_v,
+                               reduce_buf + l.dm, reduce_buf + l.dos, reduce_buf + l.dZ, reduce_buf + l.dls, Gbar, Cbar, st);
     {
         dim3 grid((unsigned)cdiv(M, ABB_COLS), (unsigned)cdiv(R, ABB_ROWS));
         k_make_abbar<<<grid, ABB_COLS, 0, st>>>(b.AB, (const double*)g_mu, (const double*)g_v, s.mvec, R, M,
@@ -331,6 +340,17 @@ int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_lay
     GemmArgs g = make_gemm(M, N, K, A, lda, a_layout, B, ldb, b_layout, C, ldc, alpha, beta);
     g.a_tri = a_tri; g.b_tri = b_tri; g.c_lower = c_lower;
     return gemm_f64(g, (cudaStream_t)stream);
+}
+
+int tgp_debug_gemm_tf32x3(int Mrows, int Ncols, int K, const float* Ahi, const float* Alo, long lda, const float* Bhi,
+                          const float* Blo, long ldb, float* Cf, double* Cd, long ldc, int out_mode, int tri_mode,
+                          int tri_rows, int lower_rows, int splitk, void* stream) {
+    tc::Params p{};
+    p.Mrows = Mrows; p.Ncols = Ncols; p.K = K; p.tri_mode = tri_mode; p.tri_rows = tri_rows; p.out_mode = out_mode;
+    p.lower_rows = lower_rows; p.Cf = Cf; p.Cd = Cd; p.ldc = ldc; p.splitk = splitk;
+    tc::Operand A{Ahi, Alo, Mrows, K, lda};
+    tc::Operand B{Bhi, Blo, Ncols, K, ldb};
+    return tc::gemm_tf32x3(A, B, p, (cudaStream_t)stream);
 }
 
 int tgp_debug_export_step(const TgpModel* md, const void* step_ws, double* L, double* Linv, double* C, void* stream) {

@@ -94,7 +94,7 @@ def _chk(t, name, shape=None):
 
 
 class Engine:
-    def __init__(self, M, D, likelihood, n_quad, flow_layout, device):
+    def __init__(self, M, D, likelihood, n_quad, flow_layout, device, compute='f64'):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -103,7 +103,10 @@ class Engine:
         self.likelihood = likelihood
         self.flow = flow_layout
         self.model = _lib.TgpModel()
-        self.model.dtype = _lib.TGP_F64
+        if compute not in ('f64', 'tf32x3'):
+            raise ValueError("compute must be 'f64' or 'tf32x3'")
+        self.compute = compute
+        self.model.dtype = _lib.TGP_F64 if compute == 'f64' else _lib.TGP_F32
         self.model.M, self.model.D = self.M, self.D
         self.model.likelihood = _LIK[likelihood]
         self.model.n_quad = int(n_quad)
@@ -230,3 +233,23 @@ def debug_gemm(A, B, C_out, M, N, K, lda, ldb, ldc, a_layout, b_layout, alpha=1.
     lib = _lib.load()
     _lib.check(lib.tgp_debug_gemm_f64(M, N, K, _ptr(A), lda, a_layout, _ptr(B), ldb, b_layout, _ptr(C_out), ldc,
                                       float(alpha), float(beta), a_tri, b_tri, c_lower, _stream()), 'tgp_debug_gemm_f64')
+
+
+def tf32_planes(x):
+    """(rn_tf32(x), x - rn_tf32(x)) for an FP32 tensor — the operand format of the tcgen05 3xTF32 GEMM."""
+    hi = ((x.view(torch.int32) + 0x1000) & -8192).view(torch.float32)     # round-to-nearest TF32 (cvt.rna)
+    return hi, x - hi
+
+
+def debug_gemm_tf32x3(A, B, out, out_mode=0, tri_mode=0, tri_rows=0, lower_rows=0, splitk=1):
+    """out (+)= A @ B.T with A (Mrows, K), B (Ncols, K) FP32 row-major; out FP32 (mode 0) or FP64 accumulated (mode 1)."""
+    lib = _lib.load()
+    Ah, Al = tf32_planes(A.contiguous())
+    Bh, Bl = tf32_planes(B.contiguous())
+    Mrows, K = A.shape
+    Ncols = B.shape[0]
+    _lib.check(lib.tgp_debug_gemm_tf32x3(Mrows, Ncols, K, _ptr(Ah), _ptr(Al), A.stride(0), _ptr(Bh), _ptr(Bl), B.stride(0),
+                                         _ptr(out) if out_mode == 0 else None, _ptr(out) if out_mode == 1 else None,
+                                         out.stride(0), out_mode, tri_mode, tri_rows, lower_rows, splitk, _stream()),
+               'tgp_debug_gemm_tf32x3')
+    return Ah, Al, Bh, Bl
