@@ -123,8 +123,8 @@ int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
 long tgp_launch_count(void);
 /* Live per-launch timing of the GEMM kernel with CUDA events on the launching stream (bench.py's roofline).
- * Returns the accumulated milliseconds / launch counts per class ([0] per-step O(M^3) work, [1] batch contractions)
- * since the last reset into ms_out[2] / launches_out[2] (host pointers, may be NULL), then enable = 1 / 0 switches the
+ * Returns the accumulated milliseconds / launch counts per class ([0] FP64 per-step O(M^3) work, [1] FP64 batch
+ * contractions, [2] tcgen05 batch contractions) since the last reset into ms_out[3] / launches_out[3] (host, may be NULL), then enable = 1 / 0 switches the
  * instrumentation on / off and resets the accumulators; enable < 0 only reads.  Synchronises on the recorded events. */
 int tgp_gemm_timing(int enable, double* ms_out, long* launches_out);
 

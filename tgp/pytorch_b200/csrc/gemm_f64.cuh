@@ -42,8 +42,8 @@ struct GemmTimer {
     cudaEvent_t ev[2 * MAXEV];
     int tagv[MAXEV];
     int n = 0, created = 0;
-    double ms[2] = {0, 0};
-    long launches[2] = {0, 0};
+    double ms[3] = {0, 0, 0};
+    long launches[3] = {0, 0, 0};
     void begin(int tag, cudaStream_t st) {
         if (n >= MAXEV) flush();
         while (created < 2 * (n + 1)) { cudaEventCreate(&ev[created]); ++created; }

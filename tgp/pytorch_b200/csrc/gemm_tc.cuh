@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include "gemm_f64.cuh"      // GemmTimer (shared live-timing hook)
 
 namespace tgp {
 namespace tc {
@@ -339,7 +340,10 @@ inline int gemm_tf32x3(const Operand& A, const Operand& B, Params p, cudaStream_
     const long tiles = (long)cdiv(p.Mrows, BM) * cdiv(p.Ncols, BN) * (p.splitk > 1 ? p.splitk : 1);
     int sms = 148;
     const int grid = (int)(tiles < sms ? tiles : sms);
+    const bool timed = g_gemm_timer.enabled;
+    if (timed) g_gemm_timer.begin(2, st);
     gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mAl, mB, mBl, p);
+    if (timed) g_gemm_timer.end(st);
     return check_launch("gemm_tf32x3_kernel");
 }
 

@@ -8,7 +8,7 @@
 namespace tgp {
 
 constexpr int POTRF_NB = 64;
-constexpr int POTRF_SMEM = 2 * POTRF_NB * (POTRF_NB + 1) * (int)sizeof(double);
+constexpr int POTRF_SMEM = (POTRF_NB * (POTRF_NB + 1) + POTRF_NB + 8) * (int)sizeof(double);
 
 // ls = softplus(raw_ls), os = softplus(raw_os), Zs = Z / ls      (gpytorch: x.div(lengthscale))
 __global__ void k_transform_params(const double* __restrict__ Z, const double* __restrict__ raw_ls,
@@ -76,56 +76,72 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
     return check_launch("k_rbf_tile");
 }
 
-// Factor the kb-th 64x64 diagonal block of the (partially updated) matrix Aw in place: L_kk -> Lout (upper zero),
+// Factor the kb-th 64x64 diagonal block of the (partially updated) matrix Aw: L_kk -> Lout (upper zero),
 // L_kk^-1 -> Dinv (dense 64x64, upper zero) and -> the diagonal block of Linv.
 // status[0] = 1-based index of the first non-positive / NaN pivot (0 = ok); only the first failure is recorded.
-__global__ void __launch_bounds__(256) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
-                                                    double* __restrict__ Linv, double* __restrict__ Dinv, int kb,
-                                                    long ld, int* __restrict__ status) {
+//
+// One CTA of 64 threads on the critical path of the factorisation, so it is written for latency: thread t keeps row t of
+// the block in registers (fully unrolled, static indices); column j is broadcast through shared memory with two
+// barriers per column; the inverse is a forward substitution with thread c owning column c (four partial sums to break
+// the dependent-FMA chain).
+__global__ void __launch_bounds__(POTRF_NB) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
+                                                         double* __restrict__ Linv, double* __restrict__ Dinv, int kb,
+                                                         long ld, int* __restrict__ status) {
     constexpr int NB = POTRF_NB, LDS = NB + 1;
     extern __shared__ double sm_potrf[];
-    double* a = sm_potrf;
-    double* inv = sm_potrf + NB * LDS;
-    const int tid = threadIdx.x;
+    double* Ls = sm_potrf;                 // [NB][LDS]
+    double* col = sm_potrf + NB * LDS;     // [NB]
+    double* piv = col + NB;                // [1]
+    const int t = threadIdx.x;
     const long base = (long)kb * NB * ld + (long)kb * NB;
-    for (int i = tid; i < NB * NB; i += 256) {
-        const int r = i / NB, c = i % NB;
-        a[r * LDS + c] = (c <= r) ? Aw[base + (long)r * ld + c] : 0.0;
-        inv[r * LDS + c] = 0.0;
+    for (int r = 0; r < NB; ++r) Ls[r * LDS + t] = (t <= r) ? Aw[base + (long)r * ld + t] : 0.0;
+    __syncthreads();
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a[c] = Ls[t * LDS + c];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        if (t == j) {
+            double d = a[j];
+            if (!(d > 0.0)) atomicCAS(status, 0, kb * NB + j + 1);
+            d = sqrt(d);
+            a[j] = d;
+            piv[0] = d;
+        }
+        __syncthreads();
+        if (t > j) a[j] = a[j] / piv[0];
+        col[t] = a[j];
+        __syncthreads();
+        if (t > j) {
+            const double lij = a[j];
+#pragma unroll
+            for (int k = j + 1; k < NB; ++k) if (k <= t) a[k] = fma(-lij, col[k], a[k]);
+        }
     }
     __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        if (tid == 0) {
-            const double d = a[j * LDS + j];
-            if (!(d > 0.0)) atomicCAS(status, 0, kb * NB + j + 1);
-            a[j * LDS + j] = sqrt(d);
-        }
-        __syncthreads();
-        const double djj = a[j * LDS + j];
-        if (tid > j && tid < NB) a[tid * LDS + j] /= djj;
-        __syncthreads();
-        const int n = NB - 1 - j;
-        for (int idx = tid; idx < n * n; idx += 256) {
-            const int i = j + 1 + idx / n, k = j + 1 + idx % n;
-            if (k <= i) a[i * LDS + k] -= a[i * LDS + j] * a[k * LDS + j];
-        }
-        __syncthreads();
-    }
-    // inverse by forward substitution, row by row; thread (c, q) sums k == q (mod 4) for column c
-    const int c = tid >> 2, q = tid & 3;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) Ls[t * LDS + c] = a[c];
+    __syncthreads();
+    for (int r = 0; r < NB; ++r) Lout[base + (long)r * ld + t] = Ls[r * LDS + t];
+    // inverse: thread t owns column t of X = L^-1 (x[i] = 0 for i < t falls out of the recurrence)
+    double x[NB];
+#pragma unroll
     for (int i = 0; i < NB; ++i) {
-        double s = 0.0;
-        if (c <= i) for (int k = c + q; k < i; k += 4) s = fma(a[i * LDS + k], inv[k * LDS + c], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (q == 0 && c <= i) inv[i * LDS + c] = ((i == c ? 1.0 : 0.0) - s) / a[i * LDS + i];
-        __syncthreads();
+        double s0 = (i == t) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double l = Ls[i * LDS + k];
+            if ((k & 3) == 0) s0 = fma(-l, x[k], s0);
+            else if ((k & 3) == 1) s1 = fma(-l, x[k], s1);
+            else if ((k & 3) == 2) s2 = fma(-l, x[k], s2);
+            else s3 = fma(-l, x[k], s3);
+        }
+        x[i] = (i < t) ? 0.0 : ((s0 + s1) + (s2 + s3)) / Ls[i * LDS + i];
     }
-    for (int i = tid; i < NB * NB; i += 256) {
-        const int r = i / NB, cc = i % NB;
-        Lout[base + (long)r * ld + cc] = a[r * LDS + cc];
-        Linv[base + (long)r * ld + cc] = inv[r * LDS + cc];
-        Dinv[i] = inv[r * LDS + cc];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        Linv[base + (long)i * ld + t] = x[i];
+        Dinv[i * NB + t] = x[i];
     }
 }
 
@@ -225,7 +241,7 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
 
     // right-looking blocked Cholesky; the panel solve is a GEMM with the inverted diagonal block
     for (int kb = 0; kb < nb; ++kb) {
-        k_potrf_diag<<<1, 256, POTRF_SMEM, st>>>(v.Kzz, v.L, v.Linv, v.Dinv, kb, Mp, status);
+        k_potrf_diag<<<1, POTRF_NB, POTRF_SMEM, st>>>(v.Kzz, v.L, v.Linv, v.Dinv, kb, Mp, status);
         TGP_TRY(check_launch("k_potrf_diag"));
         const int rem = Mp - (kb + 1) * NB;
         if (rem <= 0) break;

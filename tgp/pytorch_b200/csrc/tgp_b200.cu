@@ -325,11 +325,13 @@ long tgp_launch_count(void) { return g_launch_count; }
 
 int tgp_gemm_timing(int enable, double* ms_out, long* launches_out) {
     g_gemm_timer.flush();
-    if (ms_out) { ms_out[0] = g_gemm_timer.ms[0]; ms_out[1] = g_gemm_timer.ms[1]; }
-    if (launches_out) { launches_out[0] = g_gemm_timer.launches[0]; launches_out[1] = g_gemm_timer.launches[1]; }
+    for (int i = 0; i < 3; ++i) {
+        if (ms_out) ms_out[i] = g_gemm_timer.ms[i];
+        if (launches_out) launches_out[i] = g_gemm_timer.launches[i];
+    }
     if (enable >= 0) {
         g_gemm_timer.enabled = enable != 0;
-        g_gemm_timer.ms[0] = g_gemm_timer.ms[1] = 0; g_gemm_timer.launches[0] = g_gemm_timer.launches[1] = 0;
+        for (int i = 0; i < 3; ++i) { g_gemm_timer.ms[i] = 0; g_gemm_timer.launches[i] = 0; }
     }
     return 0;
 }

@@ -36,6 +36,8 @@ positive_transform = 'exp'
 strict_flag = True
 constant_jitter = None
 global_jitter = None
+compute = 'f64'                # 'f64': FP64 DMMA path (parity mode, what main.py's set_maximum_precission runs);
+                               # 'tf32x3': batch contractions on tcgen05 (3xTF32, FP32 accumulate), rest FP64
 check_cholesky_status = True    # False: skip the 4-byte status read-back after the factorisation (no host sync)
 
 device = check_device()

@@ -149,10 +149,10 @@ class sparse_MF_SP(nn.Module):
 
     def _engine(self, dy, layout, device):
         kind = _LIK_KIND[type(self.likelihood)]
-        key = (dy, kind, self.quad_points, tuple(tuple(sorted(l.items())) for l in layout.layers), str(device))
+        key = (dy, kind, self.quad_points, tuple(tuple(sorted(l.items())) for l in layout.layers), str(device), cg.compute)
         if key not in self._engines:
             self._engines[key] = Engine(self.M, self.inp_dim, kind, self.quad_points if kind != 'gauss_linear' else 0,
-                                        layout, device)
+                                        layout, device, compute=cg.compute)
         return self._engines[key]
 
     def _rows3(self, X):
@@ -178,9 +178,10 @@ class sparse_MF_SP(nn.Module):
         mus, vs = [], []
         for dy in range(self.out_dim):
             Z, raw_ls, raw_os, m, L_raw = self._gp_params(dy)
-            key = ('qf', dy, str(X.device))
+            key = ('qf', dy, str(X.device), cg.compute)
             if key not in self._engines:     # marginals do not involve the flow / likelihood
-                self._engines[key] = Engine(self.M, self.inp_dim, 'gauss_linear', 0, FlowLayout([]), X.device)
+                self._engines[key] = Engine(self.M, self.inp_dim, 'gauss_linear', 0, FlowLayout([]), X.device,
+                                            compute=cg.compute)
             eng = self._engines[key]
             mu, v = Fn.qf_marginals(eng, X[dy].contiguous(), Z, raw_ls, raw_os, m, L_raw, cg.check_cholesky_status)
             mus.append(mu)

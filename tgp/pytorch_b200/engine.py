@@ -237,7 +237,11 @@ def debug_gemm(A, B, C_out, M, N, K, lda, ldb, ldc, a_layout, b_layout, alpha=1.
 
 def tf32_planes(x):
     """(rn_tf32(x), x - rn_tf32(x)) for an FP32 tensor — the operand format of the tcgen05 3xTF32 GEMM."""
-    hi = ((x.view(torch.int32) + 0x1000) & -8192).view(torch.float32)     # round-to-nearest TF32 (cvt.rna)
+    bits = x.contiguous().view(torch.int32)
+    half = torch.tensor(0x1000, dtype=torch.int32, device=x.device)
+    mask = torch.tensor(-8192, dtype=torch.int32, device=x.device)
+    hi = torch.bitwise_and(bits + half, mask).view(torch.float32)        # round-to-nearest TF32 (cvt.rna)
+    assert hi.shape == x.shape
     return hi, x - hi
 
 
