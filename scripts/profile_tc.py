@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+torch.set_default_dtype(torch.float32)
 from tgp.pytorch_b200.engine import debug_gemm_tf32x3
 dev = 'cuda:0'
 R, M = 16384, 1024

@@ -19,8 +19,8 @@ def test_tcgen05_gemm_matches_fp64_matmul(Mr, Nc, K):
     Kp = (K + 3) // 4 * 4
     A = torch.zeros(Mr, Kp, dtype=torch.float32)
     B = torch.zeros(Nc, Kp, dtype=torch.float32)
-    A[:, :K] = torch.randn(Mr, K, generator=g)
-    B[:, :K] = torch.randn(Nc, K, generator=g)
+    A[:, :K] = torch.randn(Mr, K, generator=g, dtype=torch.float32)
+    B[:, :K] = torch.randn(Nc, K, generator=g, dtype=torch.float32)
     A, B = A.to(DEV), B.to(DEV)
     Np = (Nc + 3) // 4 * 4
     out = torch.full((Mr, Np), 7.0, dtype=torch.float32, device=DEV)
@@ -37,8 +37,8 @@ def test_tcgen05_gemm_fp64_accumulate_splitk_lower():
     from tgp.pytorch_b200.engine import debug_gemm_tf32x3
     g = torch.Generator().manual_seed(11)
     n, K = 384, 4096
-    A = torch.randn(n, K, generator=g).to(DEV)
-    B = torch.randn(n, K, generator=g).to(DEV)
+    A = torch.randn(n, K, generator=g, dtype=torch.float32).to(DEV)
+    B = torch.randn(n, K, generator=g, dtype=torch.float32).to(DEV)
     out = torch.zeros(n, n, dtype=torch.float64, device=DEV)
     debug_gemm_tf32x3(A, B, out, out_mode=1, lower_rows=n, splitk=4)
     debug_gemm_tf32x3(A, B, out, out_mode=1, lower_rows=n, splitk=4)     # accumulates

@@ -237,6 +237,8 @@ def debug_gemm(A, B, C_out, M, N, K, lda, ldb, ldc, a_layout, b_layout, alpha=1.
 
 def tf32_planes(x):
     """(rn_tf32(x), x - rn_tf32(x)) for an FP32 tensor — the operand format of the tcgen05 3xTF32 GEMM."""
+    if x.dtype != torch.float32:
+        raise ValueError('tf32_planes expects a float32 tensor, got %s' % x.dtype)
     bits = x.contiguous().view(torch.int32)
     half = torch.tensor(0x1000, dtype=torch.int32, device=x.device)
     mask = torch.tensor(-8192, dtype=torch.int32, device=x.device)
