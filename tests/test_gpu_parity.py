@@ -69,7 +69,7 @@ def test_prepare_cholesky_inverse_kl(M, D):
              m=torch.randn(M, generator=g, dtype=torch.float64),
              L_raw=0.5 * torch.eye(M, dtype=torch.float64) + 0.05 * torch.randn(M, M, generator=g, dtype=torch.float64),
              log_var_noise=torch.tensor(-1.0, dtype=torch.float64), flow=[])
-    eng = Engine(M, D, 'gauss_linear', 0, FlowLayout([]), DEV)
+    eng = Engine(M, D, 'gauss_linear', 0, FlowLayout([]), DEV, compute='tf32x3')    # this mode also forms C
     from tests.gpu_util import engine_inputs
     ei = engine_inputs(p, DEV)
     eng.set_params(ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'],

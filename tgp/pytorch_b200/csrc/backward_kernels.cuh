@@ -6,13 +6,13 @@
 
 namespace tgp {
 
-// In place: [A | B] -> [Abar | Bbar] with Abar = g_mu*m - 2 g_v*A, Bbar = 2 g_v*B; accumulates
+// [A | B] (ld 2M): B -> Bbar = 2 g_v*B in place, A is kept; Abar[n,j] (ld M) = g_mu*m - 2 g_v*A; accumulates
 // dm[j] += sum_n g_mu[n]*A[n,j] and (block column 0) dos += sum_n g_v[n]   (K_xx diag = outputscale).
 constexpr int ABB_ROWS = 64, ABB_COLS = 128;
-__global__ void __launch_bounds__(ABB_COLS) k_make_abbar(double* __restrict__ AB, const double* __restrict__ g_mu,
-                                                         const double* __restrict__ g_v, const double* __restrict__ m,
-                                                         long R, int M, double* __restrict__ dm,
-                                                         double* __restrict__ dos) {
+__global__ void __launch_bounds__(ABB_COLS) k_make_abbar(double* __restrict__ AB, double* __restrict__ Abar,
+                                                         const double* __restrict__ g_mu, const double* __restrict__ g_v,
+                                                         const double* __restrict__ m, long R, int M,
+                                                         double* __restrict__ dm, double* __restrict__ dos) {
     const int j = blockIdx.x * ABB_COLS + threadIdx.x;
     const long n0 = (long)blockIdx.y * ABB_ROWS, n1 = min(n0 + ABB_ROWS, R);
     const double mj = j < M ? m[j] : 0.0;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(ABB_COLS) k_make_abbar(double* __restrict__ AB
             double* row = AB + n * 2 * M;
             const double a = row[j], b = row[M + j];
             acc = fma(gm, a, acc);
-            row[j] = gm * mj - 2.0 * gv * a;
+            Abar[n * M + j] = gm * mj - 2.0 * gv * a;
             row[M + j] = 2.0 * gv * b;
         }
     }

@@ -217,7 +217,7 @@ inline StepView carve_step(void* ws, int M, int D) {
 // K_zz (+jitter) -> L, L^-1 (explicit), C = L_S^T L^-1, KL.  Everything stays on `st`; no host sync.
 inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls, const double* raw_os,
                        const double* m, const double* Lraw, double jitter, double* kl_out, int* status,
-                       cudaStream_t st) {
+                       bool need_C, cudaStream_t st) {
     const int M = v.M, Mp = v.Mp, D = v.D, NB = POTRF_NB, nb = Mp / NB;
     const size_t mm = (size_t)Mp * Mp;
     static bool potrf_attr = false;
@@ -269,9 +269,11 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
         TGP_TRY(gemm_f64(x, st));
     }
     // C = L_S^T L^-1   (Aop[m,k] = LS[k,m], nonzero k >= m;  Bop[n,k] = Linv[k,n], nonzero k >= n)
-    GemmArgs c = make_gemm(M, M, M, v.LS, Mp, 1, v.Linv, Mp, 1, v.Cm, Mp);
-    c.a_tri = 2; c.b_tri = 2;
-    TGP_TRY(gemm_f64(c, st));
+    if (need_C) {      // only the tensor-core mode contracts with C; the FP64 mode applies L_S to A directly
+        GemmArgs c = make_gemm(M, M, M, v.LS, Mp, 1, v.Linv, Mp, 1, v.Cm, Mp);
+        c.a_tri = 2; c.b_tri = 2;
+        TGP_TRY(gemm_f64(c, st));
+    }
     return 0;
 }
 

@@ -14,14 +14,14 @@ GemmTimer g_gemm_timer;
 
 constexpr long ROW_CHUNK = 8192;     // rows whose K / Kbar tiles are staged at once (L2-sized for M = 1024)
 
-struct BatchView { double *AB, *Kbuf, *Kbar; long Rc; };
+struct BatchView { double *AB, *Kbuf, *Kbar, *Abar; long Rc; };
 
 inline long chunk_rows(long R) { return R < ROW_CHUNK ? R : ROW_CHUNK; }
 inline long even(long x) { return (x + 1) / 2 * 2; }
 
 inline size_t batch_ws_doubles(int M, long R) {
     const long Rc = chunk_rows(R);
-    return (size_t)even(R * 2 * M) + 2 * (size_t)even(Rc * M) + 16;
+    return (size_t)even(R * 2 * M) + 3 * (size_t)even(Rc * M) + 16;
 }
 
 inline BatchView carve_batch(void* ws, int M, long R) {
@@ -30,7 +30,8 @@ inline BatchView carve_batch(void* ws, int M, long R) {
     double* p = reinterpret_cast<double*>(ws);
     b.AB = p; p += even(R * 2 * M);
     b.Kbuf = p; p += even(b.Rc * M);
-    b.Kbar = p;
+    b.Kbar = p; p += even(b.Rc * M);
+    b.Abar = p;
     return b;
 }
 
@@ -115,7 +116,8 @@ int tgp_prepare(const TgpModel* md, const TgpParams* p, double jitter, void* ste
     if (!p || !step_ws || !kl_out || !status) return set_error(-1, "NULL argument to tgp_prepare");
     StepView v = carve_step(step_ws, md->M, md->D);
     TGP_TRY(run_prepare(v, (const double*)p->Z, (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale,
-                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, (cudaStream_t)stream));
+                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, md->dtype == TGP_F32,
+                        (cudaStream_t)stream));
     if (md->dtype == TGP_F32) TGP_TRY(tc::make_step_planes(v, step_ws, (cudaStream_t)stream));
     return 0;
 }
@@ -140,8 +142,9 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
         ga.b_tri = 1;
         ga.tag = 1;
         TGP_TRY(gemm_f64(ga, st));
-        // B = K C^T
-        GemmArgs gb = make_gemm(rc, M, M, b.Kbuf, M, 0, s.Cm, s.Mp, 0, b.AB + r0 * 2 * M + M, 2 * M);
+        // B = A L_S   (Bop[n,k] = L_S[k,n], nonzero k >= n) — the reference's two-contraction form, both triangular
+        GemmArgs gb = make_gemm(rc, M, M, b.AB + r0 * 2 * M, 2 * M, 0, s.LS, s.Mp, 1, b.AB + r0 * 2 * M + M, 2 * M);
+        gb.b_tri = 2;
         gb.tag = 1;
         TGP_TRY(gemm_f64(gb, st));
     }
@@ -192,35 +195,36 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
     if (md->dtype == TGP_F32)
         return tc::qf_backward(s, const_cast<void*>(step_ws), batch_ws, Xd, R, (const double*)g_mu, (const double*)g_v,
                                reduce_buf + l.dm, reduce_buf + l.dos, reduce_buf + l.dZ, reduce_buf + l.dls, Gbar, Cbar, st);
-    {
-        dim3 grid((unsigned)cdiv(M, ABB_COLS), (unsigned)cdiv(R, ABB_ROWS));
-        k_make_abbar<<<grid, ABB_COLS, 0, st>>>(b.AB, (const double*)g_mu, (const double*)g_v, s.mvec, R, M,
-                                                reduce_buf + l.dm, reduce_buf + l.dos);
-        TGP_TRY(check_launch("k_make_abbar"));
-    }
+    // FP64 mode keeps the reference's two dependent triangular contractions (a = L^-1 k, b = L_S^T a):
+    //   Bbar = 2 g_v B;  Abar = g_mu m - 2 g_v A + Bbar L_S^T;  Kbar = Abar L^-1;
+    //   Gbar += tril(Abar^T K);  dL_S += tril(A^T Bbar)   (accumulated in the `Cbar` slot of the reduce buffer)
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
-        const double* ABc = b.AB + r0 * 2 * M;
+        double* ABc = b.AB + r0 * 2 * M;
+        {
+            dim3 grid((unsigned)cdiv(M, ABB_COLS), (unsigned)cdiv(rc, ABB_ROWS));
+            k_make_abbar<<<grid, ABB_COLS, 0, st>>>(ABc, b.Abar, (const double*)g_mu + r0, (const double*)g_v + r0, s.mvec,
+                                                    rc, M, reduce_buf + l.dm, reduce_buf + l.dos);
+            TGP_TRY(check_launch("k_make_abbar"));
+        }
+        // Abar += Bbar * L_S^T   (Bop[n,k] = L_S[n,k], nonzero k <= n)
+        GemmArgs g0 = make_gemm(rc, M, M, ABc + M, 2 * M, 0, s.LS, s.Mp, 0, b.Abar, M, 1.0, 1.0);
+        g0.b_tri = 1; g0.tag = 1;
+        TGP_TRY(gemm_f64(g0, st));
         TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf, M, rc, M, 0.0, st));
-        // Kbar = Abar * Linv + Bbar * C     (Bop[n,k] = Linv[k,n], nonzero k >= n)
-        GemmArgs g1 = make_gemm(rc, M, M, ABc, 2 * M, 0, s.Linv, s.Mp, 1, b.Kbar, M);
-        g1.b_tri = 2;
-        g1.tag = 1;
+        // Kbar = Abar * Linv     (Bop[n,k] = Linv[k,n], nonzero k >= n)
+        GemmArgs g1 = make_gemm(rc, M, M, b.Abar, M, 0, s.Linv, s.Mp, 1, b.Kbar, M);
+        g1.b_tri = 2; g1.tag = 1;
         TGP_TRY(gemm_f64(g1, st));
-        GemmArgs g2 = make_gemm(rc, M, M, ABc + M, 2 * M, 0, s.Cm, s.Mp, 1, b.Kbar, M, 1.0, 1.0);
-        g2.tag = 1;
-        TGP_TRY(gemm_f64(g2, st));
         TGP_TRY(launch_kernel_grads(b.Kbar, M, Xd + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, reduce_buf + l.dZ,
                                     reduce_buf + l.dls, reduce_buf + l.dos, st));
-        // Gbar += tril(Abar^T K),  Cbar += Bbar^T K      (reduction over the rows of the chunk)
-        GemmArgs g3 = make_gemm(M, M, rc, ABc, 2 * M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
-        g3.c_lower = 1;
-        g3.splitk = weight_splitk(M, rc);
-        g3.tag = 1;
+        // Gbar += tril(Abar^T K)      (reduction over the rows of the chunk)
+        GemmArgs g3 = make_gemm(M, M, rc, b.Abar, M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
+        g3.c_lower = 1; g3.splitk = weight_splitk(M, rc); g3.tag = 1;
         TGP_TRY(gemm_f64(g3, st));
-        GemmArgs g4 = make_gemm(M, M, rc, ABc + M, 2 * M, 1, b.Kbuf, M, 1, Cbar, s.Mp, 1.0, 1.0);
-        g4.splitk = weight_splitk(M, rc);
-        g4.tag = 1;
+        // dL_S += tril(A^T Bbar)
+        GemmArgs g4 = make_gemm(M, M, rc, ABc, 2 * M, 1, ABc + M, 2 * M, 1, Cbar, s.Mp, 1.0, 1.0);
+        g4.c_lower = 1; g4.splitk = weight_splitk(M, rc); g4.tag = 1;
         TGP_TRY(gemm_f64(g4, st));
     }
     return 0;
@@ -242,16 +246,21 @@ int tgp_chain_backward(const TgpModel* md, const TgpParams* p, void* step_ws, co
     double* Gtot = s.Kzz;                          // K_zz's buffer is free after the factorisation
     double* dZacc = s.S3;                          // (M*D) accumulators live at the head of S3 until Phi needs it
 
-    // dLS = tril(Linv * Cbar^T)
-    GemmArgs a1 = make_gemm(M, M, M, s.Linv, Mp, 0, Cbar, Mp, 0, s.S0, Mp);
-    a1.a_tri = 1; a1.c_lower = 1;
-    cudaMemsetAsync(s.S0, 0, mm * sizeof(double), st);
-    TGP_TRY(gemm_f64(a1, st));
-    // Gtot = Gbar + tril(LS * Cbar)
-    cudaMemcpyAsync(Gtot, reduce_buf + l.Gbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
-    GemmArgs a2 = make_gemm(M, M, M, s.LS, Mp, 0, Cbar, Mp, 1, Gtot, Mp, 1.0, 1.0);
-    a2.a_tri = 1; a2.c_lower = 1;
-    TGP_TRY(gemm_f64(a2, st));
+    if (md->dtype == TGP_F32) {
+        // tensor-core mode carries C = L_S^T L^-1:  dLS = tril(Linv * Cbar^T),  Gtot = Gbar + tril(LS * Cbar)
+        GemmArgs a1 = make_gemm(M, M, M, s.Linv, Mp, 0, Cbar, Mp, 0, s.S0, Mp);
+        a1.a_tri = 1; a1.c_lower = 1;
+        cudaMemsetAsync(s.S0, 0, mm * sizeof(double), st);
+        TGP_TRY(gemm_f64(a1, st));
+        cudaMemcpyAsync(Gtot, reduce_buf + l.Gbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        GemmArgs a2 = make_gemm(M, M, M, s.LS, Mp, 0, Cbar, Mp, 1, Gtot, Mp, 1.0, 1.0);
+        a2.a_tri = 1; a2.c_lower = 1;
+        TGP_TRY(gemm_f64(a2, st));
+    } else {
+        // FP64 mode: the batch pass already accumulated dL_S (in the Cbar slot) and the complete Gbar
+        cudaMemcpyAsync(s.S0, Cbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(Gtot, reduce_buf + l.Gbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    }
     // T1 = Gtot * Linv^T
     GemmArgs a3 = make_gemm(M, M, M, Gtot, Mp, 0, s.Linv, Mp, 0, s.S1, Mp);
     a3.a_tri = 1; a3.b_tri = 1;
