@@ -241,12 +241,18 @@ def run_ours(args):
         # pre-warm until the step time is steady (a fresh box starts with cold clocks / lazily loaded modules):
         # stop when three consecutive steps agree within 3 %, or after 8 s
         t_pre, recent = time.perf_counter(), []
-        while time.perf_counter() - t_pre < 8.0:
+        while True:
             t0 = time.perf_counter()
             step_fn(*dev_batch(0))
             torch.cuda.synchronize()
             recent = (recent + [time.perf_counter() - t0])[-3:]
-            if len(recent) == 3 and time.perf_counter() - t_pre > 2.0 and max(recent) < 1.03 * min(recent):
+            el = time.perf_counter() - t_pre
+            done = el > 8.0 or (len(recent) == 3 and el > 2.0 and max(recent) < 1.03 * min(recent))
+            if world > 1:                               # every rank must leave the loop in the same iteration
+                flag = torch.tensor([1.0 if done else 0.0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                done = bool(flag.item() > 0.5)
+            if done:
                 break
         for s in range(args.warmup):
             step_fn(*dev_batch(s))

@@ -2,6 +2,7 @@
 // derivatives w.r.t. Z / lengthscale / outputscale (K tiles recomputed on the fly), final raw-parameter gradients.
 // Mathematics: SURVEY.md Appendix B (derived from sparse_MF_SP.py:352-382 and autograd through them).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace tgp {
@@ -55,27 +56,42 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
         const long n = n0 + r;
         xs[r][d] = n < R ? (x_scaled ? X[n * D + d] : X[n * D + d] / ls[d]) : 0.0;
     }
-    double zj[MAXD], az[MAXD], al[MAXD];
+    // FP32 mode (Kbar arrives as float from the tensor-core GEMM): differences, exponential and the <= 16 per-thread
+    // partial sums run in FP32; everything that crosses threads is accumulated in FP64
+    using AccT = typename std::conditional<std::is_same<KBT, float>::value, float, double>::type;
+    double zj[MAXD];
+    AccT az[MAXD], al[MAXD];
 #pragma unroll
-    for (int d = 0; d < MAXD; ++d) { zj[d] = (d < D && j < M) ? Zs[(long)j * D + d] : 0.0; az[d] = 0.0; al[d] = 0.0; }
+    for (int d = 0; d < MAXD; ++d) { zj[d] = (d < D && j < M) ? Zs[(long)j * D + d] : 0.0; az[d] = 0; al[d] = 0; }
     __syncthreads();
     const double s = os[0];
-    double asum = 0.0;
+    AccT asum = 0;
     if (j < M) {
         for (long n = n0 + ry; n < n1; n += KG_TR) {
             const int r = (int)(n - n0);
             double kb = (double)Kbar[n * ldk + j];
             if (sym) kb = 0.5 * (kb + (double)Kbar[(long)j * ldk + n]);
-            double q = 0.0;
+            if constexpr (std::is_same<KBT, float>::value) {
+                float df[MAXD];
+                float q = 0.f;
 #pragma unroll
-            for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
-            const double t = kb * s * exp(-0.5 * q);
-            asum += t;
+                for (int d = 0; d < MAXD; ++d) if (d < D) { df[d] = (float)(xs[r][d] - zj[d]); q = fmaf(df[d], df[d], q); }
+                const float t = (float)kb * (float)s * expf(-0.5f * q);
+                asum += t;
 #pragma unroll
-            for (int d = 0; d < MAXD; ++d) if (d < D) {
-                const double df = xs[r][d] - zj[d];
-                az[d] = fma(t, df, az[d]);
-                al[d] = fma(t * df, df, al[d]);
+                for (int d = 0; d < MAXD; ++d) if (d < D) { az[d] = fmaf(t, df[d], az[d]); al[d] = fmaf(t * df[d], df[d], al[d]); }
+            } else {
+                double q = 0.0;
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
+                const double t = kb * s * exp(-0.5 * q);
+                asum += t;
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) if (d < D) {
+                    const double df = xs[r][d] - zj[d];
+                    az[d] = fma(t, df, az[d]);
+                    al[d] = fma(t * df, df, al[d]);
+                }
             }
         }
     }
@@ -83,7 +99,7 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
     for (int d = 0; d < D; ++d) {
         double vz = 0.0, vl = 0.0;
 #pragma unroll
-        for (int dd = 0; dd < MAXD; ++dd) if (dd == d) { vz = az[dd]; vl = al[dd]; }
+        for (int dd = 0; dd < MAXD; ++dd) if (dd == d) { vz = (double)az[dd]; vl = (double)al[dd]; }
         red[tid] = vz;
         __syncthreads();
         if (ry == 0 && j < M) {
@@ -103,8 +119,8 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
         }
         __syncthreads();
     }
-    asum = warp_sum(asum);
-    if ((tid & 31) == 0) red[tid >> 5] = asum;
+    double asum_d = warp_sum((double)asum);
+    if ((tid & 31) == 0) red[tid >> 5] = asum_d;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;

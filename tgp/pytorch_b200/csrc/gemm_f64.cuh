@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
-    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    // m-tiles vary fastest (CTAs that are co-resident share the B tile); n-tiles are visited heaviest-first when the
+    // triangular clipping makes their k-extent grow with n (b_tri == 1), so that the last wave holds the light tiles
+    const int nt = (g.b_tri == 1) ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
+    const int m0 = blockIdx.x * GBM, n0 = nt * GBN;
     if (g.c_lower && n0 > m0 + GBM - 1) return;
 
     const int zb = g.splitk > 1 ? 0 : blockIdx.z;
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
 inline int gemm_f64(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
     if (g.splitk > 1 && (g.batch != 1 || g.beta != 1.0)) return set_error(-3, "split-k GEMM needs batch == 1 and beta == 1");
-    dim3 grid((unsigned)cdiv(g.N, GBN), (unsigned)cdiv(g.M, GBM), (unsigned)(g.splitk > 1 ? g.splitk : g.batch));
+    dim3 grid((unsigned)cdiv(g.M, GBM), (unsigned)cdiv(g.N, GBN), (unsigned)(g.splitk > 1 ? g.splitk : g.batch));
+    if (grid.y > 65535) return set_error(-3, "too many column tiles");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_f64_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);

@@ -8,7 +8,7 @@
 namespace tgp {
 
 constexpr int POTRF_NB = 64;
-constexpr int POTRF_SMEM = (POTRF_NB * (POTRF_NB + 1) + POTRF_NB + 8) * (int)sizeof(double);
+constexpr int POTRF_SMEM = (2 * POTRF_NB * (POTRF_NB + 1) + 2 * POTRF_NB) * (int)sizeof(double);
 
 // ls = softplus(raw_ls), os = softplus(raw_os), Zs = Z / ls      (gpytorch: x.div(lengthscale))
 __global__ void k_transform_params(const double* __restrict__ Z, const double* __restrict__ raw_ls,
@@ -80,68 +80,62 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
 // L_kk^-1 -> Dinv (dense 64x64, upper zero) and -> the diagonal block of Linv.
 // status[0] = 1-based index of the first non-positive / NaN pivot (0 = ok); only the first failure is recorded.
 //
-// One CTA of 64 threads on the critical path of the factorisation, so it is written for latency: thread t keeps row t of
-// the block in registers (fully unrolled, static indices); column j is broadcast through shared memory with two
-// barriers per column; the inverse is a forward substitution with thread c owning column c (four partial sums to break
-// the dependent-FMA chain).
-__global__ void __launch_bounds__(POTRF_NB) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
-                                                         double* __restrict__ Linv, double* __restrict__ Dinv, int kb,
-                                                         long ld, int* __restrict__ status) {
+// One CTA on the critical path of the factorisation, written for latency with compact loops (a fully unrolled
+// register version is instruction-fetch bound): 256 threads = 64 rows x 4 column phases.  The trailing update works on
+// the UNSCALED columns, a[t][k] -= a[t][j] * a[k][j] / d_j, so a column never has to be rescaled in place between two
+// barriers (two barriers per column); the scaling by 1/sqrt(d_j) is applied once at the end.
+__global__ void __launch_bounds__(256) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
+                                                    double* __restrict__ Linv, double* __restrict__ Dinv, int kb,
+                                                    long ld, int* __restrict__ status) {
     constexpr int NB = POTRF_NB, LDS = NB + 1;
     extern __shared__ double sm_potrf[];
-    double* Ls = sm_potrf;                 // [NB][LDS]
-    double* col = sm_potrf + NB * LDS;     // [NB]
-    double* piv = col + NB;                // [1]
-    const int t = threadIdx.x;
+    double* a = sm_potrf;                  // [NB][LDS] working block, later L
+    double* inv = a + NB * LDS;            // [NB][LDS] L^-1
+    double* diag = inv + NB * LDS;         // [NB] sqrt(d_j)
+    double* rd = diag + NB;                // [NB] 1 / d_j
+    const int tid = threadIdx.x, t = tid & 63, q = tid >> 6;
     const long base = (long)kb * NB * ld + (long)kb * NB;
-    for (int r = 0; r < NB; ++r) Ls[r * LDS + t] = (t <= r) ? Aw[base + (long)r * ld + t] : 0.0;
+    for (int i = tid; i < NB * NB; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        a[r * LDS + c] = (c <= r) ? Aw[base + (long)r * ld + c] : 0.0;
+        inv[r * LDS + c] = 0.0;
+    }
     __syncthreads();
-    double a[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) a[c] = Ls[t * LDS + c];
-#pragma unroll
     for (int j = 0; j < NB; ++j) {
-        if (t == j) {
-            double d = a[j];
+        if (tid == 0) {
+            const double d = a[j * LDS + j];
             if (!(d > 0.0)) atomicCAS(status, 0, kb * NB + j + 1);
-            d = sqrt(d);
-            a[j] = d;
-            piv[0] = d;
+            diag[j] = sqrt(d);
+            rd[j] = 1.0 / d;
         }
-        __syncthreads();
-        if (t > j) a[j] = a[j] / piv[0];
-        col[t] = a[j];
         __syncthreads();
         if (t > j) {
-            const double lij = a[j];
-#pragma unroll
-            for (int k = j + 1; k < NB; ++k) if (k <= t) a[k] = fma(-lij, col[k], a[k]);
+            const double f = a[t * LDS + j] * rd[j];
+            for (int k = j + 1 + q; k <= t; k += 4) a[t * LDS + k] = fma(-f, a[k * LDS + j], a[t * LDS + k]);
         }
+        __syncthreads();
+    }
+    // scale: L[t][c] = a[t][c] / sqrt(d_c) below the diagonal, sqrt(d_t) on it
+    for (int i = tid; i < NB * NB; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        a[r * LDS + c] = c < r ? a[r * LDS + c] / diag[c] : (c == r ? diag[r] : 0.0);
     }
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < NB; ++c) Ls[t * LDS + c] = a[c];
-    __syncthreads();
-    for (int r = 0; r < NB; ++r) Lout[base + (long)r * ld + t] = Ls[r * LDS + t];
-    // inverse: thread t owns column t of X = L^-1 (x[i] = 0 for i < t falls out of the recurrence)
-    double x[NB];
-#pragma unroll
+    // inverse by forward substitution, row by row; thread (c, p) sums k == c + p (mod 4) for column c
+    const int c = tid >> 2, p = tid & 3;
     for (int i = 0; i < NB; ++i) {
-        double s0 = (i == t) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) {
-            const double l = Ls[i * LDS + k];
-            if ((k & 3) == 0) s0 = fma(-l, x[k], s0);
-            else if ((k & 3) == 1) s1 = fma(-l, x[k], s1);
-            else if ((k & 3) == 2) s2 = fma(-l, x[k], s2);
-            else s3 = fma(-l, x[k], s3);
-        }
-        x[i] = (i < t) ? 0.0 : ((s0 + s1) + (s2 + s3)) / Ls[i * LDS + i];
+        double s = 0.0;
+        if (c <= i) for (int k = c + p; k < i; k += 4) s = fma(a[i * LDS + k], inv[k * LDS + c], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (p == 0 && c <= i) inv[i * LDS + c] = ((i == c ? 1.0 : 0.0) - s) / a[i * LDS + i];
+        __syncthreads();
     }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        Linv[base + (long)i * ld + t] = x[i];
-        Dinv[i * NB + t] = x[i];
+    for (int i = tid; i < NB * NB; i += 256) {
+        const int r = i >> 6, cc = i & 63;
+        Lout[base + (long)r * ld + cc] = a[r * LDS + cc];
+        Linv[base + (long)r * ld + cc] = inv[r * LDS + cc];
+        Dinv[i] = inv[r * LDS + cc];
     }
 }
 
@@ -241,7 +235,7 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
 
     // right-looking blocked Cholesky; the panel solve is a GEMM with the inverted diagonal block
     for (int kb = 0; kb < nb; ++kb) {
-        k_potrf_diag<<<1, POTRF_NB, POTRF_SMEM, st>>>(v.Kzz, v.L, v.Linv, v.Dinv, kb, Mp, status);
+        k_potrf_diag<<<1, 256, POTRF_SMEM, st>>>(v.Kzz, v.L, v.Linv, v.Dinv, kb, Mp, status);
         TGP_TRY(check_launch("k_potrf_diag"));
         const int rem = Mp - (kb + 1) * NB;
         if (rem <= 0) break;

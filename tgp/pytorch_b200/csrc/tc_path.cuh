@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(RP_THREADS) k_rbf_planes(const double* __restr
         if (n < R && j < M) {
             double acc = 0.0;
             for (int d = 0; d < D; ++d) { const double df = xs[r * DP + d] - zs[c * DP + d]; acc = fma(df, df, acc); }
-            val = (float)(s * exp(-0.5 * acc));
+            // argument in FP64 (exact to ~1e-16), exponential in FP32: exp(a) = expf(a_hi) * (1 + a_lo)
+            const double arg = -0.5 * acc;
+            const float ahi = (float)arg;
+            val = (float)s * expf(ahi) * (1.0f + (float)(arg - (double)ahi));
         }
         tile[r * (RP_TC + 1) + c] = val;
         if (Khi && n < R && j < M) { put_planes(Khi, Klo, (long)n * ldk + j, val); }

@@ -70,13 +70,18 @@ inline void fill_flow(FlowDesc& fd, const TgpModel* md) {
 }
 
 // The weight-gradient GEMMs have only (M/128)^2 output tiles but a reduction over thousands of rows: split the
-// reduction so that about two waves of CTAs are in flight on the 148 SMs.
-inline int weight_splitk(int M, int rc) {
-    const long tiles = cdiv(M, GBM) * cdiv(M, GBN);
-    long want = cdiv(2 * 148, tiles);
-    const long max_split = rc / (4 * GBK) > 0 ? rc / (4 * GBK) : 1;
-    if (want > max_split) want = max_split;
-    return (int)(want < 1 ? 1 : want);
+// reduction so that the live CTAs fill whole waves of the 148 SMs (36 lower tiles x 4 splits = 144 CTAs at M = 1024).
+inline int weight_splitk(int M, int rc, bool lower) {
+    const long T = cdiv(M, GBM);
+    const long tiles = lower ? T * (T + 1) / 2 : T * T;
+    const long max_split = rc / (8 * GBK) > 0 ? rc / (8 * GBK) : 1;
+    auto util = [&](long s) { const long c = tiles * s; return (double)c / (double)(cdiv(c, 148) * 148); };
+    double best_util = 0.0;
+    for (long s = 1; s <= max_split && s <= 64; ++s) best_util = util(s) > best_util ? util(s) : best_util;
+    int best = 1;
+    for (long s = 1; s <= max_split && s <= 64; ++s)           // smallest split that fills the waves (fewest atomics)
+        if (util(s) >= best_util - 0.03) { best = (int)s; break; }
+    return best;
 }
 
 inline int row_grid(long R) {
@@ -220,11 +225,11 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
                                     reduce_buf + l.dls, reduce_buf + l.dos, st));
         // Gbar += tril(Abar^T K)      (reduction over the rows of the chunk)
         GemmArgs g3 = make_gemm(M, M, rc, b.Abar, M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
-        g3.c_lower = 1; g3.splitk = weight_splitk(M, rc); g3.tag = 1;
+        g3.c_lower = 1; g3.splitk = weight_splitk(M, rc, true); g3.tag = 1;
         TGP_TRY(gemm_f64(g3, st));
         // dL_S += tril(A^T Bbar)
         GemmArgs g4 = make_gemm(M, M, rc, ABc, 2 * M, 1, ABc + M, 2 * M, 1, Cbar, s.Mp, 1.0, 1.0);
-        g4.c_lower = 1; g4.splitk = weight_splitk(M, rc); g4.tag = 1;
+        g4.c_lower = 1; g4.splitk = weight_splitk(M, rc, true); g4.tag = 1;
         TGP_TRY(gemm_f64(g4, st));
     }
     return 0;
