@@ -84,18 +84,24 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
 // register version is instruction-fetch bound): 256 threads = 64 rows x 4 column phases.  The trailing update works on
 // the UNSCALED columns, a[t][k] -= a[t][j] * a[k][j] / d_j, so a column never has to be rescaled in place between two
 // barriers (two barriers per column); the scaling by 1/sqrt(d_j) is applied once at the end.
-__global__ void __launch_bounds__(256) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
-                                                    double* __restrict__ Linv, double* __restrict__ Dinv, int kb,
-                                                    long ld, int* __restrict__ status) {
-    constexpr int NB = POTRF_NB, LDS = NB + 1;
+constexpr int POTRF_THREADS = 1024;        // 64 rows x 16 column phases
+__global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
+                                                              double* __restrict__ Linv, double* __restrict__ Dinv,
+                                                              int kb, long ld, const double* __restrict__ os,
+                                                              int* __restrict__ status) {
+    constexpr int NB = POTRF_NB, LDS = NB + 1, NT = POTRF_THREADS, PH = NT / NB;
+    // a pivot that is not positive *to working precision* (relative to the kernel's diagonal k(z,z) = outputscale) counts
+    // as a failed factorisation: exactly singular inputs (duplicated inducing rows) then take the jitter ladder
+    // deterministically instead of depending on the sign of a 1e-16 rounding residue
+    const double pivot_floor = 8.0 * 2.220446049250313e-16 * os[0];
     extern __shared__ double sm_potrf[];
     double* a = sm_potrf;                  // [NB][LDS] working block, later L
     double* inv = a + NB * LDS;            // [NB][LDS] L^-1
-    double* diag = inv + NB * LDS;         // [NB] sqrt(d_j)
-    double* rd = diag + NB;                // [NB] 1 / d_j
+    double* rs = inv + NB * LDS;           // [NB] 1 / sqrt(d_j)
+    double* rd = rs + NB;                  // [NB] 1 / d_j
     const int tid = threadIdx.x, t = tid & 63, q = tid >> 6;
     const long base = (long)kb * NB * ld + (long)kb * NB;
-    for (int i = tid; i < NB * NB; i += 256) {
+    for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, c = i & 63;
         a[r * LDS + c] = (c <= r) ? Aw[base + (long)r * ld + c] : 0.0;
         inv[r * LDS + c] = 0.0;
@@ -104,34 +110,39 @@ __global__ void __launch_bounds__(256) k_potrf_diag(const double* __restrict__ A
     for (int j = 0; j < NB; ++j) {
         if (tid == 0) {
             const double d = a[j * LDS + j];
-            if (!(d > 0.0)) atomicCAS(status, 0, kb * NB + j + 1);
-            diag[j] = sqrt(d);
-            rd[j] = 1.0 / d;
+            if (!(d > pivot_floor)) atomicCAS(status, 0, kb * NB + j + 1);
+            const double r = rsqrt(d);
+            rs[j] = r;
+            rd[j] = r * r;
         }
         __syncthreads();
         if (t > j) {
             const double f = a[t * LDS + j] * rd[j];
-            for (int k = j + 1 + q; k <= t; k += 4) a[t * LDS + k] = fma(-f, a[k * LDS + j], a[t * LDS + k]);
+#pragma unroll 4
+            for (int k = j + 1 + q; k <= t; k += PH) a[t * LDS + k] = fma(-f, a[k * LDS + j], a[t * LDS + k]);
         }
         __syncthreads();
     }
-    // scale: L[t][c] = a[t][c] / sqrt(d_c) below the diagonal, sqrt(d_t) on it
-    for (int i = tid; i < NB * NB; i += 256) {
+    // scale: L[t][c] = a[t][c] / sqrt(d_c) below the diagonal, d_t / sqrt(d_t) on it
+    for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, c = i & 63;
-        a[r * LDS + c] = c < r ? a[r * LDS + c] / diag[c] : (c == r ? diag[r] : 0.0);
+        a[r * LDS + c] = c <= r ? a[r * LDS + c] * rs[c] : 0.0;
     }
     __syncthreads();
-    // inverse by forward substitution, row by row; thread (c, p) sums k == c + p (mod 4) for column c
-    const int c = tid >> 2, p = tid & 3;
+    // inverse by forward substitution, row by row; thread (c, p) sums k == c + p (mod 16) for column c;
+    // 1 / L_ii = rs[i] is already known
+    const int c = tid >> 4, p = tid & 15;
     for (int i = 0; i < NB; ++i) {
         double s = 0.0;
-        if (c <= i) for (int k = c + p; k < i; k += 4) s = fma(a[i * LDS + k], inv[k * LDS + c], s);
+        if (c <= i) for (int k = c + p; k < i; k += 16) s = fma(a[i * LDS + k], inv[k * LDS + c], s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (p == 0 && c <= i) inv[i * LDS + c] = ((i == c ? 1.0 : 0.0) - s) / a[i * LDS + i];
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        if (p == 0 && c <= i) inv[i * LDS + c] = ((i == c ? 1.0 : 0.0) - s) * rs[i];
         __syncthreads();
     }
-    for (int i = tid; i < NB * NB; i += 256) {
+    for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, cc = i & 63;
         Lout[base + (long)r * ld + cc] = a[r * LDS + cc];
         Linv[base + (long)r * ld + cc] = inv[r * LDS + cc];
@@ -235,7 +246,7 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
 
     // right-looking blocked Cholesky; the panel solve is a GEMM with the inverted diagonal block
     for (int kb = 0; kb < nb; ++kb) {
-        k_potrf_diag<<<1, 256, POTRF_SMEM, st>>>(v.Kzz, v.L, v.Linv, v.Dinv, kb, Mp, status);
+        k_potrf_diag<<<1, POTRF_THREADS, POTRF_SMEM, st>>>(v.Kzz, v.L, v.Linv, v.Dinv, kb, Mp, v.os, status);
         TGP_TRY(check_launch("k_potrf_diag"));
         const int rem = Mp - (kb + 1) * NB;
         if (rem <= 0) break;

@@ -84,6 +84,24 @@ inline int weight_splitk(int M, int rc, bool lower) {
     return best;
 }
 
+// M x M x M products of the per-step chain have only (M/128)^2 output tiles: split their reduction (FP64 atomics into a
+// zeroed output) so that one launch fills the SMs instead of running 36-64 long CTAs.
+inline int gemm_small(GemmArgs g, cudaStream_t st) {
+    const long Tm = cdiv(g.M, GBM), Tn = cdiv(g.N, GBN);
+    const long tiles = g.c_lower ? Tm * (Tm + 1) / 2 : Tm * Tn;
+    long split = tiles > 0 ? (148 + tiles - 1) / tiles : 1;
+    const long max_split = g.K / (4 * GBK) > 0 ? g.K / (4 * GBK) : 1;
+    if (split > max_split) split = max_split;
+    if (split > 1 && g.batch == 1) {
+        if (g.beta == 0.0) {
+            cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(double), 0, (size_t)g.N * sizeof(double), (size_t)g.M, st);
+            g.beta = 1.0;
+        }
+        if (g.beta == 1.0) g.splitk = (int)split;
+    }
+    return gemm_f64(g, st);
+}
+
 inline int row_grid(long R) {
     const long blocks = cdiv(R, ROW_THREADS / 32);
     return (int)(blocks < 148 * 16 ? blocks : 148 * 16);
@@ -256,11 +274,11 @@ int tgp_chain_backward(const TgpModel* md, const TgpParams* p, void* step_ws, co
         GemmArgs a1 = make_gemm(M, M, M, s.Linv, Mp, 0, Cbar, Mp, 0, s.S0, Mp);
         a1.a_tri = 1; a1.c_lower = 1;
         cudaMemsetAsync(s.S0, 0, mm * sizeof(double), st);
-        TGP_TRY(gemm_f64(a1, st));
+        TGP_TRY(gemm_small(a1, st));
         cudaMemcpyAsync(Gtot, reduce_buf + l.Gbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
         GemmArgs a2 = make_gemm(M, M, M, s.LS, Mp, 0, Cbar, Mp, 1, Gtot, Mp, 1.0, 1.0);
         a2.a_tri = 1; a2.c_lower = 1;
-        TGP_TRY(gemm_f64(a2, st));
+        TGP_TRY(gemm_small(a2, st));
     } else {
         // FP64 mode: the batch pass already accumulated dL_S (in the Cbar slot) and the complete Gbar
         cudaMemcpyAsync(s.S0, Cbar, mm * sizeof(double), cudaMemcpyDeviceToDevice, st);
@@ -269,25 +287,25 @@ int tgp_chain_backward(const TgpModel* md, const TgpParams* p, void* step_ws, co
     // T1 = Gtot * Linv^T
     GemmArgs a3 = make_gemm(M, M, M, Gtot, Mp, 0, s.Linv, Mp, 0, s.S1, Mp);
     a3.a_tri = 1; a3.b_tri = 1;
-    TGP_TRY(gemm_f64(a3, st));
+    TGP_TRY(gemm_small(a3, st));
     // Lbar = -tril(Linv^T * T1)
     cudaMemsetAsync(s.S2, 0, mm * sizeof(double), st);
     GemmArgs a4 = make_gemm(M, M, M, s.Linv, Mp, 1, s.S1, Mp, 1, s.S2, Mp, -1.0, 0.0);
     a4.a_tri = 2; a4.c_lower = 1;
-    TGP_TRY(gemm_f64(a4, st));
+    TGP_TRY(gemm_small(a4, st));
     // Phi = tril(L^T * Lbar), diagonal halved      (Murray 2016; equals torch's cholesky_backward)
     cudaMemsetAsync(s.S3, 0, mm * sizeof(double), st);
     GemmArgs a5 = make_gemm(M, M, M, s.L, Mp, 1, s.S2, Mp, 1, s.S3, Mp);
     a5.a_tri = 2; a5.b_tri = 2; a5.c_lower = 1;
-    TGP_TRY(gemm_f64(a5, st));
+    TGP_TRY(gemm_small(a5, st));
     k_halve_diag<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(s.S3, Mp, M);
     // S1 = Phi * Linv ;  Kbar_zz = Linv^T * S1  (symmetrised on the fly by the gradient kernel)
     GemmArgs a6 = make_gemm(M, M, M, s.S3, Mp, 0, s.Linv, Mp, 1, s.S1, Mp);
     a6.a_tri = 1; a6.b_tri = 2;
-    TGP_TRY(gemm_f64(a6, st));
+    TGP_TRY(gemm_small(a6, st));
     GemmArgs a7 = make_gemm(M, M, M, s.Linv, Mp, 1, s.S1, Mp, 1, s.S2, Mp);
     a7.a_tri = 2;
-    TGP_TRY(gemm_f64(a7, st));
+    TGP_TRY(gemm_small(a7, st));
     // K_zz -> Z (both index roles: factor 2 on the symmetrised matrix), lengthscale, outputscale.
     // accumulators: start from the K_xz-side sums of the reduce buffer
     dZacc = s.S3;   // Phi is dead now
