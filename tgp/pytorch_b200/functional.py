@@ -30,16 +30,8 @@ def _world():
     return None
 
 
-def prepare_with_jitter_ladder(engine, base_jitter=None, check=True):
-    """Reference semantics of psd_safe_cholesky (code/dsp/utils.py:222-270): factorise without jitter; only on
-    failure add 1e-8 * 10^i (FP64), i = 0..2, warning each time; raise after the third failure.
-    `check=False` skips the 4-byte status read-back (no host sync; a failed factorisation then surfaces as NaNs)."""
-    kl, status = engine.prepare(0.0)
-    if not check:
-        return kl, 0.0
-    fail = int(status.item())
-    if fail == 0:
-        return kl, 0.0
+def _jitter_ladder(engine, fail, base_jitter=None):
+    """The failure branch of psd_safe_cholesky (code/dsp/utils.py:241-270): NaN check, then jitter 1e-8 * 10^i."""
     Z = engine._keep[0]
     if torch.isnan(Z).any() or torch.isnan(engine._keep[1]).any() or torch.isnan(engine._keep[2]).any():
         raise NanError('cholesky: the kernel matrix has NaN entries')
@@ -51,6 +43,24 @@ def prepare_with_jitter_ladder(engine, base_jitter=None, check=True):
             warnings.warn('A not p.d., added jitter of %g to the diagonal' % j, NumericalWarning)
             return kl, j
     raise RuntimeError('cholesky: matrix not positive definite after 3 jitter escalations (first bad pivot %d)' % fail)
+
+
+def prepare_then(engine, work, check=True, base_jitter=None):
+    """Reference semantics of psd_safe_cholesky (code/dsp/utils.py:222-270): factorise without jitter; only on failure
+    add 1e-8 * 10^i (FP64), i = 0..2, warning each time; raise after the third failure.
+
+    `work()` enqueues everything that consumes the factorisation.  The 4-byte pivot status is read back only AFTER that
+    work has been enqueued, so the (almost always successful) check costs no pipeline bubble; on failure the ladder
+    runs and `work()` is enqueued again on the jittered factor.  `check=False` skips the read-back altogether."""
+    kl, status = engine.prepare(0.0)
+    out = work()
+    if not check:
+        return kl, out
+    fail = int(status.item())
+    if fail == 0:
+        return kl, out
+    kl, _ = _jitter_ladder(engine, fail, base_jitter)
+    return kl, work()
 
 
 def _check_generation(ctx):
@@ -66,11 +76,14 @@ class _ElboTerms(torch.autograd.Function):
         engine.set_params(Z.detach(), raw_ls.detach(), raw_os.detach(), m.detach(), L_raw.detach(),
                           None if log_var_noise is None else log_var_noise.detach(),
                           None if theta is None else theta.detach())
-        kl, jitter = prepare_with_jitter_ladder(engine, check=check_status)
-        mu, v = engine.qf_forward(X)
-        rb = engine.new_reduce_buffer()
         rp = None if rowparams is None else rowparams.detach().contiguous()
-        ell_rows, g_mu, g_v, drow = engine.ell_forward(mu, v, Y, rp, scale, rb, want_grad=need_grad)
+
+        def work():
+            mu, v = engine.qf_forward(X)
+            rb = engine.new_reduce_buffer()
+            return (mu, v, rb) + tuple(engine.ell_forward(mu, v, Y, rp, scale, rb, want_grad=need_grad))
+
+        kl, (mu, v, rb, ell_rows, g_mu, g_v, drow) = prepare_then(engine, work, check=check_status)
         ell = rb[engine.layout.ell_sum:engine.layout.ell_sum + 1].clone()
         dist = _world()
         if dist is not None:
@@ -114,8 +127,7 @@ class _QfMarginals(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, X, check_status, Z, raw_ls, raw_os, m, L_raw):
         engine.set_params(Z.detach(), raw_ls.detach(), raw_os.detach(), m.detach(), L_raw.detach(), None, None)
-        prepare_with_jitter_ladder(engine, check=check_status)
-        mu, v = engine.qf_forward(X)
+        _, (mu, v) = prepare_then(engine, lambda: engine.qf_forward(X), check=check_status)
         ctx.engine, ctx.X = engine, X
         ctx.generation = engine.generation
         return mu, v
