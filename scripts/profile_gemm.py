@@ -1,18 +1,21 @@
-"""Launches the batch-contraction GEMM shapes of one 8192-row chunk of the cfg4 step (for ncu captures)."""
+"""Launches the FP64 batch-contraction GEMM shapes of one 8192-row chunk of the cfg4 step (for ncu captures):
+forward A = K Linv^T (lower-triangular B operand), forward B = A L_S, backward-weight Gbar += Abar^T K (split-K)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tgp.pytorch_b200.engine import debug_gemm
 dev = 'cuda:0'
 R, M = 8192, 1024
-K = torch.randn(R, M, dtype=torch.float64, device=dev)
-W = torch.randn(M, M, dtype=torch.float64, device=dev)
-AB = torch.randn(R, 2 * M, dtype=torch.float64, device=dev)
-out = torch.zeros(R, M, dtype=torch.float64, device=dev)
-G = torch.zeros(M, M, dtype=torch.float64, device=dev)
+f64 = torch.float64
+K = torch.rand(R, M, dtype=f64, device=dev)
+Linv = torch.randn(M, M, dtype=f64, device=dev).tril()
+LS = torch.randn(M, M, dtype=f64, device=dev).tril()
+AB = torch.zeros(R, 2 * M, dtype=f64, device=dev)
+Abar = torch.randn(R, M, dtype=f64, device=dev)
+G = torch.zeros(M, M, dtype=f64, device=dev)
 for it in range(3):
-    debug_gemm(K, W, out, R, M, M, M, M, M, 0, 0)                       # forward B-part: dense NT
-    debug_gemm(AB, W, out, R, M, M, 2 * M, M, M, 0, 1)                  # backward data: NN
-    debug_gemm(AB, K, G, M, M, R, 2 * M, M, M, 1, 1, beta=1.0)          # backward weight: TN, reduction over rows
+    debug_gemm(K, Linv, AB, R, M, M, M, M, 2 * M, 0, 0, b_tri=1)                       # A = K Linv^T
+    debug_gemm(AB, LS, AB[:, M:], R, M, M, 2 * M, M, 2 * M, 0, 1, b_tri=2)               # B = A L_S
+    debug_gemm(Abar, K, G, M, M, R, M, M, M, 1, 1, beta=1.0, c_lower=1)                  # Gbar += tril(Abar^T K) (no split here)
 torch.cuda.synchronize()
 print('ok')
