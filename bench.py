@@ -170,7 +170,7 @@ def run_reference(args):
                                        'torch CPU with %d threads' % (CPU_SAMPLE_ROWS, M, D, N_QUAD, cores)},
             'e2e': {'value': rows_s, 'unit': 'rows/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -368,7 +368,7 @@ def run_ours(args):
                            'batch_gemm_algorithmic_tflops': 6.0 * M * M * BATCH / max((other['gemm_ms'][1] + other['gemm_ms'][2]) / args.steps * 1e-3, 1e-12) / 1e12,
                            'note': 'tf32x3 = batch contractions on tcgen05 (3xTF32 split, FP32 TMEM accumulation); per-step '
                                    'factorisation, backward chain and the row epilogue stay FP64 in both modes'}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -430,7 +430,20 @@ def run_e2e(args, p, X, Y, perm, rank, world, dev, scale):
             'note': 'sparse_MF_SP.ELBO + backward per step; includes the host-side minibatch gather into pinned memory'}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1 (e.g. NCCL's version
+    banner) was diverted to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)

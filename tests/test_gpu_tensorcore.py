@@ -95,3 +95,22 @@ def test_tensorcore_mode_elbo_against_fp64_path(name):
     print(name, 'ref-fp32 self:', {k: '%.1e' % self_err[k] for k in ours})
     bad = {k: (e, self_err[k]) for k, e in ours.items() if not e < 1e-5 + 4.0 * self_err[k]}
     assert not bad, bad
+
+
+@pytest.mark.parametrize('name', ['boston_tgp_steptanh13_p1', 'boston_svgp_p1'])
+def test_float32_model_runs_on_the_tensorcore_mode(name):
+    """A float32 model (the reference's import-time default dtype, config.py:53-58) is served by up-casting into the
+    tensor-core mode; results come back as float32 and sit within FP32-level error of the FP64 reference fixture."""
+    from tests.model_util import build_from_golden
+    g = Golden(name)
+    model = build_from_golden(g, DEV).float()
+    X, Y = g.t('X', torch.float32).to(DEV), g.t('Y', torch.float32).to(DEV)
+    ELBO, ELL, KLD = model.ELBO(X, Y)
+    assert ELBO.dtype == torch.float32
+    (-ELBO).backward()
+    assert rel_err(ELBO.detach().double().cpu(), g.t('ELBO')) < 2e-5
+    for n, prm in model.named_parameters():
+        assert prm.grad is not None and prm.grad.dtype == torch.float32, n
+        ref = -g.t('grad:' + n)
+        if float(ref.norm()) > 0:
+            assert rel_err(prm.grad.detach().double().cpu().reshape(ref.shape), ref) < 2e-4, n

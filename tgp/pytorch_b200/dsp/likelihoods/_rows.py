@@ -15,8 +15,8 @@ def flow_pack(flow, X, n_mc=1):
     """flow module -> (FlowLayout, theta tensor or None, rowparams (R, n_rowparams) or None)."""
     layers, glob, rows = flow.describe(X, n_mc) if flow is not None else ([], [], [])
     layout = FlowLayout(layers)
-    theta = torch.stack([g.reshape(()) for g in glob]) if glob else None
-    rowp = torch.stack(rows, dim=-1) if rows else None
+    theta = torch.stack([g.reshape(()) for g in glob]).to(torch.float64) if glob else None
+    rowp = torch.stack(rows, dim=-1).to(torch.float64) if rows else None
     return layout, theta, rowp
 
 
@@ -38,11 +38,13 @@ class _EllRows(torch.autograd.Function):
                        None if log_var_noise is None else log_var_noise.detach().reshape(1).contiguous(),
                        None if theta is None else theta.detach().contiguous())
         rb = eng.new_reduce_buffer()
-        rows, g_mu, g_v, drow = eng.ell_forward(mu.detach().contiguous(), v.detach().contiguous(), y.contiguous(),
+        rows, g_mu, g_v, drow = eng.ell_forward(mu.detach().double().contiguous(), v.detach().double().contiguous(),
+                                                y.double().contiguous(),
                                                 None if rowp is None else rowp.detach().contiguous(), 1.0, rb)
         ctx.save_for_backward(g_mu, g_v, drow if drow is not None else z)
         ctx.rb, ctx.layout, ctx.has = rb, eng.layout, (log_var_noise is not None, theta is not None, rowp is not None)
         ctx.n_theta, ctx.lv_shape = eng.flow.n_theta, None if log_var_noise is None else log_var_noise.shape
+        ctx.io_dtype = mu.dtype
         ctx.mark_non_differentiable(rows)
         return rb[eng.layout.ell_sum].clone(), rows
 
@@ -53,14 +55,16 @@ class _EllRows(torch.autograd.Function):
         has_noise, has_theta, has_rowp = ctx.has
         d_lv = (rb[lay.dlogvar] * g_sum).reshape(ctx.lv_shape) if has_noise else None
         d_th = rb[lay.dtheta:lay.dtheta + ctx.n_theta] * g_sum if has_theta else None
-        return (None, None, g_mu * g_sum, g_v * g_sum, d_lv, d_th, drow * g_sum if has_rowp else None)
+        return (None, None, (g_mu * g_sum).to(ctx.io_dtype), (g_v * g_sum).to(ctx.io_dtype), d_lv, d_th,
+                drow * g_sum if has_rowp else None)
 
 
 def expected_log_prob_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X):
     """Sum over the rows of E_q(f)[log p(y | G(f))] for ONE output GP, and the per-row terms."""
     layout, theta, rowp = flow_pack(flow, X) if likelihood != 'gauss_linear' else (FlowLayout([]), None, None)
     eng = row_engine(likelihood, n_quad, layout, mu.device)
-    return _EllRows.apply(eng, y, mu, v, log_var_noise, theta, rowp)
+    lv = None if log_var_noise is None else log_var_noise.to(torch.float64)
+    return _EllRows.apply(eng, y, mu, v, lv, theta, rowp)
 
 
 def test_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X, y_std=1.0, n_mc=1, bern_std=None):
@@ -79,4 +83,5 @@ def test_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X, y_std=1.0, n
             rowp = rowp.reshape(n_mc, R, -1).permute(1, 0, 2).contiguous()
         if y is None:
             y = torch.zeros(R, dtype=torch.float64, device=dev)
-        return eng.test_rows(mu.contiguous(), v.contiguous(), y.contiguous(), rowp, n_mc, y_std, bern_std)
+        return eng.test_rows(mu.double().contiguous(), v.double().contiguous(), y.double().contiguous(), rowp, n_mc, y_std,
+                             None if bern_std is None else bern_std.double())

@@ -119,8 +119,8 @@ class sparse_MF_SP(nn.Module):
     def _check_fused_scope(self, X):
         if not self.is_whiten:
             raise NotImplementedError('the fused path implements the whitened representation (every shipped configuration)')
-        if cg.dtype != torch.float64 or X.dtype != torch.float64:
-            raise NotImplementedError('this build implements the FP64 path (cg.set_maximum_precission(), as main.py does)')
+        if X.dtype not in (torch.float64, torch.float32):
+            raise NotImplementedError('inputs must be float64 (cg.set_maximum_precission(), as main.py does) or float32')
         if not X.is_cuda:
             raise RuntimeError('tgp.pytorch_b200 has no CPU path: move the model and the data to a CUDA device')
 
@@ -137,23 +137,29 @@ class sparse_MF_SP(nn.Module):
             raw_os = torch.full((1,), _INV_SOFTPLUS_ONE, dtype=torch.float64, device=raw_ls.device)
         if raw_ls.numel() != self.inp_dim:
             raw_ls = raw_ls.expand(self.inp_dim)
-        return (self.Z[zi].contiguous(), raw_ls.contiguous(), raw_os.contiguous(),
-                self.q_U.variational_mean[qi].contiguous(), self.q_U.chol_variational_covar[qi].contiguous())
+        # float32 models (the reference's import-time default, config.py:53-58) are served by the tensor-core mode:
+        # parameters are up-cast here (autograd casts the gradients back), the contractions run as 3xTF32
+        d = torch.float64
+        return (self.Z[zi].to(d).contiguous(), raw_ls.to(d).contiguous(), raw_os.to(d).contiguous(),
+                self.q_U.variational_mean[qi].to(d).contiguous(), self.q_U.chol_variational_covar[qi].to(d).contiguous())
 
     def _noise(self, dy):
         lik = self.likelihood
         if isinstance(lik, Bernoulli):
             return None
         lv = lik.log_var_noise
-        return lv[0 if lik.noise_is_shared else dy].reshape(1)
+        return lv[0 if lik.noise_is_shared else dy].reshape(1).to(torch.float64)
 
     def _engine(self, dy, layout, device):
         kind = _LIK_KIND[type(self.likelihood)]
-        key = (dy, kind, self.quad_points, tuple(tuple(sorted(l.items())) for l in layout.layers), str(device), cg.compute)
+        key = (dy, kind, self.quad_points, tuple(tuple(sorted(l.items())) for l in layout.layers), str(device), self._compute())
         if key not in self._engines:
             self._engines[key] = Engine(self.M, self.inp_dim, kind, self.quad_points if kind != 'gauss_linear' else 0,
-                                        layout, device, compute=cg.compute)
+                                        layout, device, compute=self._compute())
         return self._engines[key]
+
+    def _compute(self):
+        return cg.compute if self.Z.dtype == torch.float64 else 'tf32x3'
 
     def _rows3(self, X):
         if len(X.shape) == 2:
@@ -178,15 +184,16 @@ class sparse_MF_SP(nn.Module):
         mus, vs = [], []
         for dy in range(self.out_dim):
             Z, raw_ls, raw_os, m, L_raw = self._gp_params(dy)
-            key = ('qf', dy, str(X.device), cg.compute)
+            key = ('qf', dy, str(X.device), self._compute())
             if key not in self._engines:     # marginals do not involve the flow / likelihood
                 self._engines[key] = Engine(self.M, self.inp_dim, 'gauss_linear', 0, FlowLayout([]), X.device,
-                                            compute=cg.compute)
+                                            compute=self._compute())
             eng = self._engines[key]
-            mu, v = Fn.qf_marginals(eng, X[dy].contiguous(), Z, raw_ls, raw_os, m, L_raw, cg.check_cholesky_status)
+            mu, v = Fn.qf_marginals(eng, X[dy].to(torch.float64).contiguous(), Z, raw_ls, raw_os, m, L_raw,
+                                    cg.check_cholesky_status)
             mus.append(mu)
             vs.append(v)
-        return torch.stack(mus).unsqueeze(2), torch.stack(vs).unsqueeze(2)
+        return torch.stack(mus).unsqueeze(2).to(self.Z.dtype), torch.stack(vs).unsqueeze(2).to(self.Z.dtype)
 
     def KLD(self):
         """KL[q(u) || p(u)] per output, whitened: 0.5 (-log|S| + m'm + tr S - M).  Stand-alone helper (a few
@@ -210,7 +217,7 @@ class sparse_MF_SP(nn.Module):
         kind = _LIK_KIND[type(self.likelihood)]
         ELL, KLD = 0.0, 0.0
         for dy in range(self.out_dim):
-            Xd = X[dy].contiguous()
+            Xd = X[dy].to(torch.float64).contiguous()
             Z, raw_ls, raw_os, m, L_raw = self._gp_params(dy)
             if kind == 'gauss_linear':
                 layout, theta, rowp = FlowLayout([]), None, None
@@ -226,7 +233,8 @@ class sparse_MF_SP(nn.Module):
         for flow in self.G_matrix:
             KLD_flow = KLD_flow + flow.KLD()
         ELBO = ELL - KLD - KLD_flow
-        return ELBO, ELL, KLD + KLD_flow
+        out = self.Z.dtype
+        return ELBO.to(out), ELL.to(out), (KLD + KLD_flow).to(out)
 
     def ELL(self, X, Y, mean, cov):
         """(N/MB) * E_q(f)[log p(y|G(f))] per output from given marginals (Dy,MB,1)."""
