@@ -124,3 +124,21 @@ def test_second_forward_before_backward_is_refused():
     model.ELBO(X, Y)
     with pytest.raises(RuntimeError, match='evaluated again'):
         E1.backward()
+
+
+def test_predictive_sampling_statistics():
+    """sample_from_predictive_distribution (trainers_regression.py:331: S samples per row for coverage): the sample mean /
+    variance per row must agree with the quadrature moments of test_log_likelihood within Monte-Carlo error."""
+    g = Golden('boston_tgp_sal2_p1')
+    model = build_from_golden(g, DEV)
+    model.set_is_training(False)
+    Xt, Yt = g.t('Xte').to(DEV), g.t('Yte').to(DEV)
+    torch.manual_seed(0)
+    S = 4000
+    samples, f_k, f_0 = model.sample_from_predictive_distribution(Xt, S)
+    assert samples.shape == (1, S, Xt.shape[0], 1) and f_k.shape == (1, S * Xt.shape[0])
+    _, mom = model.test_log_likelihood(Xt, Yt, return_moments=True, Y_std=torch.ones(1, device=DEV))
+    m1, m2 = mom[0].view(-1), mom[1].view(-1)
+    sm, sv = samples[0, :, :, 0].mean(0), samples[0, :, :, 0].var(0)
+    assert float(((sm - m1).abs() / m2.sqrt()).max()) < 6.0 / S ** 0.5 * 1.5
+    assert float((sv / m2 - 1).abs().max()) < 0.25

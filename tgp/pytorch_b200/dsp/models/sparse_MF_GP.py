@@ -12,9 +12,5 @@ class sparse_MF_GP(sparse_MF_SP):
                          init_params=init_params)
 
     def sample_from_variational_marginal(self, X, S, diagonal, is_duvenaud, init_Z=None):
-        if len(X.shape) == 2:
-            X = X.repeat(self.out_dim, 1, 1)
-        assert len(X.shape) == 3, 'Invalid input X.shape'
-        f, mean_q_f, cov_q_f = self.sample_from_variational_marginal_base(X=X.repeat(1, S, 1), diagonal=diagonal,
-                                                                         is_duvenaud=is_duvenaud, init_Z=init_Z)
+        f, mean_q_f, cov_q_f, _ = super().sample_from_variational_marginal(X, S, diagonal, is_duvenaud, init_Z)
         return f, mean_q_f, cov_q_f, f

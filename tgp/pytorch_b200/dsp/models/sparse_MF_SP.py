@@ -346,14 +346,22 @@ class sparse_MF_SP(nn.Module):
         return f, mean_q_f, cov_q_f
 
     def sample_from_variational_marginal(self, X, S, diagonal, is_duvenaud, init_Z=None):
-        X = self._rows3(X).repeat(1, S, 1)
+        """S warped samples per row.  The reference repeats X S times through the whole q(f) computation
+        (sparse_MF_SP.py:911-922), i.e. S x the cost of the marginals; mu and v do not depend on the sample, so they are
+        computed ONCE here and repeated (same distribution of samples, 1/S of the work)."""
+        if not diagonal:
+            raise NotImplementedError('This function only works with diagonal=True')
+        X = self._rows3(X)
         if self.is_training:
             self.train()
         else:
             self._eval_mode()
-        f0, mean_q_f0, cov_q_f0 = self.sample_from_variational_marginal_base(X=X, diagonal=diagonal,
-                                                                             is_duvenaud=is_duvenaud, init_Z=init_Z)
-        f = torch.stack([g(f0[idx, :], X[idx]) for idx, g in enumerate(self.G_matrix)])
+        mean1, cov1 = self.marginal_variational_qf_parameters(X, diagonal=True, is_duvenaud=is_duvenaud, init_Z=init_Z)
+        mean_q_f0, cov_q_f0 = mean1.repeat(1, S, 1), cov1.repeat(1, S, 1)
+        e = torch.randn(mean_q_f0.shape, dtype=mean_q_f0.dtype, device=mean_q_f0.device)
+        f0 = (e * cov_q_f0.sqrt() + mean_q_f0).squeeze(dim=2)
+        Xr = X.repeat(1, S, 1)                      # input-dependent flows see every repeated row (fresh dropout mask each)
+        f = torch.stack([g(f0[idx, :], Xr[idx]) for idx, g in enumerate(self.G_matrix)])
         self.train()
         return f, mean_q_f0, cov_q_f0, f0
 
