@@ -1,5 +1,10 @@
+"""Observation models of the hot path.  Each class keeps the reference's constructor and method signatures
+(`expected_log_prob`, `marginal_moments`, `sample_from_output`) and launches the fused row epilogue
+(`_rows.py` -> tgp_ell_forward / tgp_test_rows) instead of materialising the S x MB quadrature grid.
+
+`MulticlassCategorical` and `WarpedGaussianLinearMean` of the reference are outside the scope table."""
+from .Bernoulli import Bernoulli
 from .GaussianLinearMean import GaussianLinearMean
 from .GaussianNonLinearMean import GaussianNonLinearMean
-from .Bernoulli import Bernoulli
 
-__all__ = ['GaussianLinearMean', 'GaussianNonLinearMean', 'Bernoulli']
+__all__ = ['Bernoulli', 'GaussianLinearMean', 'GaussianNonLinearMean']
