@@ -298,12 +298,20 @@ def run_ours(args):
                 eng.test_rows(mu, v, yb, None, 1, 1.0)
             e1.record()
             torch.cuda.synchronize()
-            tn = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            e2 = torch.cuda.Event(enable_timing=True)
+            for s in range(args.steps):                # same pass with the factorisation reused (frozen parameters)
+                xb, yb = dev_batch(args.warmup + s)
+                mu, v = eng.qf_forward(xb)
+                eng.test_rows(mu, v, yb, None, 1, 1.0)
+            e2.record()
+            torch.cuda.synchronize()
+            tn = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tn, op=dist.ReduceOp.MAX)
         return dict(ms_total=ms, value=BATCH * world * args.steps / (ms * 1e-3), loss=float(loss.item()),
                     gemm_ms=list(gemm_ms), gemm_n=list(gemm_n), launches=int(launches), clocks=clk,
-                    test_nll_rows_per_s=BATCH * world * args.steps / (float(tn.item()) * 1e-3))
+                    test_nll_rows_per_s=BATCH * world * args.steps / (float(tn[0].item()) * 1e-3),
+                    test_nll_cached_rows_per_s=BATCH * world * args.steps / (float(tn[1].item()) * 1e-3))
 
     # the secondary mode runs first: on a fresh box the first seconds of a process are not steady (cold clocks, lazy
     # module loads), and the headline should not absorb that
@@ -359,7 +367,8 @@ def run_ours(args):
             'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
             'final_loss': final_loss, 'compute': args.compute,
             'test_nll': {'value': head['test_nll_rows_per_s'], 'unit': 'rows/s',
-                         'what': 'test log-lik + predictive moments forward (prepare + marginals + quadrature), device-resident'},
+                         'what': 'test log-lik + predictive moments forward (prepare + marginals + quadrature), device-resident',
+                         'with_factorisation_reused_across_batches': head['test_nll_cached_rows_per_s']},
             'other_mode': {'compute': 'tf32x3' if args.compute == 'f64' else 'f64', 'value': other['value'], 'unit': 'rows/s',
                            'ms_per_step': other['ms_total'] / args.steps, 'final_loss': other['loss'],
                            'loss_rel_diff_vs_headline': abs(other['loss'] - final_loss) / abs(final_loss),

@@ -142,3 +142,22 @@ def test_predictive_sampling_statistics():
     sm, sv = samples[0, :, :, 0].mean(0), samples[0, :, :, 0].var(0)
     assert float(((sm - m1).abs() / m2.sqrt()).max()) < 6.0 / S ** 0.5 * 1.5
     assert float((sv / m2 - 1).abs().max()) < 0.25
+
+
+def test_eval_factorisation_cache_is_transparent():
+    """Consecutive no-grad evaluations reuse the factorisation; any parameter update or training call invalidates it."""
+    g = Golden('boston_tgp_sal2_p1')
+    model = build_from_golden(g, DEV)
+    Xt = g.t('Xte').to(DEV)
+    with torch.no_grad():
+        mu1, v1 = model.marginal_variational_qf_parameters(Xt, diagonal=True, is_duvenaud=False)
+        eng = [e for k, e in model._engines.items() if k[0] == 'qf'][0]
+        gen = eng.generation
+        mu2, v2 = model.marginal_variational_qf_parameters(Xt, diagonal=True, is_duvenaud=False)
+        assert eng.prepared_key is not None and torch.equal(mu1, mu2) and torch.equal(v1, v2)
+        model.Z.add_(0.01)                                   # in-place update bumps the version -> refactorise
+        mu3, _ = model.marginal_variational_qf_parameters(Xt, diagonal=True, is_duvenaud=False)
+        assert not torch.equal(mu1, mu3)
+        model.Z.sub_(0.01)
+    model.set_is_training(True)
+    assert eng.prepared_key is None

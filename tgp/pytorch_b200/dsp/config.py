@@ -38,6 +38,9 @@ constant_jitter = None
 global_jitter = None
 compute = 'f64'                # 'f64': FP64 DMMA path (parity mode, what main.py's set_maximum_precission runs);
                                # 'tf32x3': batch contractions on tcgen05 (3xTF32, FP32 accumulate), rest FP64
+cache_factorisation_in_eval = True   # consecutive no-grad evaluations with unchanged parameters reuse L, L^-1 (the cache
+                                     # is keyed on tensor identity + in-place version; mutate parameters through
+                                     # `.data` in-place only after set_is_training() / ELBO(), which drop it)
 check_cholesky_status = True    # False: skip the 4-byte status read-back after the factorisation (no host sync)
 
 device = check_device()

@@ -66,6 +66,12 @@ class sparse_MF_SP(nn.Module):
 
     def set_is_training(self, mode):
         self.is_training = mode
+        self._invalidate_eval_cache()
+
+    def _invalidate_eval_cache(self):
+        """Forget factorisations cached for evaluation batches (see functional._QfMarginals)."""
+        for eng in self._engines.values():
+            eng.prepared_key = None
 
     def initialize_inducing(self, init_Z, add_noise_inducing):
         if self.Z_is_shared:
@@ -189,6 +195,8 @@ class sparse_MF_SP(nn.Module):
                 self._engines[key] = Engine(self.M, self.inp_dim, 'gauss_linear', 0, FlowLayout([]), X.device,
                                             compute=self._compute())
             eng = self._engines[key]
+            if not cg.cache_factorisation_in_eval:
+                eng.prepared_key = None
             mu, v = Fn.qf_marginals(eng, X[dy].to(torch.float64).contiguous(), Z, raw_ls, raw_os, m, L_raw,
                                     cg.check_cholesky_status)
             mus.append(mu)
@@ -211,6 +219,7 @@ class sparse_MF_SP(nn.Module):
         """(ELBO, ELL, KLD) for a minibatch — the fused forward; `.backward()` runs the fused backward kernels."""
         X = self._rows3(X)
         self._check_fused_scope(X)
+        self._invalidate_eval_cache()
         assert self.G_flow_connection == 'single', 'sparse_MF_SP places one independent flow per output'
         MB = Y.size(0)
         scale = self._global_scale(MB)

@@ -125,6 +125,7 @@ class Engine:
         self._params = None
         self._keep = None
         self.generation = 0          # bumped by every prepare(); backward passes check it
+        self.prepared_key = None     # parameter identity/version of the factorisation held in step_ws (eval cache)
         self.qt, self.qw = gauss_hermite(self.n_quad, self.device) if likelihood != 'gauss_linear' else (None, None)
 
     # -- helpers ------------------------------------------------------------------------------------------------
