@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(ABB_COLS) k_make_abbar(double* __restrict__ AB
 //   dls[d]   += sum_{n,j} t * (xs[n,d] - zs[j,d])^2 / ls[d]
 //   dos      += sum_{n,j} t / os
 // sym = 1 reads Kbar symmetrised, 0.5*(Kbar[n,j] + Kbar[j,n]) (the K_zz case, where X = Zs and R = M).
-constexpr int KG_TC = 64, KG_TR = 4, KG_THREADS = KG_TC * KG_TR, KG_ROWS = 64;
+// 256 rows per CTA: every CTA ends with one FP64 atomic per (column, dimension), so taller CTAs mean fewer
+// same-address atomics on dZ (128 row-blocks per 8192-row chunk serialised on each address with 64-row CTAs)
+constexpr int KG_TC = 64, KG_TR = 4, KG_THREADS = KG_TC * KG_TR;
+__host__ __device__ constexpr int kg_rows(int maxd) { return maxd <= 16 ? 256 : 64; }      // static shared memory stays below 48 KiB
 template <int MAXD, typename KBT>
 __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restrict__ Kbar, long ldk,
                                                              const double* __restrict__ X, int x_scaled,
@@ -46,6 +49,7 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
                                                              const double* __restrict__ os, long R, int M, int D, int sym,
                                                              double zscale, double* __restrict__ dZ,
                                                              double* __restrict__ dls, double* __restrict__ dos) {
+    constexpr int KG_ROWS = kg_rows(MAXD);
     __shared__ double xs[KG_ROWS][MAXD + 1];
     __shared__ double red[KG_THREADS];
     const int tid = threadIdx.x, c = tid % KG_TC, ry = tid / KG_TC;
@@ -133,8 +137,7 @@ template <typename KBT>
 inline int launch_kernel_grads(const KBT* Kbar, long ldk, const double* X, int x_scaled, const double* Zs,
                                const double* ls, const double* os, long R, int M, int D, int sym, double zscale,
                                double* dZ, double* dls, double* dos, cudaStream_t st) {
-    dim3 grid((unsigned)cdiv(M, KG_TC), (unsigned)cdiv(R, KG_ROWS));
-#define TGP_KG(MD) k_kernel_grads<MD, KBT><<<grid, KG_THREADS, 0, st>>>(Kbar, ldk, X, x_scaled, Zs, ls, os, R, M, D, sym, \
+#define TGP_KG(MD) k_kernel_grads<MD, KBT><<<dim3((unsigned)cdiv(M, KG_TC), (unsigned)cdiv(R, kg_rows(MD))), KG_THREADS, 0, st>>>(Kbar, ldk, X, x_scaled, Zs, ls, os, R, M, D, sym, \
                                                                   zscale, dZ, dls, dos)
     if (D <= 4) TGP_KG(4);
     else if (D <= 8) TGP_KG(8);
