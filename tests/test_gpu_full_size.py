@@ -1,0 +1,108 @@
+"""Full-size checks at the BASELINE configurations (the oracle cannot run these sizes in seconds): size-independent
+properties — central finite differences of the ELBO against the analytic gradients, row-shard additivity, agreement of
+the tensor-core mode with the FP64 mode, finiteness.
+
+cfg4: regression, D = 8, M = 1024, 65536-row minibatch, StepTanhL(1,3), Gaussian likelihood, 100 GH points.
+cfg5: binary classification, D = 16, M = 2048, Bernoulli likelihood, SAL(1) flow (32768-row minibatch here).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import tgp_oracle as O
+from tests.golden_util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _state(M, D, R, seed, classification):
+    g = torch.Generator().manual_seed(seed)
+    f64 = torch.float64
+    X = torch.randn(R, D, generator=g, dtype=f64)
+    w = torch.randn(D, generator=g, dtype=f64)
+    if classification:
+        pr = 0.5 * (1 + torch.erf((X @ w) / math.sqrt(D) / math.sqrt(2.0)))
+        y = (pr > torch.rand(R, generator=g, dtype=f64)).to(f64)
+    else:
+        y = torch.sinh(0.7 * (X @ w) / math.sqrt(D)) + 0.1 * torch.randn(R, generator=g, dtype=f64)
+        y = (y - y.mean()) / y.std()
+    p = dict(Z=X[torch.randperm(R, generator=g)[:M]].clone(),
+             raw_lengthscale=O.inv_softplus(1.5 + torch.rand(D, generator=g, dtype=f64)),
+             raw_outputscale=O.inv_softplus(torch.tensor(1.5, dtype=f64)),
+             m=0.5 * torch.randn(M, generator=g, dtype=f64),
+             L_raw=0.5 * torch.eye(M, dtype=f64) + 0.02 * torch.randn(M, M, generator=g, dtype=f64),
+             log_var_noise=torch.tensor(math.log(0.1), dtype=f64))
+    if classification:
+        p['flow'] = [('sal', torch.tensor(0.1, dtype=f64), torch.tensor(1.05, dtype=f64), False, False),
+                     ('affine', torch.tensor(0.9, dtype=f64), torch.tensor(0.05, dtype=f64), False)]
+    else:
+        steps = [(torch.tensor(0.1 * i, dtype=f64), torch.tensor(-0.5, dtype=f64), torch.tensor(0.3 * i - 0.3, dtype=f64),
+                  torch.tensor(0.2, dtype=f64)) for i in range(3)]
+        p['flow'] = [('tanh_step', steps, True), ('affine', torch.tensor(1.05, dtype=f64), torch.tensor(-0.02, dtype=f64), False)]
+    return X, y, p
+
+
+def _elbo(p, X, y, N, lik, compute, grads=True, overrides=None):
+    from tests.gpu_util import engine_inputs, make_engine
+    from tgp.pytorch_b200 import functional as Fn
+    eng, theta, _, names = make_engine(p, lik, 100, DEV, compute=compute)
+    ei = engine_inputs(p, DEV)
+    if overrides:
+        for k, fn in overrides.items():
+            ei[k] = fn(ei[k])
+    leaves = [ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta]
+    for t in leaves:
+        t.requires_grad_(grads)
+    ELL, KLD, rows, mu, v = Fn.elbo_terms(eng, X, y, N / X.shape[0], ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'],
+                                          None if lik == 'bernoulli' else ei['log_var_noise'], theta, None)
+    E = ELL - KLD
+    if grads:
+        E.backward()
+    return E.detach(), rows, {k: t.grad for k, t in zip(('Z', 'raw_ls', 'raw_os', 'm', 'L_raw', 'noise', 'theta'), leaves)}
+
+
+@pytest.mark.parametrize('cfg', ['cfg4', 'cfg5'])
+def test_full_size_finite_differences_and_modes(cfg):
+    clf = cfg == 'cfg5'
+    M, D, R, N = (2048, 16, 32768, 1.0e6) if clf else (1024, 8, 65536, 5.0e6)
+    lik = 'bernoulli' if clf else 'gauss_nonlinear'
+    X, y, p = _state(M, D, R, seed=2024, classification=clf)
+    Xd, yd = X.to(DEV).contiguous(), y.to(DEV).contiguous()
+    E, rows, g = _elbo(p, Xd, yd, N, lik, 'f64')
+    assert torch.isfinite(E) and torch.isfinite(rows).all()
+    for t in g.values():
+        assert t is None or torch.isfinite(t).all()
+    # central finite differences along three parameter directions (FP64, h chosen for ~1e-7 truncation/round-off balance)
+    h = 1e-5
+    def fd(key, direction):
+        up = _elbo(p, Xd, yd, N, lik, 'f64', grads=False, overrides={key: lambda t: t + h * direction})[0]
+        dn = _elbo(p, Xd, yd, N, lik, 'f64', grads=False, overrides={key: lambda t: t - h * direction})[0]
+        return float((up - dn) / (2 * h))
+    gen = torch.Generator().manual_seed(1)
+    d_ls = torch.randn(D, generator=gen, dtype=torch.float64).to(DEV)
+    d_m = torch.randn(M, generator=gen, dtype=torch.float64).to(DEV)
+    d_Z = torch.randn(M, D, generator=gen, dtype=torch.float64).to(DEV)
+    for key, d in (('raw_ls', d_ls), ('m', d_m), ('Z', d_Z)):
+        ana = float((g[key] * d).sum())
+        num = fd(key, d)
+        assert abs(ana - num) < 2e-6 * max(abs(ana), abs(num)), (cfg, key, ana, num)
+    # row-shard additivity: two slices with the global scale
+    from tests.gpu_util import engine_inputs, make_engine
+    eng, theta, _, _ = make_engine(p, lik, 100, DEV)
+    ei = engine_inputs(p, DEV)
+    eng.set_params(ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], None if clf else ei['log_var_noise'], theta)
+    kl, _ = eng.prepare(0.0)
+    tot = 0.0
+    for sl in (slice(0, R // 3), slice(R // 3, R)):
+        rb = eng.new_reduce_buffer()
+        mu, v = eng.qf_forward(Xd[sl].contiguous())
+        eng.ell_forward(mu, v, yd[sl].contiguous(), None, N / R, rb, want_grad=False)
+        tot = tot + rb[0]
+    assert rel_err((N / R * tot - kl[0]).cpu(), E.cpu()) < 1e-12
+    # tensor-core mode against the FP64 mode at full size
+    E32, rows32, g32 = _elbo(p, Xd, yd, N, lik, 'tf32x3')
+    assert rel_err(E32.cpu(), E.cpu()) < 1e-4
+    assert rel_err(rows32.cpu(), rows.cpu()) < 2e-4
+    assert rel_err(g32['m'].cpu(), g['m'].cpu()) < 1e-3
