@@ -120,6 +120,11 @@ int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu
                   const void* rowparams, long R, int n_mc, double y_std, const void* quad_t, const void* quad_w,
                   const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream);
 
+/* Library options.  TGP_OPT_FUSED_FORWARD (tensor-core mode): 1 = tgp_qf_forward is ONE kernel that generates the K_xz
+ * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels. */
+enum { TGP_OPT_FUSED_FORWARD = 1 };
+int tgp_set_option(int key, int value);
+
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
 long tgp_launch_count(void);
 /* Live per-launch timing of the GEMM kernel with CUDA events on the launching stream (bench.py's roofline).

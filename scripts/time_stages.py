@@ -21,7 +21,10 @@ def timed(fn, n=10):
     return sorted(ts)[len(ts) // 2], out
 
 
-for compute in sys.argv[1:] or ['f64', 'tf32x3']:
+from tgp.pytorch_b200 import _lib
+for compute in sys.argv[1:] or ['f64', 'tf32x3', 'tf32x3+fused']:
+    _lib.load().tgp_set_option(_lib.OPT_FUSED_FORWARD, 1 if compute.endswith('+fused') else 0)
+    label, compute = compute, compute.split('+')[0]
     eng, theta, _, _ = make_engine(p, 'gauss_nonlinear', 100, dev, compute=compute)
     ei = engine_inputs(p, dev)
     eng.set_params(ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta)
@@ -37,5 +40,5 @@ for compute in sys.argv[1:] or ['f64', 'tf32x3']:
     t_fb, _ = timed(bwd)
     t_chain, _ = timed(lambda: eng.chain_backward(rb, 1.0, -1.0))
     t_test, _ = timed(lambda: eng.test_rows(mu, v, yb, None, 1, 1.0))
-    print('%-7s prepare %.3f  qf_forward %.3f  ell %.3f  qf_backward %.3f  chain %.3f  test_rows %.3f  | sum %.3f ms'
-          % (compute, t_prep, t_fwd, t_ell, t_fb - t_fwd, t_chain, t_test, t_prep + t_fwd + t_ell + (t_fb - t_fwd) + t_chain))
+    print('%-13s prepare %.3f  qf_forward %.3f  ell %.3f  qf_backward %.3f  chain %.3f  test_rows %.3f  | sum %.3f ms'
+          % (label, t_prep, t_fwd, t_ell, t_fb - t_fwd, t_chain, t_test, t_prep + t_fwd + t_ell + (t_fb - t_fwd) + t_chain))

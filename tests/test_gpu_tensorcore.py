@@ -114,3 +114,34 @@ def test_float32_model_runs_on_the_tensorcore_mode(name):
         ref = -g.t('grad:' + n)
         if float(ref.norm()) > 0:
             assert rel_err(prm.grad.detach().double().cpu().reshape(ref.shape), ref) < 2e-4, n
+
+
+@pytest.mark.parametrize('R,M,D', [(130, 63, 3), (1000, 200, 13), (4096, 1024, 8), (257, 300, 16), (5000, 100, 4)])
+def test_fused_forward_kernel_matches_the_staged_pipeline(R, M, D):
+    """TGP_OPT_FUSED_FORWARD: K tiles generated inside the tcgen05 kernel, mu / v from the TMEM accumulators — must agree
+    with the staged tensor-core pipeline (same operands, same MMAs) and leave an identical [A | B] for the backward."""
+    from tests.test_gpu_edge_cases import _problem
+    from tests.gpu_util import engine_inputs, make_engine
+    from tgp.pytorch_b200 import _lib
+    lib = _lib.load()
+    X, y, p = _problem(R, M, D, seed=R + M + D)
+    Xd, yd = X.to(DEV).contiguous(), y.to(DEV).contiguous()
+    out = {}
+    try:
+        for fused in (0, 1):
+            lib.tgp_set_option(_lib.OPT_FUSED_FORWARD, fused)
+            eng, theta, _, _ = make_engine(p, 'gauss_nonlinear', 30, DEV, compute='tf32x3')
+            ei = engine_inputs(p, DEV)
+            eng.set_params(ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta)
+            eng.prepare(0.0)
+            mu, v = eng.qf_forward(Xd)
+            rb = eng.new_reduce_buffer()
+            rows, g_mu, g_v, _ = eng.ell_forward(mu, v, yd, None, 3.0, rb)
+            eng.qf_backward(Xd, g_mu, g_v, rb)
+            torch.cuda.synchronize()
+            out[fused] = (mu.cpu(), v.cpu(), rb.cpu())
+    finally:
+        lib.tgp_set_option(_lib.OPT_FUSED_FORWARD, 0)
+    assert rel_err(out[1][0], out[0][0]) < 1e-12
+    assert rel_err(out[1][1], out[0][1]) < 1e-12
+    assert rel_err(out[1][2], out[0][2]) < 1e-10          # pre-chain accumulators (atomics: order differs)

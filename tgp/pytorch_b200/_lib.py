@@ -13,6 +13,7 @@ LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
 FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL = 0, 1, 2, 3
 FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
 MAX_LAYERS = 64
+OPT_FUSED_FORWARD = 1
 
 
 class TgpFlowLayer(C.Structure):
@@ -52,6 +53,7 @@ SIGNATURES = {
                                 _P, _P]),
     'tgp_test_rows': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _P, _L, _I, _D, _P, _P, _P, _P, _P,
                            _P, _P]),
+    'tgp_set_option': (_I, [_I, _I]),
     'tgp_launch_count': (_L, []),
     'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'tgp_debug_gemm_f64': (_I, [_I, _I, _I, _P, _L, _I, _P, _L, _I, _P, _L, _D, _D, _I, _I, _I, _P]),

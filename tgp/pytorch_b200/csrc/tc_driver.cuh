@@ -3,11 +3,13 @@
 #include "step_kernels.cuh"
 #include "backward_kernels.cuh"
 #include "tc_path.cuh"
+#include "tc_fused.cuh"
 
 namespace tgp {
 namespace tc {
 
 constexpr long TC_ROW_CHUNK = 16384;
+extern int g_fused_forward;      // 1: forward = ONE kernel (K tiles generated inside the tcgen05 contraction); 0: staged planes
 
 struct StepPlanes { float *Whi, *Wlo, *Wthi, *Wtlo; long ldk, ld2m; };
 struct BatchPlanes {
@@ -75,6 +77,13 @@ inline int qf_forward(const StepView& s, void* step_ws, void* batch_ws, const do
     const int M = s.M, D = s.D;
     StepPlanes sp = carve_step_planes(step_ws, M, D);
     BatchPlanes b = carve_batch_planes(batch_ws, M, R);
+    if (g_fused_forward && D <= FUSED_MAX_D) {
+        FusedFwdParams fp;
+        fp.X = X; fp.Zs = s.Zs; fp.ls = s.ls; fp.os = s.os; fp.mvec = s.mvec;
+        fp.R = (int)R; fp.M = M; fp.D = D; fp.AB = b.AB; fp.ldab = b.ld2m; fp.mu = mu; fp.v = v;
+        Operand W{sp.Whi, sp.Wlo, 2L * M, M, sp.ldk};
+        return fwd_fused(W, fp, st);
+    }
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         TGP_TRY(launch_rbf_planes(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, b.Khi, b.Klo, b.ldk, nullptr, nullptr, 0, st));

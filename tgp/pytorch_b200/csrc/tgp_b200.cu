@@ -11,6 +11,7 @@ namespace tgp {
 char g_last_error[512] = "";
 long g_launch_count = 0;
 GemmTimer g_gemm_timer;
+namespace tc { int g_fused_forward = 0; }
 
 constexpr long ROW_CHUNK = 8192;     // rows whose K / Kbar tiles are staged at once (L2-sized for M = 1024)
 
@@ -354,6 +355,11 @@ int tgp_test_rows(const TgpModel* md, const TgpParams* p, const void* mu, const 
 }
 
 long tgp_launch_count(void) { return g_launch_count; }
+
+int tgp_set_option(int key, int value) {
+    if (key == TGP_OPT_FUSED_FORWARD) { tc::g_fused_forward = value != 0; return 0; }
+    return set_error(-1, "unknown option");
+}
 
 int tgp_gemm_timing(int enable, double* ms_out, long* launches_out) {
     g_gemm_timer.flush();
