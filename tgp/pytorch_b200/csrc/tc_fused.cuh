@@ -21,7 +21,7 @@ namespace tc {
 
 constexpr int FUSED_THREADS = 512;
 constexpr int FUSED_MAX_D = 16;
-constexpr int ZBUF_DOUBLES = BK * FUSED_MAX_D;                       // one k-block of pre-scaled inducing points
+constexpr int ZBUF_DOUBLES = BK * (FUSED_MAX_D + 1);                 // one k-block of pre-scaled inducing points + their norms
 constexpr int FUSED_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + STAGES * ZBUF_DOUBLES * 8 + BM * 3 * 8 + 256;
 
 struct FusedFwdParams {
@@ -35,6 +35,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+template <int MAXD>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fwd_fused_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const FusedFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -135,44 +136,63 @@ fwd_fused_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
             const long row = (long)tile * BM + t;
-            double x[FUSED_MAX_D];
+            // squared distance by expansion in FP64: |x|^2 + |z|^2 - 2 x.z (absolute error ~1e-15, the formula gpytorch uses);
+            // eight inducing points at a time give eight independent FMA chains per thread
+            double x2[MAXD], xn = 0.0;
 #pragma unroll
-            for (int d = 0; d < FUSED_MAX_D; ++d) x[d] = (d < D && row < p.R) ? p.X[row * D + d] / p.ls[d] : 0.0;
+            for (int d = 0; d < MAXD; ++d) {
+                const double xd = (d < D && row < p.R) ? p.X[row * D + d] / p.ls[d] : 0.0;
+                xn = fma(xd, xd, xn);
+                x2[d] = -2.0 * xd;
+            }
             for (int nc = 0; nc < n_chunks; ++nc) {
                 const int ke = k_end(nc * BN);
                 for (int k = 0; k < ke; k += BK) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    double* zb = zbuf + stage * ZBUF_DOUBLES;
-                    for (int i = t; i < BK * D; i += 128) {
-                        const int c = i / D, d = i - c * D;
-                        zb[c * D + d] = (k + c < M) ? p.Zs[(long)(k + c) * D + d] : 0.0;
+                    double* zb = zbuf + stage * ZBUF_DOUBLES;          // [BK][MAXD] then [BK] norms
+                    double* zn = zb + BK * MAXD;
+                    for (int i = t; i < BK * MAXD; i += 128) {
+                        const int c = i / MAXD, d = i - c * MAXD;
+                        zb[i] = (k + c < M && d < D) ? p.Zs[(long)(k + c) * D + d] : 0.0;
+                    }
+                    named_bar_sync(2, 128);
+                    if (t < BK) {
+                        double nz = 0.0;
+#pragma unroll
+                        for (int d = 0; d < MAXD; ++d) nz = fma(zb[t * MAXD + d], zb[t * MAXD + d], nz);
+                        zn[t] = nz;
                     }
                     named_bar_sync(2, 128);
                     uint8_t* st = smem + stage * STAGE_BYTES;
                     uint8_t* rowp_hi = st + t * 128;
                     uint8_t* rowp_lo = st + A_BYTES + t * 128;
-#pragma unroll 2
-                    for (int ch = 0; ch < 8; ++ch) {                 // eight 16-byte chunks of the 128-byte swizzle row
-                        float hi[4], lo[4];
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BK; c0 += 8) {             // two 16-byte chunks of the 128-byte swizzle row
+                        double acc[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = ch * 4 + e;
+                        for (int e = 0; e < 8; ++e) acc[e] = xn + zn[c0 + e];
+#pragma unroll
+                        for (int d = 0; d < MAXD; ++d)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[e] = fma(x2[d], zb[(c0 + e) * MAXD + d], acc[e]);
+                        float hi[8], lo[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
                             float val = 0.f;
-                            if (row < p.R && k + c < M) {
-                                double acc = 0.0;
-#pragma unroll
-                                for (int d = 0; d < FUSED_MAX_D; ++d)
-                                    if (d < D) { const double df = x[d] - zb[c * D + d]; acc = fma(df, df, acc); }
-                                const double arg = -0.5 * acc;
+                            if (row < p.R && k + c0 + e < M) {
+                                const double arg = -0.5 * fmax(acc[e], 0.0);
                                 const float ahi = (float)arg;
                                 val = sf * expf(ahi) * (1.0f + (float)(arg - (double)ahi));
                             }
                             hi[e] = tf32_hi(val);
                             lo[e] = val - hi[e];
                         }
-                        const int phys = (ch ^ (t & 7)) << 4;         // Swizzle<3,4,3>: 16 B chunk index XOR (row mod 8)
-                        *reinterpret_cast<float4*>(rowp_hi + phys) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4*>(rowp_lo + phys) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int phys = (((c0 >> 2) + h2) ^ (t & 7)) << 4;   // Swizzle<3,4,3>: chunk index XOR (row mod 8)
+                            *reinterpret_cast<float4*>(rowp_hi + phys) = make_float4(hi[4 * h2], hi[4 * h2 + 1], hi[4 * h2 + 2], hi[4 * h2 + 3]);
+                            *reinterpret_cast<float4*>(rowp_lo + phys) = make_float4(lo[4 * h2], lo[4 * h2 + 1], lo[4 * h2 + 2], lo[4 * h2 + 3]);
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
                     __syncwarp();
@@ -269,14 +289,18 @@ inline int fwd_fused(const Operand& W, const FusedFwdParams& p, cudaStream_t st)
     TGP_TRY(make_map(&mBl, W.lo, W.rows, W.cols, W.ld, BN));
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+        cudaFuncSetAttribute(fwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+        cudaFuncSetAttribute(fwd_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+        cudaFuncSetAttribute(fwd_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
         attr = true;
     }
     const int tiles = (p.R + BM - 1) / BM;
     const int grid = tiles < 148 ? tiles : 148;
     const bool timed = g_gemm_timer.enabled;
     if (timed) g_gemm_timer.begin(2, st);
-    fwd_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, st>>>(mB, mBl, p);
+    if (p.D <= 4) fwd_fused_kernel<4><<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, st>>>(mB, mBl, p);
+    else if (p.D <= 8) fwd_fused_kernel<8><<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, st>>>(mB, mBl, p);
+    else fwd_fused_kernel<16><<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, st>>>(mB, mBl, p);
     if (timed) g_gemm_timer.end(st);
     return check_launch("fwd_fused_kernel");
 }
