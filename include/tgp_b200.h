@@ -121,8 +121,10 @@ int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu
                   const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream);
 
 /* Library options.  TGP_OPT_FUSED_FORWARD (tensor-core mode): 1 = tgp_qf_forward is ONE kernel that generates the K_xz
- * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels. */
-enum { TGP_OPT_FUSED_FORWARD = 1 };
+ * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels.
+ * TGP_OPT_ROW_CHUNK (FP64 mode): rows per launch of the batch contractions (default 32768; a tuning knob — it changes the
+ * workspace size, so set it before asking for tgp_batch_workspace_bytes). */
+enum { TGP_OPT_FUSED_FORWARD = 1, TGP_OPT_ROW_CHUNK = 2 };
 int tgp_set_option(int key, int value);
 
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */

@@ -22,6 +22,8 @@ def timed(fn, n=10):
 
 
 from tgp.pytorch_b200 import _lib
+if os.environ.get('TGP_ROW_CHUNK'):
+    _lib.load().tgp_set_option(_lib.OPT_ROW_CHUNK, int(os.environ['TGP_ROW_CHUNK']))
 for compute in sys.argv[1:] or ['f64', 'tf32x3', 'tf32x3+fused']:
     _lib.load().tgp_set_option(_lib.OPT_FUSED_FORWARD, 1 if compute.endswith('+fused') else 0)
     label, compute = compute, compute.split('+')[0]

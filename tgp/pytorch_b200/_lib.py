@@ -14,6 +14,7 @@ FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL = 0, 1, 2, 3
 FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
 MAX_LAYERS = 64
 OPT_FUSED_FORWARD = 1
+OPT_ROW_CHUNK = 2
 
 
 class TgpFlowLayer(C.Structure):

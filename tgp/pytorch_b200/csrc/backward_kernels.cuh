@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
                                                              const double* __restrict__ Zs, const double* __restrict__ ls,
                                                              const double* __restrict__ os, long R, int M, int D, int sym,
                                                              double zscale, double* __restrict__ dZ,
-                                                             double* __restrict__ dls, double* __restrict__ dos) {
+                                                             double* __restrict__ dls, double* __restrict__ dos,
+                                                             const double* __restrict__ Kval, long ldkv) {
     constexpr int KG_ROWS = kg_rows(MAXD);
     __shared__ double xs[KG_ROWS][MAXD + 1];
     __shared__ double red[KG_THREADS];
@@ -85,10 +86,15 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
 #pragma unroll
                 for (int d = 0; d < MAXD; ++d) if (d < D) { az[d] = fmaf(t, df[d], az[d]); al[d] = fmaf(t * df[d], df[d], al[d]); }
             } else {
-                double q = 0.0;
+                double t;
+                if (Kval) {                  // the forward's K tile is still resident: no distance / exponential needed
+                    t = kb * Kval[n * ldkv + j];
+                } else {
+                    double q = 0.0;
 #pragma unroll
-                for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
-                const double t = kb * s * exp(-0.5 * q);
+                    for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
+                    t = kb * s * exp(-0.5 * q);
+                }
                 asum += t;
 #pragma unroll
                 for (int d = 0; d < MAXD; ++d) if (d < D) {
@@ -136,9 +142,10 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
 template <typename KBT>
 inline int launch_kernel_grads(const KBT* Kbar, long ldk, const double* X, int x_scaled, const double* Zs,
                                const double* ls, const double* os, long R, int M, int D, int sym, double zscale,
-                               double* dZ, double* dls, double* dos, cudaStream_t st) {
+                               double* dZ, double* dls, double* dos, cudaStream_t st, const double* Kval = nullptr,
+                               long ldkv = 0) {
 #define TGP_KG(MD) k_kernel_grads<MD, KBT><<<dim3((unsigned)cdiv(M, KG_TC), (unsigned)cdiv(R, kg_rows(MD))), KG_THREADS, 0, st>>>(Kbar, ldk, X, x_scaled, Zs, ls, os, R, M, D, sym, \
-                                                                  zscale, dZ, dls, dos)
+                                                                  zscale, dZ, dls, dos, Kval, ldkv)
     if (D <= 4) TGP_KG(4);
     else if (D <= 8) TGP_KG(8);
     else if (D <= 16) TGP_KG(16);

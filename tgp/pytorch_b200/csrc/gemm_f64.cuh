@@ -63,65 +63,123 @@ struct GemmTimer {
 };
 extern GemmTimer g_gemm_timer;
 
-constexpr int GBM = 128, GBN = 128, GBK = 16, GPAD = 4, GLD = GBK + GPAD;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = 2 * 2 * GBM * GLD * (int)sizeof(double);   // 2 stages x (A,B)
+// CTA tile 128 x 64 (4 warps as 2 x 2, warp tile 64 x 32), two CTAs per SM: one CTA's prologue / epilogue / barrier bubbles
+// are covered by the other's MMAs (the 128 accumulator registers per thread leave room for exactly 8 such warps per SM).
+// -DTGP_GEMM_WIDE selects the earlier 128 x 128 / 8-warp / one-CTA-per-SM shape for A/B measurements.
+#ifdef TGP_GEMM_WIDE
+constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 4, GEMM_CTAS_PER_SM = 1;
+#else
+constexpr int GBM = 128, GBN = 64, GBK = 16, GSTAGES = 3, GEMM_CTAS_PER_SM = 2;
+#endif
+constexpr int GWARPS_N = GBN / 32;
+constexpr int GEMM_THREADS = 32 * 2 * GWARPS_N;
+constexpr int GEMM_SLOTS = 148 * GEMM_CTAS_PER_SM;      // co-resident CTAs on a B200
+constexpr int GLD = GBK + 4;        // [row][k] tile: row pitch in doubles (conflict-free 8x4 fragment reads)
+constexpr int GLDT_A = GBM + 4;     // [k][row] tiles: k pitch in doubles, = 4 mod 16 (conflict-free 4x8 fragment reads)
+constexpr int GLDT_B = GBN + 4;
+constexpr int GOPER_A = GBM * GLD > GBK * GLDT_A ? GBM * GLD : GBK * GLDT_A;    // doubles per operand slot
+constexpr int GOPER_B = GBN * GLD > GBK * GLDT_B ? GBN * GLD : GBK * GLDT_B;
+constexpr int GSTAGE = GOPER_A + GOPER_B;
+constexpr int GEMM_SMEM_BYTES = GSTAGES * GSTAGE * (int)sizeof(double);
+
+// number of CTAs that do work for an M x N output (lower: tiles strictly above the diagonal exit immediately)
+inline long gemm_tiles(int M, int N, bool lower) {
+    const long Tm = (M + GBM - 1) / GBM, Tn = (N + GBN - 1) / GBN;
+    if (!lower) return Tm * Tn;
+    long t = 0;
+    for (long i = 0; i < Tm; ++i)
+        for (long j = 0; j < Tn; ++j) t += (j * GBN <= i * GBM + GBM - 1);
+    return t;
+}
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Loads this thread's 8 elements of a 128 x 16 operand tile into r[8].
-//   layout 0: thread -> row = tid>>1, k-offset (tid&1)*8, 8 consecutive k
-//   layout 1: thread -> k = tid&15, rows (tid>>4)*8 .. +7   (k fastest across lanes: transposing smem stores
-//             then hit 16 distinct banks)
-template <int LAYOUT>
-__device__ __forceinline__ void load_tile(double (&r)[8], const double* __restrict__ P, long ld, int rows, int K,
-                                          int row0, int k0, int kend, bool vec_ok, int tid) {
-    if (LAYOUT == 0) {
-        const int row = row0 + (tid >> 1);
-        const int k = k0 + (tid & 1) * 8;
-        if (row < rows && vec_ok && k + 8 <= kend) {
-            const double2* src = reinterpret_cast<const double2*>(P + (long)row * ld + k);
+// cp.async with zero fill: copies `bytes` (0..16 / 0..8) from global and zero-fills the rest of the destination.
+__device__ __forceinline__ void cp_async16(double* dst, const double* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Asynchronously copies one ROWS x 16 operand tile (rows row0.., k-range k0..k0+15 clipped to kend) into shared memory.
+//   layout 0 (memory [row][k]):  smem [row][GLD];      16-byte chunk c -> row c>>3, k (c&7)*2
+//   layout 1 (memory [k][row]):  smem [k][ROWS + 4];   16-byte chunk c -> k c/(ROWS/2), row (c%(ROWS/2))*2
+// Out-of-range elements are zero-filled by the copy itself; unaligned operands fall back to 8-byte copies.
+template <int LAYOUT, int ROWS>
+__device__ __forceinline__ void issue_tile(double* __restrict__ S, const double* __restrict__ P, long ld, int rows,
+                                           int row0, int k0, int kend, bool vec_ok, int tid) {
+    constexpr int PITCH_T = ROWS + 4;
+    static_assert((ROWS * 8) % GEMM_THREADS == 0, "tile chunks must divide over the threads");
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { double2 t = __ldg(src + i); r[2 * i] = t.x; r[2 * i + 1] = t.y; }
+    for (int i = 0; i < ROWS * 8 / GEMM_THREADS; ++i) {
+        const int c = tid + i * GEMM_THREADS;
+        int r, k;
+        double* dst;
+        if (LAYOUT == 0) { r = c >> 3; k = (c & 7) * 2; dst = S + r * GLD + k; }
+        else { k = c / (ROWS / 2); r = (c % (ROWS / 2)) * 2; dst = S + k * PITCH_T + r; }
+        const int row = row0 + r, kk = k0 + k;
+        // number of valid elements along the contiguous direction (0, 1 or 2); 0 if the other index is out of range
+        int nv;
+        const double* src;
+        if (LAYOUT == 0) { nv = row < rows ? min(2, max(0, kend - kk)) : 0; src = P + (long)row * ld + kk; }
+        else { nv = kk < kend ? min(2, max(0, rows - row)) : 0; src = P + (long)kk * ld + row; }
+        if (nv == 0) src = P;
+        if (vec_ok) {
+            cp_async16(dst, src, nv * 8);
         } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = (row < rows && k + i < kend) ? __ldg(P + (long)row * ld + k + i) : 0.0;
-        }
-    } else {
-        const int k = k0 + (tid & 15);
-        const int row = row0 + (tid >> 4) * 8;
-        if (k < kend && vec_ok && row + 8 <= rows) {
-            const double2* src = reinterpret_cast<const double2*>(P + (long)k * ld + row);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { double2 t = __ldg(src + i); r[2 * i] = t.x; r[2 * i + 1] = t.y; }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = (k < kend && row + i < rows) ? __ldg(P + (long)k * ld + row + i) : 0.0;
+            cp_async8(dst, src, nv >= 1 ? 8 : 0);
+            cp_async8(dst + 1, nv >= 2 ? src + 1 : P, nv >= 2 ? 8 : 0);
         }
     }
 }
 
-template <int LAYOUT>
-__device__ __forceinline__ void store_tile(const double (&r)[8], double* __restrict__ S, int tid) {
-    if (LAYOUT == 0) {
-        double2* dst = reinterpret_cast<double2*>(S + (tid >> 1) * GLD + (tid & 1) * 8);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_double2(r[2 * i], r[2 * i + 1]);
-    } else {
-        const int k = tid & 15, row = (tid >> 4) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) S[(row + i) * GLD + k] = r[i];
+// Fast path of the same copy for tiles that are interior in rows and k (every tile of the batch contractions at the
+// benchmark sizes): all address arithmetic is done once per CTA, a k-tile costs one pointer bump per operand and one
+// cp.async per 16-byte chunk.  (The generic path above spends ~40 integer instructions per chunk on bounds.)
+template <int LAYOUT, int ROWS>
+struct TileCopy {
+    static constexpr int NCHUNK = ROWS * 8 / GEMM_THREADS;
+    static constexpr int DSTEP = LAYOUT == 0 ? (GEMM_THREADS / 8) * GLD : (GEMM_THREADS / (ROWS / 2)) * (ROWS + 4);
+    const double* src0;   // this thread's chunk 0 of k-tile 0
+    long kstep, istep;    // doubles per k-tile / per chunk index
+    int dst0;
+    __device__ __forceinline__ void init(const double* P, long ld, int row0, int kb, int tid) {
+        if (LAYOUT == 0) {
+            const int r = tid >> 3, k = (tid & 7) * 2;
+            src0 = P + (long)(row0 + r) * ld + kb + k; kstep = GBK; istep = (long)(GEMM_THREADS / 8) * ld; dst0 = r * GLD + k;
+        } else {
+            const int k = tid / (ROWS / 2), r = (tid % (ROWS / 2)) * 2;
+            src0 = P + (long)(kb + k) * ld + row0 + r; kstep = (long)GBK * ld; istep = (long)(GEMM_THREADS / (ROWS / 2)) * ld;
+            dst0 = k * (ROWS + 4) + r;
+        }
     }
-}
+    __device__ __forceinline__ void issue(double* S, int kt) const {
+        const double* src = src0 + (long)kt * kstep;
+        double* dst = S + dst0;
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i) cp_async16(dst + i * DSTEP, src + (long)i * istep, 16);
+    }
+};
 
 template <int AL, int BL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_f64_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    // warp grid 2 (m) x GWARPS_N (n).  Warps that share a scheduler get complementary n-positions, so that the per-warp
+    // triangular clipping below removes the same amount of work from every scheduler: in the 8-warp shape warp and
+    // warp + 4 take n-quarters q and 3 - q; in the 4-warp shape neighbouring m-tiles (co-resident CTAs) swap halves.
+#ifdef TGP_GEMM_WIDE
+    const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
+#else
+    const int wm = warp >> 1, wn = (warp & 1) ^ (blockIdx.x & 1);
+#endif
     // m-tiles vary fastest (CTAs that are co-resident share the B tile); n-tiles are visited heaviest-first when the
     // triangular clipping makes their k-extent grow with n (b_tri == 1), so that the last wave holds the light tiles
     const int nt = (g.b_tri == 1) ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
@@ -148,6 +206,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
         nk = t1 - t0;
         if (nk == 0) return;
     }
+    // per-warp k-range inside the tile's range: a warp whose 64 rows / 32 columns see only zeros of a triangular operand
+    // in a k-tile skips that k-tile's MMAs (it still takes part in the copies and barriers)
+    int wkb = kb, wke = ke;
+    if (g.a_tri == 1) wke = min(wke, m0 + wm * 64 + 64);
+    if (g.a_tri == 2) wkb = max(wkb, m0 + wm * 64);
+    if (g.b_tri == 1) wke = min(wke, n0 + wn * 32 + 32);
+    if (g.b_tri == 2) wkb = max(wkb, n0 + wn * 32);
+    const bool warp_dead = g.c_lower && (n0 + wn * 32 > m0 + wm * 64 + 63);     // sub-tile strictly above the diagonal
 
     const bool vecA = ((g.lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool vecB = ((g.ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
@@ -158,47 +224,62 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_kernel(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // stage s: A tile at smem + s*STAGE, B tile at smem + s*STAGE + GBM*GLD
-    constexpr int STAGE = 2 * GBM * GLD;
-    double ra[8], rb[8];
-
-    if (nk > 0) {
-        load_tile<AL>(ra, A, g.lda, g.M, g.K, m0, kb, ke, vecA, tid);
-        load_tile<BL>(rb, B, g.ldb, g.N, g.K, n0, kb, ke, vecB, tid);
-        store_tile<AL>(ra, smem, tid);
-        store_tile<BL>(rb, smem + GBM * GLD, tid);
+    TileCopy<AL, GBM> cpA;
+    TileCopy<BL, GBN> cpB;
+    cpA.init(A, g.lda, m0, kb, tid);
+    cpB.init(B, g.ldb, n0, kb, tid);
+    const bool fastA = vecA && m0 + GBM <= g.M, fastB = vecB && n0 + GBN <= g.N;
+    auto load_ktile = [&](int t) {                 // k-tile t -> its ring slot
+        double* S = smem + (t % GSTAGES) * GSTAGE;
+        const bool k_inner = kb + (t + 1) * GBK <= ke;
+        if (fastA && k_inner) cpA.issue(S, t);
+        else issue_tile<AL, GBM>(S, A, g.lda, g.M, m0, kb + t * GBK, ke, vecA, tid);
+        if (fastB && k_inner) cpB.issue(S + GOPER_A, t);
+        else issue_tile<BL, GBN>(S + GOPER_A, B, g.ldb, g.N, n0, kb + t * GBK, ke, vecB, tid);
+    };
+    // prologue: GSTAGES-1 k-tiles in flight (one commit group per k-tile, empty groups keep the counting uniform)
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; ++s) {
+        if (s < nk) load_ktile(s);
+        cp_async_commit();
     }
-    __syncthreads();
 
     const int fr = lane >> 2, fc = lane & 3;
+    // fragment element (row r, k) of a tile: layout 0 -> r*GLD + k, layout 1 -> k*pitch + r
+    const int a_off = (AL == 0) ? (wm * 64 + fr) * GLD + fc : fc * GLDT_A + wm * 64 + fr;
+    const int b_off = (BL == 0) ? (wn * 32 + fr) * GLD + fc : fc * GLDT_B + wn * 32 + fr;
+    constexpr int A_RS = (AL == 0) ? 8 * GLD : 8, A_KS = (AL == 0) ? 4 : 4 * GLDT_A;
+    constexpr int B_RS = (BL == 0) ? 8 * GLD : 8, B_KS = (BL == 0) ? 4 : 4 * GLDT_B;
+
     for (int kt = 0; kt < nk; ++kt) {
-        const int cur = kt & 1;
-        if (kt + 1 < nk) {
-            load_tile<AL>(ra, A, g.lda, g.M, g.K, m0, kb + (kt + 1) * GBK, ke, vecA, tid);
-            load_tile<BL>(rb, B, g.ldb, g.N, g.K, n0, kb + (kt + 1) * GBK, ke, vecB, tid);
+        cp_async_wait<GSTAGES - 2>();          // k-tile kt has landed (for this thread's copies)
+        __syncthreads();                       // ... and for everyone's; everyone is also done with k-tile kt-1
+        {
+            const int nx = kt + GSTAGES - 1;   // refill the slot k-tile kt-1 occupied
+            if (nx < nk) load_ktile(nx);
+            cp_async_commit();
         }
-        const double* as = smem + cur * STAGE + (wm * 64 + fr) * GLD + fc;
-        const double* bs = smem + cur * STAGE + GBM * GLD + (wn * 32 + fr) * GLD + fc;
+        const int k0 = kb + kt * GBK;
+        if (warp_dead || k0 >= wke || k0 + GBK <= wkb) continue;
+        const double* as = smem + (kt % GSTAGES) * GSTAGE + a_off;
+        const double* bs = smem + (kt % GSTAGES) * GSTAGE + GOPER_A + b_off;
 #pragma unroll
         for (int k4 = 0; k4 < GBK / 4; ++k4) {
             double fa[8], fb[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) fa[i] = as[i * 8 * GLD + k4 * 4];
+            for (int i = 0; i < 8; ++i) fa[i] = as[i * A_RS + k4 * A_KS];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) fb[j] = bs[j * 8 * GLD + k4 * 4];
+            for (int j = 0; j < 4; ++j) fb[j] = bs[j * B_RS + k4 * B_KS];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
-        if (kt + 1 < nk) {
-            store_tile<AL>(ra, smem + (cur ^ 1) * STAGE, tid);
-            store_tile<BL>(rb, smem + (cur ^ 1) * STAGE + GBM * GLD, tid);
-        }
-        __syncthreads();
     }
+    cp_async_wait<0>();
 
     // epilogue: each lane owns C[row = fr][cols 2*fc, 2*fc+1] of every 8x8 tile
+    if (warp_dead) return;
     const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -233,10 +314,14 @@ inline int gemm_f64(const GemmArgs& g, cudaStream_t st) {
     if (grid.y > 65535) return set_error(-3, "too many column tiles");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_f64_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_f64_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_f64_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_f64_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        auto setup = [](const void* f) {
+            cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // room for GEMM_CTAS_PER_SM CTAs
+        };
+        setup((const void*)gemm_f64_kernel<0, 0>);
+        setup((const void*)gemm_f64_kernel<0, 1>);
+        setup((const void*)gemm_f64_kernel<1, 0>);
+        setup((const void*)gemm_f64_kernel<1, 1>);
         attr_set = true;
     }
     const bool timed = g_gemm_timer.enabled;

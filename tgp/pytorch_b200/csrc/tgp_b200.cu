@@ -13,16 +13,18 @@ long g_launch_count = 0;
 GemmTimer g_gemm_timer;
 namespace tc { int g_fused_forward = 0; }
 
-constexpr long ROW_CHUNK = 8192;     // rows whose K / Kbar tiles are staged at once (L2-sized for M = 1024)
+long g_row_chunk = 32768;             // rows per launch of the batch contractions (Kbar / Abar staging); measured at cfg4:
+                                      // 8192 -> 20.3 ms/step, 16384 -> 20.0, 32768 -> 19.6, 65536 -> 19.5
 
+// AB = [A | B] (R x 2M) and K (R x M) are kept from the forward for the backward; Kbar / Abar are per-chunk staging
 struct BatchView { double *AB, *Kbuf, *Kbar, *Abar; long Rc; };
 
-inline long chunk_rows(long R) { return R < ROW_CHUNK ? R : ROW_CHUNK; }
+inline long chunk_rows(long R) { return R < g_row_chunk ? R : g_row_chunk; }
 inline long even(long x) { return (x + 1) / 2 * 2; }
 
 inline size_t batch_ws_doubles(int M, long R) {
     const long Rc = chunk_rows(R);
-    return (size_t)even(R * 2 * M) + 3 * (size_t)even(Rc * M) + 16;
+    return (size_t)even(R * 2 * M) + (size_t)even(R * M) + 2 * (size_t)even(Rc * M) + 16;
 }
 
 inline BatchView carve_batch(void* ws, int M, long R) {
@@ -30,7 +32,7 @@ inline BatchView carve_batch(void* ws, int M, long R) {
     b.Rc = chunk_rows(R);
     double* p = reinterpret_cast<double*>(ws);
     b.AB = p; p += even(R * 2 * M);
-    b.Kbuf = p; p += even(b.Rc * M);
+    b.Kbuf = p; p += even(R * M);
     b.Kbar = p; p += even(b.Rc * M);
     b.Abar = p;
     return b;
@@ -73,10 +75,9 @@ inline void fill_flow(FlowDesc& fd, const TgpModel* md) {
 // The weight-gradient GEMMs have only (M/128)^2 output tiles but a reduction over thousands of rows: split the
 // reduction so that the live CTAs fill whole waves of the 148 SMs (36 lower tiles x 4 splits = 144 CTAs at M = 1024).
 inline int weight_splitk(int M, int rc, bool lower) {
-    const long T = cdiv(M, GBM);
-    const long tiles = lower ? T * (T + 1) / 2 : T * T;
+    const long tiles = gemm_tiles(M, M, lower);
     const long max_split = rc / (8 * GBK) > 0 ? rc / (8 * GBK) : 1;
-    auto util = [&](long s) { const long c = tiles * s; return (double)c / (double)(cdiv(c, 148) * 148); };
+    auto util = [&](long s) { const long c = tiles * s; return (double)c / (double)(cdiv(c, GEMM_SLOTS) * GEMM_SLOTS); };
     double best_util = 0.0;
     for (long s = 1; s <= max_split && s <= 64; ++s) best_util = util(s) > best_util ? util(s) : best_util;
     int best = 1;
@@ -88,9 +89,8 @@ inline int weight_splitk(int M, int rc, bool lower) {
 // M x M x M products of the per-step chain have only (M/128)^2 output tiles: split their reduction (FP64 atomics into a
 // zeroed output) so that one launch fills the SMs instead of running 36-64 long CTAs.
 inline int gemm_small(GemmArgs g, cudaStream_t st) {
-    const long Tm = cdiv(g.M, GBM), Tn = cdiv(g.N, GBN);
-    const long tiles = g.c_lower ? Tm * (Tm + 1) / 2 : Tm * Tn;
-    long split = tiles > 0 ? (148 + tiles - 1) / tiles : 1;
+    const long tiles = gemm_tiles(g.M, g.N, g.c_lower != 0);
+    long split = tiles > 0 ? (GEMM_SLOTS + tiles - 1) / tiles : 1;
     const long max_split = g.K / (4 * GBK) > 0 ? g.K / (4 * GBK) : 1;
     if (split > max_split) split = max_split;
     if (split > 1 && g.batch == 1) {
@@ -160,9 +160,10 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
     const double* Xd = (const double*)X;
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
-        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf, M, rc, M, 0.0, st));
+        double* Kc = b.Kbuf + r0 * M;
+        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
         // A = K L^-T   (Bop[n,k] = Linv[n,k], nonzero k <= n)
-        GemmArgs ga = make_gemm(rc, M, M, b.Kbuf, M, 0, s.Linv, s.Mp, 0, b.AB + r0 * 2 * M, 2 * M);
+        GemmArgs ga = make_gemm(rc, M, M, Kc, M, 0, s.Linv, s.Mp, 0, b.AB + r0 * 2 * M, 2 * M);
         ga.b_tri = 1;
         ga.tag = 1;
         TGP_TRY(gemm_f64(ga, st));
@@ -235,15 +236,15 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
         GemmArgs g0 = make_gemm(rc, M, M, ABc + M, 2 * M, 0, s.LS, s.Mp, 0, b.Abar, M, 1.0, 1.0);
         g0.b_tri = 1; g0.tag = 1;
         TGP_TRY(gemm_f64(g0, st));
-        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf, M, rc, M, 0.0, st));
+        const double* Kc = b.Kbuf + r0 * M;          // K_xz of these rows, kept by the forward
         // Kbar = Abar * Linv     (Bop[n,k] = Linv[k,n], nonzero k >= n)
         GemmArgs g1 = make_gemm(rc, M, M, b.Abar, M, 0, s.Linv, s.Mp, 1, b.Kbar, M);
         g1.b_tri = 2; g1.tag = 1;
         TGP_TRY(gemm_f64(g1, st));
         TGP_TRY(launch_kernel_grads(b.Kbar, M, Xd + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, reduce_buf + l.dZ,
-                                    reduce_buf + l.dls, reduce_buf + l.dos, st));
+                                    reduce_buf + l.dls, reduce_buf + l.dos, st, Kc, M));
         // Gbar += tril(Abar^T K)      (reduction over the rows of the chunk)
-        GemmArgs g3 = make_gemm(M, M, rc, b.Abar, M, 1, b.Kbuf, M, 1, Gbar, s.Mp, 1.0, 1.0);
+        GemmArgs g3 = make_gemm(M, M, rc, b.Abar, M, 1, Kc, M, 1, Gbar, s.Mp, 1.0, 1.0);
         g3.c_lower = 1; g3.splitk = weight_splitk(M, rc, true); g3.tag = 1;
         TGP_TRY(gemm_f64(g3, st));
         // dL_S += tril(A^T Bbar)
@@ -358,6 +359,11 @@ long tgp_launch_count(void) { return g_launch_count; }
 
 int tgp_set_option(int key, int value) {
     if (key == TGP_OPT_FUSED_FORWARD) { tc::g_fused_forward = value != 0; return 0; }
+    if (key == TGP_OPT_ROW_CHUNK) {
+        if (value < 128) return set_error(-1, "row chunk must be >= 128");
+        g_row_chunk = value;
+        return 0;
+    }
     return set_error(-1, "unknown option");
 }
 
