@@ -224,6 +224,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_f64_kerne
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // beta * C enters through the accumulators: the read of C is issued before the k-loop and hidden behind it, instead
+    // of a dependent read-modify-write at the very end of the CTA
+    const int fr = lane >> 2, fc = lane & 3;
+    const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool beta_early = g.beta != 0.0 && g.splitk <= 1 && g.alpha != 0.0 && !warp_dead;
+    if (beta_early) {
+        const double sc = g.beta / g.alpha;
+        if (vecC && m0 + GBM <= g.M && n0 + GBN <= g.N) {
+            // interior tile: 32 independent, unconditional 16-byte loads in flight at once (elements above the diagonal of
+            // a lower-only output are read and masked — they exist in memory, they are just never written)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 o = *reinterpret_cast<const double2*>(C + (long)(m0 + wm * 64 + i * 8 + fr) * g.ldc + n0 + wn * 32 + j * 8 + 2 * fc);
+                    acc[i][j][0] = o.x; acc[i][j][1] = o.y;
+                }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + wm * 64 + i * 8 + fr, n = n0 + wn * 32 + j * 8 + 2 * fc;
+                    acc[i][j][0] = (!g.c_lower || n <= m) ? sc * acc[i][j][0] : 0.0;
+                    acc[i][j][1] = (!g.c_lower || n + 1 <= m) ? sc * acc[i][j][1] : 0.0;
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + wm * 64 + i * 8 + fr;
+                if (m >= g.M) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = n0 + wn * 32 + j * 8 + 2 * fc;
+                    if (n >= g.N) continue;
+                    const double* cp = C + (long)m * g.ldc + n;
+                    if (!g.c_lower || n <= m) acc[i][j][0] = sc * cp[0];
+                    if ((n + 1 < g.N) && (!g.c_lower || n + 1 <= m)) acc[i][j][1] = sc * cp[1];
+                }
+            }
+        }
+    }
+
     TileCopy<AL, GBM> cpA;
     TileCopy<BL, GBN> cpB;
     cpA.init(A, g.lda, m0, kb, tid);
@@ -244,7 +286,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_f64_kerne
         cp_async_commit();
     }
 
-    const int fr = lane >> 2, fc = lane & 3;
     // fragment element (row r, k) of a tile: layout 0 -> r*GLD + k, layout 1 -> k*pitch + r
     const int a_off = (AL == 0) ? (wm * 64 + fr) * GLD + fc : fc * GLDT_A + wm * 64 + fr;
     const int b_off = (BL == 0) ? (wn * 32 + fr) * GLD + fc : fc * GLDT_B + wn * 32 + fr;
@@ -280,7 +321,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_f64_kerne
 
     // epilogue: each lane owns C[row = fr][cols 2*fc, 2*fc+1] of every 8x8 tile
     if (warp_dead) return;
-    const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const double beta = beta_early ? 0.0 : g.beta;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + wm * 64 + i * 8 + fr;
@@ -297,11 +338,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_f64_kerne
                 if (ok0) atomicAdd(cp, v0);
                 if (ok1) atomicAdd(cp + 1, v1);
             } else if (ok0 && ok1 && vecC) {
-                if (g.beta != 0.0) { double2 o = *reinterpret_cast<double2*>(cp); v0 += g.beta * o.x; v1 += g.beta * o.y; }
+                if (beta != 0.0) { double2 o = *reinterpret_cast<double2*>(cp); v0 += beta * o.x; v1 += beta * o.y; }
                 *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
             } else {
-                if (ok0) { if (g.beta != 0.0) v0 += g.beta * cp[0]; cp[0] = v0; }
-                if (ok1) { if (g.beta != 0.0) v1 += g.beta * cp[1]; cp[1] = v1; }
+                if (ok0) { if (beta != 0.0) v0 += beta * cp[0]; cp[0] = v0; }
+                if (ok1) { if (beta != 0.0) v1 += beta * cp[1]; cp[1] = v1; }
             }
         }
     }

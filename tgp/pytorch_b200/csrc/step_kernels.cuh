@@ -81,10 +81,14 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
 // status[0] = 1-based index of the first non-positive / NaN pivot (0 = ok); only the first failure is recorded.
 //
 // One CTA on the critical path of the factorisation, written for latency with compact loops (a fully unrolled
-// register version is instruction-fetch bound): 256 threads = 64 rows x 4 column phases.  The trailing update works on
-// the UNSCALED columns, a[t][k] -= a[t][j] * a[k][j] / d_j, so a column never has to be rescaled in place between two
-// barriers (two barriers per column); the scaling by 1/sqrt(d_j) is applied once at the end.
-constexpr int POTRF_THREADS = 1024;        // 64 rows x 16 column phases
+// register version is instruction-fetch bound): 1024 threads = 64 rows x 16 column phases.  The trailing update works on
+// the UNSCALED columns, a[t][k] -= a[t][j] * a[k][j] / d_j, so a column never has to be rescaled in place (one barrier
+// per column); the scaling by 1/sqrt(d_j) is applied once at the end.  The inverse of the block comes out of the same
+// loop (Gauss-Jordan on an identity), not from a second, 64-step substitution.
+#ifndef TGP_POTRF_THREADS
+#define TGP_POTRF_THREADS 1024
+#endif
+constexpr int POTRF_THREADS = TGP_POTRF_THREADS;        // 64 rows x 16 column phases
 __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
                                                               double* __restrict__ Linv, double* __restrict__ Dinv,
                                                               int kb, long ld, const double* __restrict__ os,
@@ -95,58 +99,55 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(const double* __re
     // deterministically instead of depending on the sign of a 1e-16 rounding residue
     const double pivot_floor = 8.0 * 2.220446049250313e-16 * os[0];
     extern __shared__ double sm_potrf[];
-    double* a = sm_potrf;                  // [NB][LDS] working block, later L
-    double* inv = a + NB * LDS;            // [NB][LDS] L^-1
-    double* rs = inv + NB * LDS;           // [NB] 1 / sqrt(d_j)
+    double* a = sm_potrf;                  // [NB][LDS] working block (unscaled columns)
+    double* w = a + NB * LDS;              // [NB][LDS] the same row operations applied to I: inverse of the unit-lower factor
+    double* rs = w + NB * LDS;             // [NB] 1 / sqrt(d_j)
     double* rd = rs + NB;                  // [NB] 1 / d_j
     const int tid = threadIdx.x, t = tid & 63, q = tid >> 6;
     const long base = (long)kb * NB * ld + (long)kb * NB;
     for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, c = i & 63;
         a[r * LDS + c] = (c <= r) ? Aw[base + (long)r * ld + c] : 0.0;
-        inv[r * LDS + c] = 0.0;
+        w[r * LDS + c] = (c == r) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // One barrier per column.  Step j eliminates column j from the rows below it, row_t -= (a[t][j] / d_j) * row_j, on the
+    // lower triangle of A (row_j read through symmetry as column j) and on W; everything step j reads (1 / d_j, column j
+    // of A, row j of W) was finalised by step j-1 and is not written in step j.  The one thread that finalises the next
+    // pivot a[j+1][j+1] also checks it and publishes its reciprocal, so the division is off the other 31 warps' pipes.
+    if (tid == 0) {
+        const double d = a[0];
+        if (!(d > pivot_floor)) atomicCAS(status, 0, kb * NB + 1);
+        rd[0] = 1.0 / d;
     }
     __syncthreads();
     for (int j = 0; j < NB; ++j) {
-        if (tid == 0) {
-            const double d = a[j * LDS + j];
-            if (!(d > pivot_floor)) atomicCAS(status, 0, kb * NB + j + 1);
-            const double r = rsqrt(d);
-            rs[j] = r;
-            rd[j] = r * r;
-        }
-        __syncthreads();
         if (t > j) {
             const double f = a[t * LDS + j] * rd[j];
 #pragma unroll 4
-            for (int k = j + 1 + q; k <= t; k += PH) a[t * LDS + k] = fma(-f, a[k * LDS + j], a[t * LDS + k]);
+            for (int k = j + 1 + q; k <= t; k += PH) {
+                const double nv = fma(-f, a[k * LDS + j], a[t * LDS + k]);
+                a[t * LDS + k] = nv;
+                if (k == j + 1 && t == j + 1) {              // thread (t = j+1, q = 0): the next pivot is final
+                    if (!(nv > pivot_floor)) atomicCAS(status, 0, kb * NB + j + 2);
+                    rd[j + 1] = 1.0 / nv;
+                }
+            }
+#pragma unroll 4
+            for (int k = q; k <= j; k += PH) w[t * LDS + k] = fma(-f, w[j * LDS + k], w[t * LDS + k]);
         }
         __syncthreads();
     }
-    // scale: L[t][c] = a[t][c] / sqrt(d_c) below the diagonal, d_t / sqrt(d_t) on it
+    if (tid < NB) rs[tid] = rsqrt(a[tid * LDS + tid]);
+    __syncthreads();
+    // A = Lu D Lu^T with Lu unit lower, a[t][c] = Lu[t][c] d_c, W = Lu^-1:   L = Lu D^1/2,   L^-1 = D^-1/2 W
     for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, c = i & 63;
-        a[r * LDS + c] = c <= r ? a[r * LDS + c] * rs[c] : 0.0;
-    }
-    __syncthreads();
-    // inverse by forward substitution, row by row; thread (c, p) sums k == c + p (mod 16) for column c;
-    // 1 / L_ii = rs[i] is already known
-    const int c = tid >> 4, p = tid & 15;
-    for (int i = 0; i < NB; ++i) {
-        double s = 0.0;
-        if (c <= i) for (int k = c + p; k < i; k += 16) s = fma(a[i * LDS + k], inv[k * LDS + c], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        if (p == 0 && c <= i) inv[i * LDS + c] = ((i == c ? 1.0 : 0.0) - s) * rs[i];
-        __syncthreads();
-    }
-    for (int i = tid; i < NB * NB; i += NT) {
-        const int r = i >> 6, cc = i & 63;
-        Lout[base + (long)r * ld + cc] = a[r * LDS + cc];
-        Linv[base + (long)r * ld + cc] = inv[r * LDS + cc];
-        Dinv[i] = inv[r * LDS + cc];
+        const double l = c <= r ? a[r * LDS + c] * rs[c] : 0.0;
+        const double li = c <= r ? w[r * LDS + c] * rs[r] : 0.0;
+        Lout[base + (long)r * ld + c] = l;
+        Linv[base + (long)r * ld + c] = li;
+        Dinv[i] = li;
     }
 }
 

@@ -1,4 +1,5 @@
 // C-ABI entry points (include/tgp_b200.h) — host-side orchestration of the sm_100a kernels.
+#include <cstdlib>
 #include "../../../include/tgp_b200.h"
 #include "common.cuh"
 #include "gemm_f64.cuh"
