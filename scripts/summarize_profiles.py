@@ -19,11 +19,14 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 
 def launches(src, dst):
     lines = [l for l in open(src) if not l.startswith('==')]
-    rows = list(csv.DictReader(io.StringIO(''.join(lines))))
+    while lines and not lines[0].startswith('"ID"'):
+        lines.pop(0)
+    rows = [r for r in csv.DictReader(io.StringIO(''.join(lines))) if r['Metric Name'] == 'gpu__time_duration.sum']
     names = [r['Kernel Name'] for r in rows]
     marks = [i for i, n in enumerate(names) if 'k_transform_params' in n]
     # a bench step = [k_transform_params .. next k_transform_params); take the last complete device-arm step
-    s, e = marks[-3], marks[-2]
+    # (scripts/one_step.py runs exactly two steps: take the first, complete one)
+    s, e = (marks[-3], marks[-2]) if len(marks) >= 3 else (marks[0], marks[1])
     agg, tot = collections.OrderedDict(), 0.0
     for r in rows[s:e]:
         t = float(r['Metric Value'].replace(',', '')) / 1e6

@@ -71,6 +71,7 @@ constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 4, GEMM_CTAS_PER_SM = 1;
 #else
 constexpr int GBM = 128, GBN = 64, GBK = 16, GSTAGES = 3, GEMM_CTAS_PER_SM = 2;
 #endif
+constexpr int GEMM_GROUP_M = 32;     // m-tiles per rasterisation group
 constexpr int GWARPS_N = GBN / 32;
 constexpr int GEMM_THREADS = 32 * 2 * GWARPS_N;
 constexpr int GEMM_SLOTS = 148 * GEMM_CTAS_PER_SM;      // co-resident CTAs on a B200
@@ -172,18 +173,29 @@ template <int AL, int BL>
 __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_f64_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Rasterisation: CTAs are dealt in groups of GEMM_GROUP_M m-tiles x all n-tiles, m fastest inside a group (co-resident
+    // CTAs share the B tile; the A rows of a group, <= 4096 x K doubles, are read from HBM once and served to the other
+    // n-tiles by L2).  n-tiles are visited heaviest-first when the triangular clipping makes their k-extent grow with n
+    // (b_tri == 1), so that the last wave holds the light tiles.
+    int mt, nt;
+    {
+        const int Tm = (int)gridDim.x, Tn = (int)gridDim.y;
+        const int lin = (int)blockIdx.y * Tm + (int)blockIdx.x;
+        const int grp = lin / (GEMM_GROUP_M * Tn), within = lin - grp * GEMM_GROUP_M * Tn;
+        const int g_rows = min(GEMM_GROUP_M, Tm - grp * GEMM_GROUP_M);
+        nt = within / g_rows;
+        mt = grp * GEMM_GROUP_M + (within - nt * g_rows);
+    }
+    if (g.b_tri == 1) nt = (int)gridDim.y - 1 - nt;
+    const int m0 = mt * GBM, n0 = nt * GBN;
     // warp grid 2 (m) x GWARPS_N (n).  Warps that share a scheduler get complementary n-positions, so that the per-warp
     // triangular clipping below removes the same amount of work from every scheduler: in the 8-warp shape warp and
     // warp + 4 take n-quarters q and 3 - q; in the 4-warp shape neighbouring m-tiles (co-resident CTAs) swap halves.
 #ifdef TGP_GEMM_WIDE
     const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
 #else
-    const int wm = warp >> 1, wn = (warp & 1) ^ (blockIdx.x & 1);
+    const int wm = warp >> 1, wn = (warp & 1) ^ (mt & 1);
 #endif
-    // m-tiles vary fastest (CTAs that are co-resident share the B tile); n-tiles are visited heaviest-first when the
-    // triangular clipping makes their k-extent grow with n (b_tri == 1), so that the last wave holds the light tiles
-    const int nt = (g.b_tri == 1) ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
-    const int m0 = blockIdx.x * GBM, n0 = nt * GBN;
     if (g.c_lower && n0 > m0 + GBM - 1) return;
 
     const int zb = g.splitk > 1 ? 0 : blockIdx.z;
