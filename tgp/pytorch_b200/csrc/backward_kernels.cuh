@@ -72,35 +72,51 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
     const double s = os[0];
     AccT asum = 0;
     if (j < M) {
-        for (long n = n0 + ry; n < n1; n += KG_TR) {
-            const int r = (int)(n - n0);
-            double kb = (double)Kbar[n * ldk + j];
-            if (sym) kb = 0.5 * (kb + (double)Kbar[(long)j * ldk + n]);
-            if constexpr (std::is_same<KBT, float>::value) {
-                float df[MAXD];
-                float q = 0.f;
+        // FP64 mode: four rows per iteration, their Kbar / K loads issued together (the kernel is load-latency bound
+        // otherwise); the FP32 variant recomputes the exponential and is ALU-bound, it keeps one row per iteration
+        constexpr int UR = std::is_same<KBT, float>::value ? 1 : 4;
+        for (long nb = n0 + ry; nb < n1; nb += UR * KG_TR) {
+            double kbr[UR], kvr[UR];
 #pragma unroll
-                for (int d = 0; d < MAXD; ++d) if (d < D) { df[d] = (float)(xs[r][d] - zj[d]); q = fmaf(df[d], df[d], q); }
-                const float t = (float)kb * (float)s * expf(-0.5f * q);
-                asum += t;
+            for (int u = 0; u < UR; ++u) {
+                const long n = nb + u * KG_TR;
+                const bool ok = n < n1;
+                kbr[u] = ok ? (double)Kbar[n * ldk + j] : 0.0;
+                if (sym && ok) kbr[u] = 0.5 * (kbr[u] + (double)Kbar[(long)j * ldk + n]);
+                kvr[u] = (Kval && ok) ? Kval[n * ldkv + j] : 0.0;
+            }
 #pragma unroll
-                for (int d = 0; d < MAXD; ++d) if (d < D) { az[d] = fmaf(t, df[d], az[d]); al[d] = fmaf(t * df[d], df[d], al[d]); }
-            } else {
-                double t;
-                if (Kval) {                  // the forward's K tile is still resident: no distance / exponential needed
-                    t = kb * Kval[n * ldkv + j];
+            for (int u = 0; u < UR; ++u) {
+                const long n = nb + u * KG_TR;
+                if (n >= n1) break;
+                const int r = (int)(n - n0);
+                const double kb = kbr[u];
+                if constexpr (std::is_same<KBT, float>::value) {
+                    float df[MAXD];
+                    float q = 0.f;
+#pragma unroll
+                    for (int d = 0; d < MAXD; ++d) if (d < D) { df[d] = (float)(xs[r][d] - zj[d]); q = fmaf(df[d], df[d], q); }
+                    const float t = (float)kb * (float)s * expf(-0.5f * q);
+                    asum += t;
+#pragma unroll
+                    for (int d = 0; d < MAXD; ++d) if (d < D) { az[d] = fmaf(t, df[d], az[d]); al[d] = fmaf(t * df[d], df[d], al[d]); }
                 } else {
-                    double q = 0.0;
+                    double t;
+                    if (Kval) {                  // the forward's K tile is still resident: no distance / exponential needed
+                        t = kb * kvr[u];
+                    } else {
+                        double q = 0.0;
 #pragma unroll
-                    for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
-                    t = kb * s * exp(-0.5 * q);
-                }
-                asum += t;
+                        for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = xs[r][d] - zj[d]; q = fma(df, df, q); }
+                        t = kb * s * exp(-0.5 * q);
+                    }
+                    asum += t;
 #pragma unroll
-                for (int d = 0; d < MAXD; ++d) if (d < D) {
-                    const double df = xs[r][d] - zj[d];
-                    az[d] = fma(t, df, az[d]);
-                    al[d] = fma(t * df, df, al[d]);
+                    for (int d = 0; d < MAXD; ++d) if (d < D) {
+                        const double df = xs[r][d] - zj[d];
+                        az[d] = fma(t, df, az[d]);
+                        al[d] = fma(t * df, df, al[d]);
+                    }
                 }
             }
         }

@@ -51,30 +51,73 @@ __device__ __forceinline__ double flow_param(const TgpFlowLayer& L, int idx, con
     return (L.flags & TGP_FLOW_PER_ROW) ? rowp[L.p0 + idx] : theta[L.p0 + idx];
 }
 
+__device__ __forceinline__ int layer_nparams(const TgpFlowLayer& L);
+
+// Node-independent transforms of the GLOBAL flow parameters, hoisted out of the (rows x quadrature nodes) loop: for every
+// parameter slot s (layer-major, descriptor order) prep[2s] = the value the forward uses (softplus where restricted,
+// 1/softplus(d) for the tanh width), prep[2s+1] = d(value)/d(raw) (sigmoid where restricted, else 1).  Per-row
+// (input-dependent) parameters are not prepared; flow_forward transforms those per row.
+constexpr int FLOW_PREP_DOUBLES = 2 * (MAX_THETA + MAX_ROWP);
+__device__ __forceinline__ void flow_prepare(const FlowDesc& fd, const double* __restrict__ theta, double* prep) {
+    int total = 0;
+    for (int l = 0; l < fd.n_layers; ++l) total += layer_nparams(fd.layers[l]);
+    for (int s = threadIdx.x; s < total; s += blockDim.x) {
+        int l = 0, base = 0;
+        while (s >= base + layer_nparams(fd.layers[l])) { base += layer_nparams(fd.layers[l]); ++l; }
+        const TgpFlowLayer& L = fd.layers[l];
+        if (L.flags & TGP_FLOW_PER_ROW) continue;
+        const int idx = s - base;
+        const double raw = theta[L.p0 + idx];
+        double v0 = raw, v1 = 1.0;
+        const bool res = L.flags & TGP_FLOW_RESTRICT;
+        if (L.kind == TGP_FLOW_AFFINE) {
+            if (idx == 0 && res) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
+        } else if (L.kind == TGP_FLOW_TANH_STEP) {
+            const int w = idx & 3;
+            if (w == 1) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
+            else if (w == 3) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
+        } else if (L.kind == TGP_FLOW_SAL) {
+            if (idx == 1 && res) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
+        }
+        prep[2 * s] = v0; prep[2 * s + 1] = v1;
+    }
+    __syncthreads();
+}
+
 // Forward through all layers.  Returns G(f); *dG = G'(f).  If pg != nullptr, stores for every parameter slot k
 // (layer-major, in descriptor order) dG_l/dtheta_k at this location into pg[], and the layer derivatives into dl[].
+// prep: the table flow_prepare filled (shared memory).
 __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, const double* __restrict__ theta,
-                                               const double* __restrict__ rowp, double* dG, double* pg, double* dl) {
+                                               const double* __restrict__ rowp, double* dG, double* pg, double* dl,
+                                               const double* prep) {
     double dtot = 1.0;
     int slot = 0;
     for (int l = 0; l < fd.n_layers; ++l) {
         const TgpFlowLayer& L = fd.layers[l];
-        double g, d;
+        const bool per_row = L.flags & TGP_FLOW_PER_ROW;
+        const bool res = L.flags & TGP_FLOW_RESTRICT;
+        // transformed value / chain factor of parameter idx (restricted = through softplus)
+        auto val = [&](int idx, bool restricted, double& chain) -> double {
+            if (!per_row) { chain = prep[2 * (slot + idx) + 1]; return prep[2 * (slot + idx)]; }
+            const double raw = rowp[L.p0 + idx];
+            if (restricted) { chain = sigmoid_d(raw); return softplus_d(raw); }
+            chain = 1.0;
+            return raw;
+        };
+        double g, d, ch0, ch1;
         if (L.kind == TGP_FLOW_AFFINE) {
-            const double a_raw = flow_param(L, 0, theta, rowp), b = flow_param(L, 1, theta, rowp);
-            const bool res = L.flags & TGP_FLOW_RESTRICT;
-            const double a = res ? softplus_d(a_raw) : a_raw;
+            const double a = val(0, res, ch0), b = val(1, false, ch1);
             g = a * f + b;
             d = a;
-            if (pg) { pg[slot] = res ? f * sigmoid_d(a_raw) : f; pg[slot + 1] = 1.0; }
+            if (pg) { pg[slot] = f * ch0; pg[slot + 1] = 1.0; }
             slot += 2;
         } else if (L.kind == TGP_FLOW_TANH_STEP) {
             double acc = 0.0;
             d = 0.0;
             for (int i = 0; i < L.n_steps; ++i) {
-                const double a = flow_param(L, 4 * i, theta, rowp), b_raw = flow_param(L, 4 * i + 1, theta, rowp);
-                const double c = flow_param(L, 4 * i + 2, theta, rowp), d_raw = flow_param(L, 4 * i + 3, theta, rowp);
-                const double be = softplus_d(b_raw), de = softplus_d(d_raw);
+                double chb, chd;
+                const double a = val(4 * i, false, ch0), be = val(4 * i + 1, true, chb);
+                const double c = val(4 * i + 2, false, ch0), de = val(4 * i + 3, true, chd);
                 const double u = (f - c) / de;
                 const double th = tanh(u);
                 const double sech2 = 1.0 - th * th;
@@ -83,25 +126,23 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
                 d += slope;
                 if (pg) {
                     pg[slot + 4 * i] = 1.0;
-                    pg[slot + 4 * i + 1] = th * sigmoid_d(b_raw);
+                    pg[slot + 4 * i + 1] = th * chb;
                     pg[slot + 4 * i + 2] = -slope;
-                    pg[slot + 4 * i + 3] = -slope * u * sigmoid_d(d_raw);
+                    pg[slot + 4 * i + 3] = -slope * u * chd;
                 }
             }
             slot += 4 * L.n_steps;
             g = acc;
             if (L.flags & TGP_FLOW_ADD_F0) { g += f; d += 1.0; }
         } else if (L.kind == TGP_FLOW_SAL) {
-            const double a = flow_param(L, 0, theta, rowp), b_raw = flow_param(L, 1, theta, rowp);
-            const bool res = L.flags & TGP_FLOW_RESTRICT;
-            const double b = res ? softplus_d(b_raw) : b_raw;
+            const double a = val(0, false, ch0), b = val(1, res, ch1);
             const double r = sqrt(f * f + 1.0);
             const double w = log(f + r);                 // the reference's asinh (flow.py:904-905)
             const double z = b * w - a;
             const double ch = cosh(z);
             g = sinh(z);
             d = ch * b * ((1.0 + f / r) / (f + r));      // derivative of log(f + sqrt(f^2+1)) as autograd forms it
-            if (pg) { pg[slot] = -ch; pg[slot + 1] = ch * w * (res ? sigmoid_d(b_raw) : 1.0); }
+            if (pg) { pg[slot] = -ch; pg[slot + 1] = ch * w * ch1; }
             slot += 2;
             if (L.flags & TGP_FLOW_ADD_F0) { g += f; d += 1.0; }
         } else {   // identity
@@ -135,6 +176,8 @@ struct RowQuadArgs {
 // Expected log-likelihood per row + gradients w.r.t. (mu, v, log_var_noise, flow parameters).
 __global__ void __launch_bounds__(ROW_THREADS) k_row_quad(const RowQuadArgs a) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    __shared__ double prep[FLOW_PREP_DOUBLES];
+    flow_prepare(a.flow, a.theta, prep);
     double acc_theta[MAX_THETA];
     double pg[MAX_THETA + MAX_ROWP];
     double dl[TGP_MAX_LAYERS];
@@ -170,7 +213,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_row_quad(const RowQuadArgs a) {
                 const double t = a.qt[s], cw = a.qw[s] * INV_SQRT_PI;
                 const double f = sd2 * t + mu;
                 double dG;
-                const double g = flow_forward(a.flow, f, a.theta, rowp, &dG, grad ? pg : nullptr, grad ? dl : nullptr);
+                const double g = flow_forward(a.flow, f, a.theta, rowp, &dG, grad ? pg : nullptr, grad ? dl : nullptr, prep);
                 double h, hg;
                 if (a.likelihood == TGP_LIK_GAUSS_NONLINEAR) {
                     const double q = y * inv * y - 2.0 * (y * inv * g) + g * inv * g;     // utils.py:191
@@ -253,6 +296,8 @@ struct RowTestArgs {
 // reference's float32 arithmetic.
 __global__ void __launch_bounds__(ROW_THREADS) k_row_test(const RowTestArgs a) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    __shared__ double prep[FLOW_PREP_DOUBLES];
+    flow_prepare(a.flow, a.theta, prep);
     const double var = a.likelihood == TGP_LIK_BERNOULLI ? 1.0 : exp(a.log_var_noise[0]);
     const double NEG_INF = -INFINITY;
     for (long n = (long)blockIdx.x * wpb + wid; n < a.R; n += (long)gridDim.x * wpb) {
@@ -279,7 +324,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_row_test(const RowTestArgs a) {
                 for (int s = lane; s < a.n_quad; s += 32) {
                     double dG;
                     const double g = flow_forward(a.flow, sd2 * a.qt[s] + mu, a.theta,
-                                                  a.rowp ? a.rowp + n * a.n_rowp : nullptr, &dG, nullptr, nullptr);
+                                                  a.rowp ? a.rowp + n * a.n_rowp : nullptr, &dG, nullptr, nullptr, prep);
                     acc += INV_SQRT_PI * (norm_cdf_ref(g) * a.qw[s]);
                 }
                 P = fmin(fmax(warp_sum(acc), 0.0), 1.0);
@@ -300,13 +345,13 @@ __global__ void __launch_bounds__(ROW_THREADS) k_row_test(const RowTestArgs a) {
             for (int s = lane; s < a.n_quad; s += 32) {
                 const double t = a.qt[s], w = a.qw[s];
                 double dG;
-                const double g = flow_forward(a.flow, sd2_t * t + mu, a.theta, rowp, &dG, nullptr, nullptr);
+                const double g = flow_forward(a.flow, sd2_t * t + mu, a.theta, rowp, &dG, nullptr, nullptr, prep);
                 const double mm = a.y_std * g;
                 const double lp = -0.5 * (LOG_2PI_F32PI + logC + (yy * ic * yy - 2.0 * (yy * ic * mm) + mm * ic * mm));
                 const double val = log(w) + lp;
                 if (val > mx) { sm = sm * exp(mx - val) + 1.0; mx = val; } else if (val > NEG_INF) { sm += exp(val - mx); }
                 const double gm = (sd2_m == sd2_t) ? g
-                                                   : flow_forward(a.flow, sd2_m * t + mu, a.theta, rowp, &dG, nullptr, nullptr);
+                                                   : flow_forward(a.flow, sd2_m * t + mu, a.theta, rowp, &dG, nullptr, nullptr, prep);
                 e1 += INV_SQRT_PI * (gm * w);
                 e2 += INV_SQRT_PI * (gm * gm * w);
             }
