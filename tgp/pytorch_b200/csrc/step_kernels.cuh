@@ -8,7 +8,7 @@
 namespace tgp {
 
 constexpr int POTRF_NB = 64;
-constexpr int POTRF_SMEM = (2 * POTRF_NB * (POTRF_NB + 1) + 2 * POTRF_NB) * (int)sizeof(double);
+constexpr int POTRF_SMEM = (2 * POTRF_NB * (POTRF_NB + 1) + 3 * POTRF_NB + 2) * (int)sizeof(double);
 
 // ls = softplus(raw_ls), os = softplus(raw_os), Zs = Z / ls      (gpytorch: x.div(lengthscale))
 __global__ void k_transform_params(const double* __restrict__ Z, const double* __restrict__ raw_ls,
@@ -80,74 +80,116 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
 // L_kk^-1 -> Dinv (dense 64x64, upper zero) and -> the diagonal block of Linv.
 // status[0] = 1-based index of the first non-positive / NaN pivot (0 = ok); only the first failure is recorded.
 //
-// One CTA on the critical path of the factorisation, written for latency with compact loops (a fully unrolled
-// register version is instruction-fetch bound): 1024 threads = 64 rows x 16 column phases.  The trailing update works on
-// the UNSCALED columns, a[t][k] -= a[t][j] * a[k][j] / d_j, so a column never has to be rescaled in place (one barrier
-// per column); the scaling by 1/sqrt(d_j) is applied once at the end.  The inverse of the block comes out of the same
-// loop (Gauss-Jordan on an identity), not from a second, 64-step substitution.
-#ifndef TGP_POTRF_THREADS
-#define TGP_POTRF_THREADS 1024
-#endif
-constexpr int POTRF_THREADS = TGP_POTRF_THREADS;        // 64 rows x 16 column phases
+// One CTA on the critical path of the factorisation, written for latency.  Gauss-Jordan on the UNSCALED block: step j
+// subtracts f_t = a[t][j] / d_j times row j from every row t > j, on the lower triangle of A (row j read through
+// symmetry as column j) and on an identity (which turns into W = Lu^-1, A = Lu D Lu^T).  Row t then always has exactly
+// t + 1 live entries, columns k <= j holding W[t][k] and columns k > j holding A[t][k]; so the assignment of entries to
+// threads is static — thread (t, q) keeps entries k = q, q+8, ..., q+56 of row t in REGISTERS for the whole
+// factorisation, and the only shared-memory traffic per step is the operand vector op[k] (= a[k][j] for k > j,
+// = w[j][k] for k < j: one array, one formula val -= f * op[k]) that the owners of column j+1 / row j+1 publish for the
+// next step.  The column loop is fully unrolled (entry indices, owner phases and buffer parities are compile-time
+// constants): one barrier and ~30 instructions per warp per column.  What is left is the dependent FP64 chain of a
+// column (f = a*rd, the update of the next pivot, its reciprocal by a hardware seed + two Newton steps): measured
+// 1.21-1.25 ms per M = 1024 factorisation with 256 / 512 / 1024 threads alike (it was 2.04 ms with a two-barrier
+// shared-memory version followed by a 64-step substitution for the inverse).
+constexpr int POTRF_THREADS = 512;         // 64 rows x 8 column phases, 8 register-resident entries per thread
+__device__ __forceinline__ double fast_rcp(double d) {   // reciprocal to ~1 ulp: hardware seed + two Newton steps
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    x = fma(x, fma(-d, x, 1.0), x);
+    x = fma(x, fma(-d, x, 1.0), x);
+    return x;
+}
 __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_diag(const double* __restrict__ Aw, double* __restrict__ Lout,
                                                               double* __restrict__ Linv, double* __restrict__ Dinv,
                                                               int kb, long ld, const double* __restrict__ os,
                                                               int* __restrict__ status) {
-    constexpr int NB = POTRF_NB, LDS = NB + 1, NT = POTRF_THREADS, PH = NT / NB;
+    constexpr int NB = POTRF_NB, LDS = NB + 1, NT = POTRF_THREADS, PH = NT / NB, NI = NB / PH;
     // a pivot that is not positive *to working precision* (relative to the kernel's diagonal k(z,z) = outputscale) counts
     // as a failed factorisation: exactly singular inputs (duplicated inducing rows) then take the jitter ladder
     // deterministically instead of depending on the sign of a 1e-16 rounding residue
     const double pivot_floor = 8.0 * 2.220446049250313e-16 * os[0];
     extern __shared__ double sm_potrf[];
-    double* a = sm_potrf;                  // [NB][LDS] working block (unscaled columns)
-    double* w = a + NB * LDS;              // [NB][LDS] the same row operations applied to I: inverse of the unit-lower factor
-    double* rs = w + NB * LDS;             // [NB] 1 / sqrt(d_j)
-    double* rd = rs + NB;                  // [NB] 1 / d_j
+    double* sa = sm_potrf;                 // [NB][LDS] staging: input block, later L
+    double* sw = sa + NB * LDS;            // [NB][LDS] staging: L^-1
+    double* op = sw + NB * LDS;            // [2][NB] operand vector of the current / next step
+    double* dd = op + 2 * NB;              // [NB] pivots d_j
+    double* rdv = dd + NB;                 // [2] 1 / d_j of the current / next step
     const int tid = threadIdx.x, t = tid & 63, q = tid >> 6;
     const long base = (long)kb * NB * ld + (long)kb * NB;
     for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, c = i & 63;
-        a[r * LDS + c] = (c <= r) ? Aw[base + (long)r * ld + c] : 0.0;
-        w[r * LDS + c] = (c == r) ? 1.0 : 0.0;
+        sa[r * LDS + c] = (c <= r) ? Aw[base + (long)r * ld + c] : 0.0;
     }
     __syncthreads();
-    // One barrier per column.  Step j eliminates column j from the rows below it, row_t -= (a[t][j] / d_j) * row_j, on the
-    // lower triangle of A (row_j read through symmetry as column j) and on W; everything step j reads (1 / d_j, column j
-    // of A, row j of W) was finalised by step j-1 and is not written in step j.  The one thread that finalises the next
-    // pivot a[j+1][j+1] also checks it and publishes its reciprocal, so the division is off the other 31 warps' pipes.
-    if (tid == 0) {
-        const double d = a[0];
-        if (!(d > pivot_floor)) atomicCAS(status, 0, kb * NB + 1);
-        rd[0] = 1.0 / d;
+    double val[NI], lsave[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { val[i] = sa[t * LDS + q + PH * i]; lsave[i] = 0.0; }
+    // Entries right of the diagonal (k > t) take part in the arithmetic but are never read: the loop body below has no
+    // per-entry branches at all (the kernel is bound by the instruction latency of one warp per column, not by work).
+    // Conventions that make this work: f = 0 for finished rows (t <= j); op[j] = 0 in step j, so that the entry that is
+    // about to change type is left alone by the generic update.
+    if (q == 0) {
+        op[t] = t == 0 ? 0.0 : val[0];           // operands of step 0: column 0 of A
+        if (t == 0) {
+            const double d = val[0];
+            if (!(d > pivot_floor)) atomicCAS(status, 0, kb * NB + 1);
+            dd[0] = d;
+            rdv[0] = fast_rcp(d);
+        }
     }
     __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        if (t > j) {
-            const double f = a[t * LDS + j] * rd[j];
-#pragma unroll 4
-            for (int k = j + 1 + q; k <= t; k += PH) {
-                const double nv = fma(-f, a[k * LDS + j], a[t * LDS + k]);
-                a[t * LDS + k] = nv;
-                if (k == j + 1 && t == j + 1) {              // thread (t = j+1, q = 0): the next pivot is final
-                    if (!(nv > pivot_floor)) atomicCAS(status, 0, kb * NB + j + 2);
-                    rd[j + 1] = 1.0 / nv;
+    // Fully unrolled over the 64 columns (j = PH*jo + ji): every entry index, owner phase and buffer parity is a
+    // compile-time constant, so a column costs one warp ~20 instructions.
+    const double* op_t = op + t;
+    const double* op_q = op + q;
+#pragma unroll
+    for (int jo = 0; jo < NI; ++jo) {
+#pragma unroll
+        for (int ji = 0; ji < PH; ++ji) {
+            const int j = PH * jo + ji;
+            const int cur = (j & 1) * NB, nxt = ((j + 1) & 1) * NB;
+            const double f = t > j ? op_t[cur] * rdv[j & 1] : 0.0;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) val[i] = fma(-f, op_q[cur + PH * i], val[i]);
+            if (q == ji && t > j) { lsave[jo] = val[jo]; val[jo] = -f; }     // a[t][j] is final; the entry becomes W[t][j]
+            if (j + 1 < NB) {
+                const int jn = j + 1, jno = jn / PH, jni = jn % PH;
+                if (q == jni) {                    // warp-uniform: owners of column j+1 publish it for the next step
+                    const double v = val[jno];
+                    if (t > jn) op[nxt + t] = v;
+                    else if (t == jn) {            // ... and its pivot
+                        if (!(v > pivot_floor)) atomicCAS(status, 0, kb * NB + jn + 1);
+                        dd[jn] = v;
+                        rdv[jn & 1] = fast_rcp(v);
+                        op[nxt + jn] = 0.0;
+                    }
+                }
+                if (t == jn) {                     // row j+1 of W (left of the diagonal) is final
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) if (q + PH * i <= j) op[nxt + q + PH * i] = val[i];
                 }
             }
-#pragma unroll 4
-            for (int k = q; k <= j; k += PH) w[t * LDS + k] = fma(-f, w[j * LDS + k], w[t * LDS + k]);
+            __syncthreads();
         }
-        __syncthreads();
     }
-    if (tid < NB) rs[tid] = rsqrt(a[tid * LDS + tid]);
+    // A = Lu D Lu^T with a[t][k] = Lu[t][k] d_k, W = Lu^-1:   L = Lu D^1/2,   L^-1 = D^-1/2 W
+    const double rst = rsqrt(dd[t]);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int k = q + PH * i;
+        double l = 0.0, li = 0.0;
+        if (k < t) { l = lsave[i] * rsqrt(dd[k]); li = val[i] * rst; }
+        else if (k == t) { l = val[i] * rst; li = rst; }
+        sa[t * LDS + k] = l;
+        sw[t * LDS + k] = li;
+    }
     __syncthreads();
-    // A = Lu D Lu^T with Lu unit lower, a[t][c] = Lu[t][c] d_c, W = Lu^-1:   L = Lu D^1/2,   L^-1 = D^-1/2 W
     for (int i = tid; i < NB * NB; i += NT) {
         const int r = i >> 6, c = i & 63;
-        const double l = c <= r ? a[r * LDS + c] * rs[c] : 0.0;
-        const double li = c <= r ? w[r * LDS + c] * rs[r] : 0.0;
-        Lout[base + (long)r * ld + c] = l;
-        Linv[base + (long)r * ld + c] = li;
-        Dinv[i] = li;
+        Lout[base + (long)r * ld + c] = sa[r * LDS + c];
+        Linv[base + (long)r * ld + c] = sw[r * LDS + c];
+        Dinv[i] = sw[r * LDS + c];
     }
 }
 
