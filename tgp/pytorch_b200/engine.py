@@ -159,6 +159,27 @@ class Engine:
                                         _ptr(self.status), _stream()), 'tgp_prepare')
         return self.kl, self.status
 
+    def status_reader(self):
+        """Starts the device->host copy of the 4-byte pivot status on a side stream that waits only for the work enqueued
+        SO FAR (call right after prepare()).  Returns a function that blocks until that copy has landed and yields the
+        status — by then the caller has enqueued the kernels that consume the factorisation, so the check does not
+        drain the compute stream."""
+        if getattr(self, '_status_host', None) is None:
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._status_stream = torch.cuda.Stream(device=self.device)
+            self._status_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        ready, landed = self._status_ev
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._status_stream):
+            self._status_stream.wait_event(ready)
+            self._status_host.copy_(self.status, non_blocking=True)
+            landed.record(self._status_stream)
+
+        def read():
+            landed.synchronize()
+            return int(self._status_host[0])
+        return read
+
     def qf_forward(self, X):
         R = X.shape[0]
         _chk(X, 'X', (R, self.D))

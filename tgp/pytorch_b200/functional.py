@@ -49,15 +49,18 @@ def prepare_then(engine, work, check=True, base_jitter=None):
     """Reference semantics of psd_safe_cholesky (code/dsp/utils.py:222-270): factorise without jitter; only on failure
     add 1e-8 * 10^i (FP64), i = 0..2, warning each time; raise after the third failure.
 
-    `work()` enqueues everything that consumes the factorisation.  The 4-byte pivot status is read back only AFTER that
-    work has been enqueued, so the (almost always successful) check costs no pipeline bubble; on failure the ladder
-    runs and `work()` is enqueued again on the jittered factor.  `check=False` skips the read-back altogether."""
+    `work()` enqueues everything that consumes the factorisation.  The 4-byte pivot status is copied to the host on a
+    side stream that waits for the factorisation only, and is read AFTER `work()` has been enqueued: the host blocks
+    ~1 ms (until the factorisation is done) while the compute stream still holds the whole forward, so the (almost
+    always successful) check costs no pipeline bubble; on failure the ladder runs and `work()` is enqueued again on the
+    jittered factor.  `check=False` skips the read-back altogether."""
     engine.prepared_key = None
     kl, status = engine.prepare(0.0)
-    out = work()
     if not check:
-        return kl, out
-    fail = int(status.item())
+        return kl, work()
+    read_status = engine.status_reader()        # D2H of the status on a side stream, ordered after prepare only
+    out = work()
+    fail = read_status()
     if fail == 0:
         return kl, out
     kl, _ = _jitter_ladder(engine, fail, base_jitter)
