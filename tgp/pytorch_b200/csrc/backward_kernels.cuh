@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
                                                              const double* __restrict__ os, long R, int M, int D, int sym,
                                                              double zscale, double* __restrict__ dZ,
                                                              double* __restrict__ dls, double* __restrict__ dos,
-                                                             const double* __restrict__ Kval, long ldkv) {
+                                                             const double* __restrict__ Kval, long ldkv,
+                                                             const float* __restrict__ Kfhi, const float* __restrict__ Kflo,
+                                                             long ldkf) {
     constexpr int KG_ROWS = kg_rows(MAXD);
     __shared__ double xs[KG_ROWS][MAXD + 1];
     __shared__ double red[KG_THREADS];
@@ -72,8 +74,8 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
     const double s = os[0];
     AccT asum = 0;
     if (j < M) {
-        // FP64 mode: four rows per iteration, their Kbar / K loads issued together (the kernel is load-latency bound
-        // otherwise); the FP32 variant recomputes the exponential and is ALU-bound, it keeps one row per iteration
+        // FP64 variant: four rows per iteration, their Kbar / K loads issued together (it is load-latency bound otherwise);
+        // the FP32 variant measured slower that way (4.54 vs 4.22 ms backward at cfg4) and keeps one row per iteration
         constexpr int UR = std::is_same<KBT, float>::value ? 1 : 4;
         for (long nb = n0 + ry; nb < n1; nb += UR * KG_TR) {
             double kbr[UR], kvr[UR];
@@ -83,7 +85,9 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
                 const bool ok = n < n1;
                 kbr[u] = ok ? (double)Kbar[n * ldk + j] : 0.0;
                 if (sym && ok) kbr[u] = 0.5 * (kbr[u] + (double)Kbar[(long)j * ldk + n]);
-                kvr[u] = (Kval && ok) ? Kval[n * ldkv + j] : 0.0;
+                kvr[u] = 0.0;
+                if (Kval && ok) kvr[u] = Kval[n * ldkv + j];
+                if (Kfhi && ok) kvr[u] = (double)(Kfhi[n * ldkf + j] + Kflo[n * ldkf + j]);   // FP32 planes: value = hi + lo exactly
             }
 #pragma unroll
             for (int u = 0; u < UR; ++u) {
@@ -93,10 +97,17 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
                 const double kb = kbr[u];
                 if constexpr (std::is_same<KBT, float>::value) {
                     float df[MAXD];
-                    float q = 0.f;
 #pragma unroll
-                    for (int d = 0; d < MAXD; ++d) if (d < D) { df[d] = (float)(xs[r][d] - zj[d]); q = fmaf(df[d], df[d], q); }
-                    const float t = (float)kb * (float)s * expf(-0.5f * q);
+                    for (int d = 0; d < MAXD; ++d) if (d < D) df[d] = (float)(xs[r][d] - zj[d]);
+                    float t;
+                    if (Kfhi) {                  // the forward's K planes are still resident
+                        t = (float)kb * (float)kvr[u];
+                    } else {
+                        float q = 0.f;
+#pragma unroll
+                        for (int d = 0; d < MAXD; ++d) if (d < D) q = fmaf(df[d], df[d], q);
+                        t = (float)kb * (float)s * expf(-0.5f * q);
+                    }
                     asum += t;
 #pragma unroll
                     for (int d = 0; d < MAXD; ++d) if (d < D) { az[d] = fmaf(t, df[d], az[d]); al[d] = fmaf(t * df[d], df[d], al[d]); }
@@ -159,9 +170,9 @@ template <typename KBT>
 inline int launch_kernel_grads(const KBT* Kbar, long ldk, const double* X, int x_scaled, const double* Zs,
                                const double* ls, const double* os, long R, int M, int D, int sym, double zscale,
                                double* dZ, double* dls, double* dos, cudaStream_t st, const double* Kval = nullptr,
-                               long ldkv = 0) {
+                               long ldkv = 0, const float* Kfhi = nullptr, const float* Kflo = nullptr, long ldkf = 0) {
 #define TGP_KG(MD) k_kernel_grads<MD, KBT><<<dim3((unsigned)cdiv(M, KG_TC), (unsigned)cdiv(R, kg_rows(MD))), KG_THREADS, 0, st>>>(Kbar, ldk, X, x_scaled, Zs, ls, os, R, M, D, sym, \
-                                                                  zscale, dZ, dls, dos, Kval, ldkv)
+                                                                  zscale, dZ, dls, dos, Kval, ldkv, Kfhi, Kflo, ldkf)
     if (D <= 4) TGP_KG(4);
     else if (D <= 8) TGP_KG(8);
     else if (D <= 16) TGP_KG(16);

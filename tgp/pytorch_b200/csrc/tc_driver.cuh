@@ -14,8 +14,8 @@ extern int g_fused_forward;      // 1: forward = ONE kernel (K tiles generated i
 struct StepPlanes { float *Whi, *Wlo, *Wthi, *Wtlo; long ldk, ld2m; };
 struct BatchPlanes {
     float *AB;                       // (R x ld2m) saved forward -> backward
-    float *Khi, *Klo;                // (Rc x ldk)
-    float *KThi, *KTlo;              // (M x ldt)
+    float *Khi, *Klo;                // (R x ldk)  K_xz planes, kept from the forward (kernel gradients read hi + lo)
+    float *KThi, *KTlo;              // per row chunk (M x ldt): transposed planes, kept for the weight contraction
     float *Phi, *Plo;                // (Rc x ld2m)
     float *PThi, *PTlo;              // (2M x ldt)
     float *Kbar;                     // (Rc x ldk)
@@ -43,7 +43,8 @@ inline StepPlanes carve_step_planes(void* step_ws, int M, int D) {
 
 inline size_t batch_plane_floats(int M, long R) {
     const long Rc = chunk_rows(R), ldk = pad4(M), ld2m = pad4(2L * M), ldt = pad4(Rc);
-    return (size_t)(R * ld2m + 2 * Rc * ldk + 2 * (long)M * ldt + 2 * Rc * ld2m + 2 * 2L * M * ldt + Rc * ldk + 64);
+    const long nch = (R + Rc - 1) / Rc;
+    return (size_t)(R * ld2m + 2 * R * ldk + 2 * nch * (long)M * ldt + 2 * Rc * ld2m + 2 * 2L * M * ldt + Rc * ldk + 64);
 }
 
 inline BatchPlanes carve_batch_planes(void* ws, int M, long R) {
@@ -51,8 +52,9 @@ inline BatchPlanes carve_batch_planes(void* ws, int M, long R) {
     b.Rc = chunk_rows(R); b.ldk = pad4(M); b.ld2m = pad4(2L * M); b.ldt = pad4(b.Rc);
     float* p = reinterpret_cast<float*>(ws);
     b.AB = p; p += R * b.ld2m;
-    b.Khi = p; p += b.Rc * b.ldk; b.Klo = p; p += b.Rc * b.ldk;
-    b.KThi = p; p += (long)M * b.ldt; b.KTlo = p; p += (long)M * b.ldt;
+    const long nch = (R + b.Rc - 1) / b.Rc;
+    b.Khi = p; p += R * b.ldk; b.Klo = p; p += R * b.ldk;
+    b.KThi = p; p += nch * (long)M * b.ldt; b.KTlo = p; p += nch * (long)M * b.ldt;
     b.Phi = p; p += b.Rc * b.ld2m; b.Plo = p; p += b.Rc * b.ld2m;
     b.PThi = p; p += 2L * M * b.ldt; b.PTlo = p; p += 2L * M * b.ldt;
     b.Kbar = p;
@@ -86,12 +88,15 @@ inline int qf_forward(const StepView& s, void* step_ws, void* batch_ws, const do
     }
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
-        TGP_TRY(launch_rbf_planes(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, b.Khi, b.Klo, b.ldk, nullptr, nullptr, 0, st));
+        const long kt_off = (r0 / b.Rc) * (long)M * b.ldt;
+        float *Khi = b.Khi + r0 * b.ldk, *Klo = b.Klo + r0 * b.ldk;
+        TGP_TRY(launch_rbf_planes(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, Khi, Klo, b.ldk, b.KThi + kt_off, b.KTlo + kt_off,
+                                  b.ldt, st));
         Params p{};
         p.Mrows = rc; p.Ncols = 2 * M; p.K = M;
         p.tri_mode = 1; p.tri_rows = M;
         p.out_mode = 0; p.lower_rows = 0; p.Cf = b.AB + r0 * b.ld2m; p.Cd = nullptr; p.ldc = b.ld2m; p.splitk = 1;
-        Operand A{b.Khi, b.Klo, rc, M, b.ldk};
+        Operand A{Khi, Klo, rc, M, b.ldk};
         Operand B{sp.Whi, sp.Wlo, 2L * M, M, sp.ldk};
         TGP_TRY(gemm_tf32x3(A, B, p, st));
     }
@@ -114,7 +119,11 @@ inline int qf_backward(const StepView& s, void* step_ws, void* batch_ws, const d
                                                       b.Plo, b.ld2m, b.PThi, b.PTlo, b.ldt, dm, dos);
             TGP_TRY(check_launch("k_make_abbar_planes"));
         }
-        TGP_TRY(launch_rbf_planes(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, nullptr, nullptr, 0, b.KThi, b.KTlo, b.ldt, st));
+        const long kt_off = (r0 / b.Rc) * (long)M * b.ldt;          // K^T planes of this chunk, kept by the forward
+        float *KThi = b.KThi + kt_off, *KTlo = b.KTlo + kt_off;
+        if (g_fused_forward && D <= FUSED_MAX_D)                     // the fused forward never wrote K: generate it here
+            TGP_TRY(launch_rbf_planes(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, b.Khi + r0 * b.ldk, b.Klo + r0 * b.ldk, b.ldk, KThi,
+                                      KTlo, b.ldt, st));
         {   // Kbar (rc x M) = ABbar (rc x 2M) * Wt (M x 2M)^T ; for k < M only k >= n contributes
             Params p{};
             p.Mrows = rc; p.Ncols = M; p.K = 2 * M;
@@ -124,7 +133,8 @@ inline int qf_backward(const StepView& s, void* step_ws, void* batch_ws, const d
             Operand B{sp.Wthi, sp.Wtlo, M, 2L * M, sp.ld2m};
             TGP_TRY(gemm_tf32x3(A, B, p, st));
         }
-        TGP_TRY(launch_kernel_grads<float>(b.Kbar, b.ldk, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st));
+        TGP_TRY(launch_kernel_grads<float>(b.Kbar, b.ldk, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st,
+                                           nullptr, 0, b.Khi + r0 * b.ldk, b.Klo + r0 * b.ldk, b.ldk));
         const int kblocks = (rc + BK - 1) / BK;
         int split = (int)cdiv(2 * 148, cdiv(M, BM) * cdiv(M, BN));
         if (split > kblocks / 8) split = kblocks / 8 > 0 ? kblocks / 8 : 1;
@@ -133,7 +143,7 @@ inline int qf_backward(const StepView& s, void* step_ws, void* batch_ws, const d
             p.Mrows = M; p.Ncols = M; p.K = rc;
             p.tri_mode = 0; p.out_mode = 1; p.lower_rows = M; p.Cd = Gbar; p.ldc = s.Mp; p.splitk = split;
             Operand A{b.PThi, b.PTlo, M, rc, b.ldt};
-            Operand B{b.KThi, b.KTlo, M, rc, b.ldt};
+            Operand B{KThi, KTlo, M, rc, b.ldt};
             TGP_TRY(gemm_tf32x3(A, B, p, st));
         }
         {   // Cbar (M x M) += Bbar^T K
@@ -141,7 +151,7 @@ inline int qf_backward(const StepView& s, void* step_ws, void* batch_ws, const d
             p.Mrows = M; p.Ncols = M; p.K = rc;
             p.tri_mode = 0; p.out_mode = 1; p.lower_rows = 0; p.Cd = Cbar; p.ldc = s.Mp; p.splitk = split;
             Operand A{b.PThi + (long)M * b.ldt, b.PTlo + (long)M * b.ldt, M, rc, b.ldt};
-            Operand B{b.KThi, b.KTlo, M, rc, b.ldt};
+            Operand B{KThi, KTlo, M, rc, b.ldt};
             TGP_TRY(gemm_tf32x3(A, B, p, st));
         }
     }
