@@ -85,9 +85,10 @@ __global__ void __launch_bounds__(KG_THREADS) k_kernel_grads(const KBT* __restri
                 const bool ok = n < n1;
                 kbr[u] = ok ? (double)Kbar[n * ldk + j] : 0.0;
                 if (sym && ok) kbr[u] = 0.5 * (kbr[u] + (double)Kbar[(long)j * ldk + n]);
-                kvr[u] = 0.0;
-                if (Kval && ok) kvr[u] = Kval[n * ldkv + j];
-                if (Kfhi && ok) kvr[u] = (double)(Kfhi[n * ldkf + j] + Kflo[n * ldkf + j]);   // FP32 planes: value = hi + lo exactly
+                if constexpr (std::is_same<KBT, float>::value)       // FP32 planes: value = hi + lo exactly
+                    kvr[u] = (Kfhi && ok) ? (double)(Kfhi[n * ldkf + j] + Kflo[n * ldkf + j]) : 0.0;
+                else
+                    kvr[u] = (Kval && ok) ? Kval[n * ldkv + j] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < UR; ++u) {
