@@ -54,10 +54,11 @@ __device__ __forceinline__ double flow_param(const TgpFlowLayer& L, int idx, con
 __device__ __forceinline__ int layer_nparams(const TgpFlowLayer& L);
 
 // Node-independent transforms of the GLOBAL flow parameters, hoisted out of the (rows x quadrature nodes) loop: for every
-// parameter slot s (layer-major, descriptor order) prep[2s] = the value the forward uses (softplus where restricted,
-// 1/softplus(d) for the tanh width), prep[2s+1] = d(value)/d(raw) (sigmoid where restricted, else 1).  Per-row
+// parameter slot s (layer-major, descriptor order) prep[3s] = the value the forward uses (softplus where restricted),
+// prep[3s+1] = d(value)/d(raw) (sigmoid where restricted, else 1), prep[3s+2] = 1/value (used for the tanh widths: the
+// per-node divisions by a constant become multiplications).  Per-row
 // (input-dependent) parameters are not prepared; flow_forward transforms those per row.
-constexpr int FLOW_PREP_DOUBLES = 2 * (MAX_THETA + MAX_ROWP);
+constexpr int FLOW_PREP_DOUBLES = 3 * (MAX_THETA + MAX_ROWP);
 __device__ __forceinline__ void flow_prepare(const FlowDesc& fd, const double* __restrict__ theta, double* prep) {
     int total = 0;
     for (int l = 0; l < fd.n_layers; ++l) total += layer_nparams(fd.layers[l]);
@@ -79,7 +80,7 @@ __device__ __forceinline__ void flow_prepare(const FlowDesc& fd, const double* _
         } else if (L.kind == TGP_FLOW_SAL) {
             if (idx == 1 && res) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
         }
-        prep[2 * s] = v0; prep[2 * s + 1] = v1;
+        prep[3 * s] = v0; prep[3 * s + 1] = v1; prep[3 * s + 2] = 1.0 / v0;
     }
     __syncthreads();
 }
@@ -98,7 +99,7 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
         const bool res = L.flags & TGP_FLOW_RESTRICT;
         // transformed value / chain factor of parameter idx (restricted = through softplus)
         auto val = [&](int idx, bool restricted, double& chain) -> double {
-            if (!per_row) { chain = prep[2 * (slot + idx) + 1]; return prep[2 * (slot + idx)]; }
+            if (!per_row) { chain = prep[3 * (slot + idx) + 1]; return prep[3 * (slot + idx)]; }
             const double raw = rowp[L.p0 + idx];
             if (restricted) { chain = sigmoid_d(raw); return softplus_d(raw); }
             chain = 1.0;
@@ -118,11 +119,12 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
                 double chb, chd;
                 const double a = val(4 * i, false, ch0), be = val(4 * i + 1, true, chb);
                 const double c = val(4 * i + 2, false, ch0), de = val(4 * i + 3, true, chd);
-                const double u = (f - c) / de;
+                const double ide = per_row ? 1.0 / de : prep[3 * (slot + 4 * i + 3) + 2];
+                const double u = (f - c) * ide;
                 const double th = tanh(u);
                 const double sech2 = 1.0 - th * th;
                 acc += a + be * th;
-                const double slope = be * sech2 / de;
+                const double slope = be * sech2 * ide;
                 d += slope;
                 if (pg) {
                     pg[slot + 4 * i] = 1.0;

@@ -62,8 +62,61 @@ __global__ void __launch_bounds__(RBF_THREADS) k_rbf_tile(const double* __restri
     }
 }
 
+// Register-blocked variant for D <= 64 (every shipped configuration): a thread owns one column j — its inducing point
+// lives in registers, zero-padded to MAXD — and walks the tile's rows; the X rows are read from shared memory as
+// warp-uniform 16-byte broadcasts (MAXD/2 LDS per element instead of 2*D 8-byte ones in the generic kernel above).
+template <int MAXD>
+__global__ void __launch_bounds__(RBF_THREADS) k_rbf_tile_reg(const double* __restrict__ X, const double* __restrict__ Zs,
+                                                              const double* __restrict__ ls, const double* __restrict__ os,
+                                                              int R, int M, int D, int x_scaled, double* __restrict__ out,
+                                                              long ldo, int Rp, int Mp, double jitter) {
+    __shared__ __align__(16) double xs[RBF_TR][MAXD];
+    const int r0 = blockIdx.y * RBF_TR, c0 = blockIdx.x * RBF_TC, tid = threadIdx.x;
+    for (int i = tid; i < RBF_TR * MAXD; i += RBF_THREADS) {
+        const int r = i / MAXD, d = i % MAXD, n = r0 + r;
+        double v = 0.0;
+        if (n < R && d < D) v = x_scaled ? X[(long)n * D + d] : X[(long)n * D + d] / ls[d];
+        xs[r][d] = v;
+    }
+    const int c = tid % RBF_TC, j = c0 + c;
+    double zj[MAXD];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) zj[d] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
+    __syncthreads();
+    const double s = os[0];
+    for (int r = tid / RBF_TC; r < RBF_TR; r += RBF_THREADS / RBF_TC) {
+        const int n = r0 + r;
+        if (n >= Rp || j >= Mp) continue;
+        double val;
+        if (n < R && j < M) {
+            double acc = 0.0;
+            const double2* xr = reinterpret_cast<const double2*>(xs[r]);
+#pragma unroll
+            for (int d = 0; d < MAXD / 2; ++d) {
+                const double2 x2 = xr[d];
+                const double d0 = x2.x - zj[2 * d], d1 = x2.y - zj[2 * d + 1];
+                acc = fma(d0, d0, acc);
+                acc = fma(d1, d1, acc);
+            }
+            val = s * exp(-0.5 * acc);
+            if (n == j) val += jitter;
+        } else {
+            val = (n == j) ? 1.0 : 0.0;
+        }
+        out[(long)n * ldo + j] = val;
+    }
+}
+
 inline int launch_rbf(const double* X, const double* Zs, const double* ls, const double* os, int R, int M, int D,
                       int x_scaled, double* out, long ldo, int Rp, int Mp, double jitter, cudaStream_t st) {
+    dim3 grid((unsigned)cdiv(Mp, RBF_TC), (unsigned)cdiv(Rp, RBF_TR));
+#define TGP_RBF(MD) k_rbf_tile_reg<MD><<<grid, RBF_THREADS, 0, st>>>(X, Zs, ls, os, R, M, D, x_scaled, out, ldo, Rp, Mp, jitter)
+    if (D <= 4) { TGP_RBF(4); return check_launch("k_rbf_tile_reg"); }
+    if (D <= 8) { TGP_RBF(8); return check_launch("k_rbf_tile_reg"); }
+    if (D <= 16) { TGP_RBF(16); return check_launch("k_rbf_tile_reg"); }
+    if (D <= 32) { TGP_RBF(32); return check_launch("k_rbf_tile_reg"); }
+    if (D <= 64) { TGP_RBF(64); return check_launch("k_rbf_tile_reg"); }
+#undef TGP_RBF
     const size_t smem = (size_t)(RBF_TR + RBF_TC) * (D + 1) * sizeof(double);
     if (smem > 200 * 1024) return set_error(-2, "input dimension too large for the RBF tile kernel");
     static size_t configured = 0;
@@ -71,7 +124,6 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
         cudaFuncSetAttribute(k_rbf_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    dim3 grid((unsigned)cdiv(Mp, RBF_TC), (unsigned)cdiv(Rp, RBF_TR));
     k_rbf_tile<<<grid, RBF_THREADS, smem, st>>>(X, Zs, ls, os, R, M, D, x_scaled, out, ldo, Rp, Mp, jitter);
     return check_launch("k_rbf_tile");
 }
