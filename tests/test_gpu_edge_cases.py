@@ -118,3 +118,21 @@ def test_two_output_model_matches_sum_of_single_output_oracles(shared):
     assert rel_err(ELBO.detach().cpu(), total) < 1e-10
     ref_gZ = (gZ[0] + gZ[1]).unsqueeze(0) if shared else torch.stack(gZ)
     assert rel_err(model.Z.grad.cpu(), ref_gZ) < 1e-8
+
+
+@pytest.mark.parametrize('chunk', [128, 384])
+def test_batch_contractions_in_several_ragged_row_chunks(chunk):
+    """The FP64 batch contractions run in launches of `TGP_OPT_ROW_CHUNK` rows (32768 by default, i.e. a single launch for
+    every small fixture).  Force several launches with a ragged last one: forward, kept K_xz, backward staging and the
+    accumulation over chunks must reproduce the oracle."""
+    from tgp.pytorch_b200 import _lib
+    lib = _lib.load()
+    X, y, p = _problem(1000, 96, 5, seed=11)
+    try:
+        _lib.check(lib.tgp_set_option(_lib.OPT_ROW_CHUNK, chunk), 'tgp_set_option')
+        err = _cuda_vs_oracle(X, y, p, N=25000.0)
+    finally:
+        _lib.check(lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 32768), 'tgp_set_option')
+    bad = {k: e for k, e in err.items() if not e < 1e-8}
+    assert not bad, (bad, err)
+    assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 1) != 0            # refused: below one GEMM tile

@@ -98,3 +98,12 @@ def test_no_cpu_fallback():
     model = build_from_golden(g, 'cpu')
     with pytest.raises(RuntimeError, match='no CPU path'):
         model.ELBO(g.t('X'), g.t('Y'))
+
+
+def test_minibatch_stager_has_no_cpu_path():
+    """The pinned-host stager copies into CUDA memory; asking it for a CPU device must fail loudly, not degrade."""
+    import pytest
+    from tgp.pytorch_b200.data import PinnedMinibatchStager
+    X, Y = torch.zeros(8, 2, dtype=torch.float64), torch.zeros(8, 1, dtype=torch.float64)
+    with pytest.raises(RuntimeError):
+        PinnedMinibatchStager(X, Y, 4, 'cpu')
