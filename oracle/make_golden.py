@@ -131,7 +131,12 @@ def dropout_off(model):
             m.eval()
 
 
+ONLY = set(sys.argv[1:])      # optional fixture names: write only these (the others are left untouched on disk)
+
+
 def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=None):
+    if ONLY and name not in ONLY:
+        return
     store = {}
     model.set_is_training(True)
     for prm in model.parameters():
@@ -259,6 +264,12 @@ def main():
         m.Z[0, 1] = m.Z[0, 0]
         m.Z[0, 3] = m.Z[0, 2]
     record('boston_svgp_jitter', m, Xb[:128], Yb[:128], Xbt, Ybt, ysb, 'gauss_linear', extra={'expects_jitter': True})
+
+    # the largest StepTanhL architecture of the reference's launch scripts (bash_scripts/launch_test_uci_medium-small_
+    # regression.sh, 'energy': 15 blocks x 4 steps = 270 flow scalars), on the boston split
+    m = build('TGP', Xb, 100, Nb, StepTanhL(15, 4, add_f0=True), seed=22)
+    randomise(m, 32)
+    record('boston_tgp_steptanh154_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
 
 
 if __name__ == '__main__':

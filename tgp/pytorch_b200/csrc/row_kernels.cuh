@@ -10,7 +10,7 @@
 
 namespace tgp {
 
-constexpr int MAX_THETA = 160;     // global flow scalars (StepTanhL(10,2) has 100)
+constexpr int MAX_THETA = 288;     // global flow scalars (largest shipped architecture: StepTanhL(15,4) = 270)
 constexpr int MAX_ROWP = 16;       // per-row (input-dependent) flow parameters
 constexpr int ROW_THREADS = 128;   // 4 warps = 4 rows per CTA pass
 
