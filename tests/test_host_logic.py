@@ -107,3 +107,28 @@ def test_minibatch_stager_has_no_cpu_path():
     X, Y = torch.zeros(8, 2, dtype=torch.float64), torch.zeros(8, 1, dtype=torch.float64)
     with pytest.raises(RuntimeError):
         PinnedMinibatchStager(X, Y, 4, 'cpu')
+
+
+def test_library_options_and_workspace_sizing_without_a_gpu():
+    """Option ids in the ctypes binding equal the header's enum; the row-chunk option is validated and changes the batch
+    workspace size it documents (pure host code: no kernel is launched)."""
+    from tgp.pytorch_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'tgp_b200.h')).read()
+    enum = dict(re.findall(r'(TGP_OPT_[A-Z_]+)\s*=\s*(\d+)', header))
+    assert int(enum['TGP_OPT_FUSED_FORWARD']) == _lib.OPT_FUSED_FORWARD
+    assert int(enum['TGP_OPT_ROW_CHUNK']) == _lib.OPT_ROW_CHUNK
+    m = _lib.TgpModel()
+    m.dtype, m.M, m.D, m.likelihood, m.n_quad = _lib.TGP_F64, 256, 4, 1, 30
+    R = 100000
+    try:
+        assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 8192) == 0
+        small = lib.tgp_batch_workspace_bytes(m, R)
+        assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 65536) == 0
+        large = lib.tgp_batch_workspace_bytes(m, R)
+        # [A|B] (2M) and K_xz (M) are per row; the two staging buffers (M each) are per chunk
+        assert small >= 8 * (3 * 256 * R + 2 * 256 * 8192) and large - small == 8 * 2 * 256 * (65536 - 8192)
+        assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 64) != 0 and b'row chunk' in lib.tgp_last_error()
+        assert lib.tgp_set_option(99, 1) != 0
+    finally:
+        assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 32768) == 0
