@@ -3,19 +3,24 @@
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path, one process per GPU under torchrun
   python bench.py --impl reference --gpus N ...            # the reference's algorithm on the host CPU cores (oracle port)
+  options: --workload cfg4|cfg5   --scaling weak|strong   --compute f64|tf32x3
 
-Workload (BASELINE.json configs[3]): TGP regression, synthetic N = 5 M rows, D = 8, M = 1024 inducing
-points, StepTanhL(1,3) flow, Gaussian likelihood, 100 Gauss-Hermite points, FP64 (what the reference's main.py runs);
-one step = ELBO forward + backward over one minibatch of 65536 rows PER GPU (weak scaling; the global minibatch is
-65536 * N rows, N/MB scaling uses the global size, one NCCL all-reduce of the packed pre-chain gradient buffer).
+Workloads:
+  cfg4 (default; BASELINE.json configs[3], the configuration the metric is quoted on): TGP regression, synthetic
+       N = 5 M rows, D = 8, M = 1024 inducing points, StepTanhL(1,3) flow, Gaussian likelihood, 100 Gauss-Hermite points;
+  cfg5 (configs[4]): TGP binary classification, N = 1 M, D = 16, M = 2048, SAL(1) flow, Bernoulli likelihood, 100 points.
+Both FP64 (what the reference's main.py runs).  One step = ELBO forward + backward over one minibatch:
+  weak scaling  (default): 65536 rows PER GPU, global minibatch 65536 * N;
+  strong scaling          : 65536 rows in total, 65536 / N per GPU.
+The N/MB scale uses the global size; ranks exchange ONE all-reduce of the tril-packed pre-chain gradient buffer per step.
 
-One JSON line on stdout (rank 0).  Keys per the driver contract plus `roofline` and `cpu_baseline`.
+One JSON line on stdout (rank 0).  Keys per the driver contract plus `roofline`, `cpu_baseline`, `dist_parity` (N > 1).
 """
 import argparse
+import hashlib
 import json
 import math
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -26,39 +31,80 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_DATA, D, M, BATCH = 5_000_000, 8, 1024, 65536
-N_QUAD = 100
 SEED = 1234
-CPU_SAMPLE_ROWS = 8192           # rows per CPU step: a bounded sample of the same workload
+N_QUAD = 100
 METRIC = 'elbo_fwd_bwd_rows_per_s'
+WORKLOADS = {
+    'cfg4': dict(N=5_000_000, D=8, M=1024, batch=65536, likelihood='gauss_nonlinear', flow='StepTanhL(1,3)',
+                 text='TGP regression synthetic N=5M D=8 M=1024, StepTanhL(1,3), Gaussian lik, 100 GH points (BASELINE configs[3])'),
+    'cfg5': dict(N=1_000_000, D=16, M=2048, batch=65536, likelihood='bernoulli', flow='SAL(1)',
+                 text='TGP binary classification synthetic N=1M D=16 M=2048, SAL(1), Bernoulli lik, 100 GH points (BASELINE configs[4])'),
+}
 
 
-def synth(n, d, gen):
+def synth(wl, n, gen):
+    """SURVEY.md §8d synthetic data: regression y = sinh(0.7 Xw / sqrt D) + 0.1 eps (standardised); classification
+    y = 1[Phi(Xw / sqrt D) > u]."""
+    d = wl['D']
     X = torch.randn(n, d, generator=gen, dtype=torch.float64)
     w = torch.randn(d, generator=gen, dtype=torch.float64)
-    y = torch.sinh(0.7 * (X @ w) / math.sqrt(d)) + 0.1 * torch.randn(n, generator=gen, dtype=torch.float64)
-    y = (y - y.mean()) / y.std()
+    if wl['likelihood'] == 'bernoulli':
+        pr = 0.5 * (1 + torch.erf((X @ w) / math.sqrt(d) / math.sqrt(2.0)))
+        y = (pr > torch.rand(n, generator=gen, dtype=torch.float64)).double()
+    else:
+        y = torch.sinh(0.7 * (X @ w) / math.sqrt(d)) + 0.1 * torch.randn(n, generator=gen, dtype=torch.float64)
+        y = (y - y.mean()) / y.std()
     return X, y.view(-1, 1)
 
 
-def param_state(X, gen):
-    """'Mid-training' state P1: nothing at a trivial value; K_zz stays well conditioned."""
+def param_state(wl, X, gen):
+    """'Mid-training' state P1: nothing at a trivial value; K_zz stays well conditioned.  Oracle-style
+    dict (oracle/tgp_oracle.py), also consumed by `build_engine` below."""
+    M, D = wl['M'], wl['D']
     idx = torch.randperm(X.shape[0], generator=gen)[:M]
     inv_sp = lambda t: t + torch.log(-torch.expm1(-t))  # noqa: E731
+    f64 = torch.float64
     p = dict(Z=X[idx].clone(),
-             raw_lengthscale=inv_sp(1.5 + 1.0 * torch.rand(D, generator=gen, dtype=torch.float64)),
-             raw_outputscale=inv_sp(torch.tensor(1.5, dtype=torch.float64)),
-             m=torch.randn(M, generator=gen, dtype=torch.float64),
-             L_raw=0.5 * torch.eye(M, dtype=torch.float64) + 0.05 * torch.randn(M, M, generator=gen, dtype=torch.float64),
-             log_var_noise=torch.log(torch.tensor(0.05, dtype=torch.float64)))
-    steps = []
-    for _ in range(3):
-        e = torch.randn(4, generator=gen, dtype=torch.float64)
-        steps.append((e[0].clone(), inv_sp(torch.abs((e[1] + 1.0) / 3.0) + 1e-3), e[2].clone(),
-                      inv_sp(torch.abs((e[3] + 1.0) / 3.0) + 1e-3)))
-    p['flow'] = [('tanh_step', steps, True), ('affine', torch.tensor(1.1, dtype=torch.float64),
-                                               torch.tensor(-0.05, dtype=torch.float64), False)]
+             raw_lengthscale=inv_sp(1.5 + 1.0 * torch.rand(D, generator=gen, dtype=f64)),
+             raw_outputscale=inv_sp(torch.tensor(1.5, dtype=f64)),
+             m=torch.randn(M, generator=gen, dtype=f64),
+             L_raw=0.5 * torch.eye(M, dtype=f64) + 0.05 * torch.randn(M, M, generator=gen, dtype=f64),
+             log_var_noise=torch.log(torch.tensor(0.05, dtype=f64)))
+    if wl['flow'] == 'StepTanhL(1,3)':
+        steps = []
+        for _ in range(3):
+            e = torch.randn(4, generator=gen, dtype=f64)
+            steps.append((e[0].clone(), inv_sp(torch.abs((e[1] + 1.0) / 3.0) + 1e-3), e[2].clone(),
+                          inv_sp(torch.abs((e[3] + 1.0) / 3.0) + 1e-3)))
+        p['flow'] = [('tanh_step', steps, True), ('affine', torch.tensor(1.1, dtype=f64), torch.tensor(-0.05, dtype=f64), False)]
+    else:   # SAL(1): sinh-arcsinh then affine (reference flows.py:115-136)
+        e = torch.randn(2, generator=gen, dtype=f64)
+        p['flow'] = [('sal', 0.3 * e[0].clone(), 1.0 + 0.2 * torch.tanh(e[1]), False, False),
+                     ('affine', torch.tensor(0.9, dtype=f64), torch.tensor(0.1, dtype=f64), False)]
     return p
+
+
+def build_engine(p, wl, dev, compute):
+    """Oracle-style parameter dict -> (Engine, device parameter tensors in C-ABI order, theta)."""
+    from tgp.pytorch_b200.engine import Engine, FlowLayout
+    desc, theta = [], []
+    for lay in p['flow']:
+        if lay[0] == 'affine':
+            desc.append(dict(kind='affine', restrict=lay[3]))
+            theta += [lay[1], lay[2]]
+        elif lay[0] == 'tanh_step':
+            desc.append(dict(kind='tanh_step', n_steps=len(lay[1]), add_f0=lay[2]))
+            for st in lay[1]:
+                theta += list(st)
+        elif lay[0] == 'sal':
+            desc.append(dict(kind='sal', restrict=lay[3], add_f0=lay[4]))
+            theta += [lay[1], lay[2]]
+    f = lambda t: t.detach().to(dev).double().contiguous()  # noqa: E731
+    eng = Engine(wl['M'], wl['D'], wl['likelihood'], N_QUAD, FlowLayout(desc), dev, compute=compute)
+    t = dict(Z=f(p['Z']), raw_ls=f(p['raw_lengthscale'].reshape(-1)), raw_os=f(p['raw_outputscale'].reshape(1)), m=f(p['m']),
+             L_raw=f(p['L_raw']), log_var_noise=None if wl['likelihood'] == 'bernoulli' else f(p['log_var_noise'].reshape(1)),
+             theta=f(torch.stack([x.reshape(()) for x in theta])))
+    return eng, t
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -116,35 +162,52 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def measure_fp64_peak(dev):
-    """cuBLAS DGEMM 8192^3 via torch.matmul, best of 5 — MEASURED_PEAKS.json has no FP64 figure (method of that file)."""
-    n = 8192
-    a = torch.randn(n, n, dtype=torch.float64, device=dev)
-    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+def measure_gemm_peak(dev, dtype, tf32=False, n=8192, reps=5):
+    """cuBLAS GEMM n^3 via torch.matmul, best of `reps` (the method of MEASURED_PEAKS.json, which holds no FP64 / TF32 figure)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    a = torch.randn(n, n, dtype=dtype, device=dev)
+    b = torch.randn(n, n, dtype=dtype, device=dev)
     torch.matmul(a, b)
     torch.cuda.synchronize()
     best = 1e9
-    for _ in range(5):
+    for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); torch.matmul(a, b); e1.record()  # noqa: E702
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     del a, b
+    torch.backends.cuda.matmul.allow_tf32 = old
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def load_json(path):
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def lib_hash():
+    from tgp.pytorch_b200 import _lib
+    h = hashlib.sha1()
+    with open(_lib.LIB_PATH, 'rb') as fh:
+        h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(p, X, Y, rows, steps, warmup):
-    """ELBO + backward of the reference's algorithm (oracle port O2, pinned to the reference by tests/golden) on the
-    host cores; each step is a `rows`-row sample of the workload."""
+def cpu_reference_steps(wl, p, X, Y, rows, steps, warmup):
+    """ELBO + backward of the reference's algorithm (oracle port O2, pinned to the unmodified reference by tests/golden:
+    /root/reference does not exist on the GPU box) on the host cores; each step is a `rows`-row minibatch."""
     from oracle import tgp_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     times = []
     for s in range(warmup + steps):
-        lo = (s * rows) % (X.shape[0] - rows)
+        lo = (s * rows) % max(X.shape[0] - rows, 1)
         xb, yb = X[lo:lo + rows], Y[lo:lo + rows].view(-1)
         t0 = time.perf_counter()
-        O.elbo_and_grads(xb, yb, p, float(N_DATA), 'gauss_nonlinear', N_QUAD)
+        O.elbo_and_grads(xb, yb, p, float(wl['N']), wl['likelihood'], N_QUAD)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -152,36 +215,42 @@ def cpu_reference_steps(p, X, Y, rows, steps, warmup):
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (kind 'port': the oracle restatement — the reference itself needs
+    /root/reference, absent on the GPU box), all host threads, at the SAME minibatch size as our arm."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
+    rows = wl['batch']                                  # the arm's own minibatch size: 65536 rows per step
     gen = torch.Generator().manual_seed(SEED)
-    n_cpu = max(CPU_SAMPLE_ROWS * 8, 200_000)
-    X, Y = synth(n_cpu, D, gen)
-    p = param_state(X, gen)
-    rows_s, sec = cpu_reference_steps(p, X, Y, CPU_SAMPLE_ROWS, args.steps, args.warmup)
+    X, Y = synth(wl, rows * 2, gen)
+    p = param_state(wl, X, gen)
+    rows_s, sec = cpu_reference_steps(wl, p, X, Y, rows, args.steps, args.warmup)
     cores = torch.get_num_threads()
     line = {'impl': 'reference', 'metric': METRIC, 'value': rows_s, 'unit': 'rows/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args.gpus),
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_config(wl, args, 1), cpu_rows_per_step=rows,
+                           cpu_arm='oracle port O2 (torch CPU, all host threads); one host, independent of --gpus'),
             'cpu_baseline': {'value': rows_s, 'unit': 'rows/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d-row minibatch per step of the same workload (M=%d, D=%d, %d GH points, FP64), '
-                                       'torch CPU with %d threads' % (CPU_SAMPLE_ROWS, M, D, N_QUAD, cores)},
+                             'sample': '%d-row minibatch per step (the arm\'s own batch size; M=%d, D=%d, %d GH points, FP64), '
+                                       'torch CPU with %d threads, median of %d steps' % (rows, wl['M'], wl['D'], N_QUAD, cores, args.steps)},
             'e2e': {'value': rows_s, 'unit': 'rows/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
 
 
-def workload_config(n_gpus):
-    return {'workload': 'TGP regression synthetic N=5M D=8 M=1024 batch 65536/GPU, StepTanhL(1,3), Gaussian lik, '
-                        '100 GH points (BASELINE configs[3])', 'N': N_DATA, 'D': D, 'M': M, 'rows_per_gpu_per_step': BATCH,
-            'global_batch': BATCH * n_gpus, 'parallelism': 'rows x%d' % n_gpus,
-            'l2': 'per-step working set (A|B workspace 1.07 GB) >> 126 MB L2, plus an explicit 256 MiB L2 flush between steps'}
+def workload_config(wl, args, world):
+    rows = wl['batch'] if args.scaling == 'weak' else wl['batch'] // world
+    return {'workload': wl['text'], 'name': args.workload, 'N': wl['N'], 'D': wl['D'], 'M': wl['M'],
+            'rows_per_gpu_per_step': rows, 'global_batch': rows * world, 'parallelism': 'rows x%d' % world,
+            'l2': 'per-step working set (A|B workspace %.2f GB) >> 126 MB L2, plus an explicit 256 MiB L2 flush between steps'
+                  % (rows * 2 * wl['M'] * 8 / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import ctypes as C
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -193,46 +262,75 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    from tests.gpu_util import engine_inputs, make_engine
     from tgp.pytorch_b200 import _lib, functional as Fn
+    from tgp.pytorch_b200.dist import local_slice
     lib = _lib.load()
+    wl = WORKLOADS[args.workload]
+    N_DATA, D, M = wl['N'], wl['D'], wl['M']
+    BATCH = wl['batch'] if args.scaling == 'weak' else wl['batch'] // world      # rows per GPU per step
+    global_batch = BATCH * world
 
     gen = torch.Generator().manual_seed(SEED)
-    X, Y = synth(N_DATA, D, gen)                      # identical on every rank (same seed)
-    p = param_state(X, gen)
+    X, Y = synth(wl, N_DATA, gen)                     # identical on every rank (same seed)
+    p = param_state(wl, X, gen)
     perm = torch.randperm(N_DATA, generator=gen)
     steps_total = args.warmup + args.steps
-    global_batch = BATCH * world
     scale = float(N_DATA) / global_batch
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     # the dataset lives in HBM for the device arm; minibatches are gathered by index on the device
     Xd, Yd = X.to(dev), Y.view(-1).to(dev)
     perm_d = perm.to(dev)
-    import ctypes as C
 
     def dev_batch(step):
         lo = ((step * global_batch) + rank * BATCH) % (N_DATA - global_batch)
         idx = perm_d[lo:lo + BATCH]
         return Xd.index_select(0, idx), Yd.index_select(0, idx)
 
-    def measure(compute, sample_clocks):
-        """W warm-up + K timed ELBO fwd+bwd steps of the device arm in one compute mode."""
-        eng, theta, _, _ = make_engine(p, 'gauss_nonlinear', N_QUAD, dev, compute=compute)
-        ei = engine_inputs(p, dev)
-        leaves = [ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta]
-        for t in leaves:
-            t.requires_grad_(True)
+    def make_step(compute):
+        eng, t = build_engine(p, wl, dev, compute)
+        leaves = [t['Z'], t['raw_ls'], t['raw_os'], t['m'], t['L_raw'], t['log_var_noise'], t['theta']]
+        for x in leaves:
+            if x is not None:
+                x.requires_grad_(True)
 
-        def step_fn(xb, yb):
-            for t in leaves:
-                t.grad = None
-            ELL, KLD, _, _, _ = Fn.elbo_terms(eng, xb, yb, scale, ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'],
-                                              ei['L_raw'], ei['log_var_noise'], theta, None, check_status=True)
+        def step_fn(xb, yb, sc=scale):
+            for x in leaves:
+                if x is not None:
+                    x.grad = None
+            # sync_ell=False: ONE collective per step (the global ELL rides in the packed all-reduce of the backward)
+            ELL, KLD, _, _, _ = Fn.elbo_terms(eng, xb, yb, sc, *leaves, None, check_status=True, sync_ell=False)
             loss = -(ELL - KLD)
             loss.backward()
             return loss
+        return eng, leaves, step_fn
 
+    def dist_parity():
+        """N > 1: the all-reduced gradients of a row-sharded global minibatch against ONE rank evaluating the whole
+        minibatch alone (same kernels, no collective).  Max L2-relative error over tensors and ranks."""
+        eng, leaves, step_fn = make_step('f64')
+        G = 2048 * world
+        idx = perm_d[:G]
+        xg, yg = Xd.index_select(0, idx), Yd.index_select(0, idx)
+        sl = local_slice(G, rank, world)
+        sc = float(N_DATA) / G
+        step_fn(xg[sl].contiguous(), yg[sl].contiguous(), sc)
+        got = [None if x is None else x.grad.clone() for x in leaves]
+        ell_global = float((sc * eng.last_ell_sum).item())
+        with Fn.local_only():
+            loss = step_fn(xg, yg, sc)
+        errs = [float((a - x.grad).norm() / x.grad.norm()) for a, x in zip(got, leaves) if x is not None]
+        kl = float(eng.kl.item())
+        errs.append(abs((-(ell_global - kl)) - float(loss.item())) / abs(float(loss.item())))
+        w = torch.tensor([max(errs)], dtype=torch.float64, device=dev)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        return {'max_rel_err': float(w.item()), 'global_rows': G, 'ok': bool(w.item() < 1e-10),
+                'what': 'all-reduced ELBO and gradients (Z, lengthscale, outputscale, m, L_S, noise, flow) of a row-sharded '
+                        'global minibatch vs one rank evaluating it alone; max L2-relative error over tensors and ranks'}
+
+    def measure(compute, sample_clocks):
+        """W warm-up + K timed ELBO fwd+bwd steps of the device arm in one compute mode."""
+        eng, leaves, step_fn = make_step(compute)
         clocks = ClockSampler(local)
         if sample_clocks and rank == 0 and not args.no_clocks:
             clocks.start()                              # sampler runs through warm-up + timed region (same load)
@@ -281,124 +379,149 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        loss_global = float((-(scale * eng.last_ell_sum - eng.kl[0])).item())      # global ELBO from the packed all-reduce
         # test-NLL forward (no gradients): marginals + quadrature log-lik + moments on the same batches
         with torch.no_grad():
-            eng.set_params(*[t.detach() for t in leaves])
+            eng.set_params(*[None if x is None else x.detach() for x in leaves])
             eng.prepare(0.0)
-            for s in range(2):
-                mu, v = eng.qf_forward(dev_batch(s)[0])
-                eng.test_rows(mu, v, dev_batch(s)[1], None, 1, 1.0)
+            bstd = torch.ones(1, dtype=torch.float64, device=dev) if wl['likelihood'] == 'bernoulli' else None
+
+            def nll_pass(refactor):
+                for s in range(args.steps):
+                    xb, yb = dev_batch(args.warmup + s)
+                    if refactor:
+                        eng.prepare(0.0)
+                    mu, v = eng.qf_forward(xb)
+                    eng.test_rows(mu, v, yb, None, 1, 1.0, v.std().reshape(1) if bstd is not None else None)
+            nll_pass(True)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            for s in range(args.steps):
-                xb, yb = dev_batch(args.warmup + s)
-                eng.prepare(0.0)
-                mu, v = eng.qf_forward(xb)
-                eng.test_rows(mu, v, yb, None, 1, 1.0)
+            nll_pass(True)
             e1.record()
-            torch.cuda.synchronize()
-            e2 = torch.cuda.Event(enable_timing=True)
-            for s in range(args.steps):                # same pass with the factorisation reused (frozen parameters)
-                xb, yb = dev_batch(args.warmup + s)
-                mu, v = eng.qf_forward(xb)
-                eng.test_rows(mu, v, yb, None, 1, 1.0)
+            nll_pass(False)                            # same pass with the factorisation reused (frozen parameters)
             e2.record()
             torch.cuda.synchronize()
             tn = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-        return dict(ms_total=ms, value=BATCH * world * args.steps / (ms * 1e-3), loss=float(loss.item()),
+        return dict(ms_total=ms, value=global_batch * args.steps / (ms * 1e-3), loss=loss_global,
                     gemm_ms=list(gemm_ms), gemm_n=list(gemm_n), launches=int(launches), clocks=clk,
-                    test_nll_rows_per_s=BATCH * world * args.steps / (float(tn[0].item()) * 1e-3),
-                    test_nll_cached_rows_per_s=BATCH * world * args.steps / (float(tn[1].item()) * 1e-3))
+                    test_nll_rows_per_s=global_batch * args.steps / (float(tn[0].item()) * 1e-3),
+                    test_nll_cached_rows_per_s=global_batch * args.steps / (float(tn[1].item()) * 1e-3))
 
+    parity = dist_parity() if world > 1 else None
     # the secondary mode runs first: on a fresh box the first seconds of a process are not steady (cold clocks, lazy
     # module loads), and the headline should not absorb that
     second = 'tf32x3' if args.compute == 'f64' else 'f64'
-    measure(second, False)                      # discarded: absorbs the cold start of a fresh box
+    other = None
+    if not args.no_other_mode:
+        measure(second, False)                      # discarded: absorbs the cold start of a fresh box
     head = measure(args.compute, True)
-    other = measure(second, False)
+    if not args.no_other_mode:
+        other = measure(second, False)
     ms_total, value, final_loss, launches, clk = head['ms_total'], head['value'], head['loss'], head['launches'], head['clocks']
     gemm_ms, gemm_n = head['gemm_ms'], head['gemm_n']
 
     # ---- end-to-end arm: host (pinned) minibatches through the public class API, loss read back every step -----
-    e2e = run_e2e(args, p, X, Y, perm, rank, world, dev, scale)
+    e2e = run_e2e(args, wl, p, X, Y, perm, rank, world, dev, BATCH)
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (gemm_f64_kernel, batch contractions) ----------------------------------
-    peak64 = measure_fp64_peak(dev)
-    alg_flop_step = 6.0 * M * M * BATCH                         # 6*M^2 FLOP per row, fwd+bwd
-    gemm_ms_step = (gemm_ms[1] + gemm_ms[2]) / args.steps
-    gemm_launches_step = (gemm_n[1] + gemm_n[2]) / args.steps
-    achieved = alg_flop_step / (gemm_ms_step * 1e-3) / 1e12 if gemm_ms_step > 0 else 0.0
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_f64_kernel (FP64 DMMA), batch contractions' if args.compute == 'f64'
-                else 'gemm_tf32x3_kernel (tcgen05) — event timing covers only the FP64 per-step GEMMs in this mode', 'achieved': achieved,
-                'peak': peak64, 'unit': 'TFLOP/s', 'frac': achieved / peak64,
-                'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (MEASURED_PEAKS.json has no FP64 '
-                               'figure; its bf16 %.0f TF/s does not bound an FP64 kernel)' % peaks.get('bf16_tflops', 1707.0),
-                'algorithmic_flop_per_launch': alg_flop_step / max(gemm_launches_step, 1),
-                'avg_launch_ms': gemm_ms_step / max(gemm_launches_step, 1), 'launches_per_step': gemm_launches_step,
-                'kernel_share_of_step': gemm_ms_step / (ms_total / args.steps),
-                'executed_dense_tile_tflops': None, 'traffic': None,
-                'per_step_o_m3_gemm_ms': gemm_ms[0] / args.steps}
-    prof = os.path.join(ROOT, 'profiles', 'r01_roofline_extra.json')
-    if os.path.exists(prof):
-        try:
-            roofline.update(json.load(open(prof)))
-        except Exception:
-            pass
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
+    peaks = load_json(os.path.join(ROOT, 'MEASURED_PEAKS.json'))
+    extra = load_json(os.path.join(ROOT, 'profiles', 'r02_measured_peaks_extra.json'))     # scripts/measure_peaks.py on this pool
+    peak64 = measure_gemm_peak(dev, torch.float64)
+    peak_tf32 = measure_gemm_peak(dev, torch.float32, tf32=True)
+    alg_flop_step = 6.0 * M * M * BATCH                         # 6*M^2 FLOP per row, fwd+bwd (per GPU)
+
+    def roofline_of(mode, g_ms, g_n, step_ms):
+        tag = 1 if mode == 'f64' else 2
+        k_ms, k_n = g_ms[tag] / args.steps, g_n[tag] / args.steps
+        ach = alg_flop_step / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        if mode == 'f64':
+            peak, src, kern = peak64, 'cuBLAS DGEMM 8192^3 via torch.matmul, best of 5, measured in this run', \
+                'gemm_f64_kernel (FP64 DMMA mma.sync.m8n8k4), the six batch contractions'
+        else:
+            peak, src, kern = peak_tf32, 'cuBLAS TF32 GEMM 8192^3 via torch.matmul (allow_tf32), best of 5, measured in this run', \
+                'gemm_tf32x3_kernel (tcgen05 kind::tf32, TMEM accumulators), the three batch contractions'
+        r = {'bound': 'tensor', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak if peak else None,
+             'peak_source': src + '; MEASURED_PEAKS.json holds bf16 %.0f TF/s and HBM %.0f GB/s only'
+                            % (peaks.get('bf16_tflops', 0.0), peaks.get('hbm_gbs', 0.0)),
+             'pool_peaks': {k: extra.get(k) for k in ('fp64_tflops', 'fp64_tflops_sustained', 'tf32_tflops', 'tf32_tflops_sustained',
+                                                      'int8_tops')} if extra else None,
+             'algorithmic_flop_per_launch': alg_flop_step / max(k_n, 1), 'avg_launch_ms': k_ms / max(k_n, 1),
+             'launches_per_step': k_n, 'kernel_share_of_step': k_ms / step_ms, 'traffic': None,
+             'per_step_o_m3_gemm_ms': g_ms[0] / args.steps}
+        if mode == 'tf32x3':
+            # executed: three TF32 MMAs per product, dense 128x256 tiles incl. the dense C half: (2 + 2 + 2) M^2 MACs * 3
+            r['executed_tflops'] = 3.0 * 2.0 * (1.5 + 1.5 + 1.5) * M * M * BATCH / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+            r['executed_frac_of_peak'] = r['executed_tflops'] / peak if peak else None
+        prof = load_json(os.path.join(ROOT, 'profiles', 'r02_roofline_traffic.json')).get(args.workload + ':' + mode)
+        if prof and prof.get('lib_hash') == lib_hash():
+            r['traffic'] = prof.get('traffic')                  # dram bytes per launch from ncu --set full of THIS build
+            r['traffic_source'] = prof.get('source')
+        elif prof:
+            r['traffic_note'] = 'profiles/r02_roofline_traffic.json was captured from a different build (%s); not reported' % prof.get('lib_hash')
+        return r
+
+    roofline = roofline_of(args.compute, gemm_ms, gemm_n, ms_total / args.steps)
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ----------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        rows_s, sec = cpu_reference_steps(p, X[:CPU_SAMPLE_ROWS * 8], Y[:CPU_SAMPLE_ROWS * 8], CPU_SAMPLE_ROWS, 3, 1)
+        rows = wl['batch']
+        rows_s, sec = cpu_reference_steps(wl, p, X[:rows * 2], Y[:rows * 2], rows, 3, 1)
         cpu = {'value': rows_s, 'unit': 'rows/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': '3 steps of a %d-row minibatch of the same workload after 1 warm-up (median %.2f s/step)'
-                         % (CPU_SAMPLE_ROWS, sec)}
+               'sample': '3 steps of a %d-row minibatch of the same workload after 1 warm-up (median %.2f s/step); oracle '
+                         'port O2, torch CPU' % (rows, sec)}
     line = {'metric': METRIC, 'value': value, 'unit': 'rows/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(world),
+            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(wl, args, world),
             'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
-            'final_loss': final_loss, 'compute': args.compute,
+            'final_loss': final_loss, 'compute': args.compute, 'collectives_per_step': 1 if world > 1 else 0,
             'test_nll': {'value': head['test_nll_rows_per_s'], 'unit': 'rows/s',
                          'what': 'test log-lik + predictive moments forward (prepare + marginals + quadrature), device-resident',
-                         'with_factorisation_reused_across_batches': head['test_nll_cached_rows_per_s']},
-            'other_mode': {'compute': 'tf32x3' if args.compute == 'f64' else 'f64', 'value': other['value'], 'unit': 'rows/s',
-                           'ms_per_step': other['ms_total'] / args.steps, 'final_loss': other['loss'],
-                           'loss_rel_diff_vs_headline': abs(other['loss'] - final_loss) / abs(final_loss),
-                           'test_nll_rows_per_s': other['test_nll_rows_per_s'],
-                           'batch_gemm_ms_per_step': (other['gemm_ms'][1] + other['gemm_ms'][2]) / args.steps,
-                           'batch_gemm_algorithmic_tflops': 6.0 * M * M * BATCH / max((other['gemm_ms'][1] + other['gemm_ms'][2]) / args.steps * 1e-3, 1e-12) / 1e12,
-                           'note': 'tf32x3 = batch contractions on tcgen05 (3xTF32 split, FP32 TMEM accumulation); per-step '
-                                   'factorisation, backward chain and the row epilogue stay FP64 in both modes'}}
+                         'with_factorisation_reused_across_batches': head['test_nll_cached_rows_per_s']}}
+    if parity is not None:
+        line['dist_parity'] = parity
+    if other is not None:
+        line['other_mode'] = {'compute': second, 'value': other['value'], 'unit': 'rows/s',
+                              'ms_per_step': other['ms_total'] / args.steps, 'final_loss': other['loss'],
+                              'loss_rel_diff_vs_headline': abs(other['loss'] - final_loss) / abs(final_loss),
+                              'test_nll_rows_per_s': other['test_nll_rows_per_s'],
+                              'roofline': roofline_of(second, other['gemm_ms'], other['gemm_n'], other['ms_total'] / args.steps),
+                              'note': 'tf32x3 = batch contractions on tcgen05 (3xTF32 split, FP32 TMEM accumulation); per-step '
+                                      'factorisation, backward chain and the row epilogue stay FP64 in both modes'}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(args, p, X, Y, perm, rank, world, dev, scale):
+def run_e2e(args, wl, p, X, Y, perm, rank, world, dev, BATCH):
     """Same metric through the public API (`sparse_MF_SP.ELBO` + backward) with HOST buffers: every step gathers its
     minibatch into pinned memory, copies it to the device, and reads the loss back."""
     import torch.distributed as dist
     from tgp.pytorch_b200.dsp import config as cg
     cg.set_maximum_precission()
     cg.device = str(dev)
+    cg.sync_elbo_in_forward = False            # one collective per step; the global ELBO is read after backward
     from tgp.pytorch_b200.dsp.models import instance_kernel, sparse_MF_SP
     from tgp.pytorch_b200.dsp.models.flow import instance_flow
-    from tgp.pytorch_b200.dsp.likelihoods import GaussianNonLinearMean
-    from tgp.pytorch_b200.dsp.flows import StepTanhL
+    from tgp.pytorch_b200.dsp.likelihoods import GaussianNonLinearMean, Bernoulli
+    from tgp.pytorch_b200.dsp.flows import StepTanhL, SAL
+    N_DATA, D, M = wl['N'], wl['D'], wl['M']
     K = instance_kernel('scale_rbf', ard_num_dim=D, num_multioutput=1, kernel_is_shared=False,
                         init_params={'length_scale': 2.0, 'kernel_scale': 2.0})
-    lik = GaussianNonLinearMean(out_dim=1, noise_init=0.05, noise_is_shared=False, quadrature_points=N_QUAD)
     np.random.seed(0)
+    if wl['likelihood'] == 'bernoulli':
+        lik, flow = Bernoulli(), instance_flow(SAL(1))
+    else:
+        lik = GaussianNonLinearMean(out_dim=1, noise_init=0.05, noise_is_shared=False, quadrature_points=N_QUAD)
+        flow = instance_flow(StepTanhL(1, 3, add_f0=True))
     model = sparse_MF_SP(['zero', K], X[:1024], p['Z'], float(N_DATA), lik, 1, True, False, False, False, False,
-                         [instance_flow(StepTanhL(1, 3, add_f0=True))], 'single', 0.0, False,
+                         [flow], 'single', 0.0, False,
                          {'variational_distribution': {'variance_scale': 1e-5, 'mean_scale': 0.0}})
     with torch.no_grad():
         model.q_U.variational_mean.copy_(p['m'].view(1, -1))
@@ -422,7 +545,7 @@ def run_e2e(args, p, X, Y, perm, rank, world, dev, scale):
         ELBO, _, _ = model.ELBO(xb, yb)
         (-ELBO).backward()
         stager.stage(batch_index(step + 1))             # host gather + H2D of the next step under this step's backward
-        return float(ELBO.item())                       # device -> host read of the step's result
+        return float(model.last_global_elbo().item())   # device -> host read of the step's result (global ELBO)
 
     stager.stage(batch_index(0))
     for s in range(min(args.warmup, 3)):
@@ -441,7 +564,7 @@ def run_e2e(args, p, X, Y, perm, rank, world, dev, scale):
             'h2d_bytes_per_step': stager.bytes_per_step, 'd2h_bytes_per_step': 8,
             'note': 'sparse_MF_SP.ELBO + backward per step through the class API; every step gathers its minibatch from host '
                     'memory into pinned buffers and copies it to the device (PinnedMinibatchStager: the gather + H2D of step '
-                    's+1 overlap the kernels of step s), and reads the loss back'}
+                    's+1 overlap the kernels of step s), and reads the (global) ELBO back'}
 
 
 _REAL_STDOUT = None
@@ -463,8 +586,12 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: 65536 rows per GPU per step; strong: 65536 rows per step in total')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--compute', default='f64', choices=['f64', 'tf32x3'], help='f64: DMMA path (what main.py runs); tf32x3: tcgen05 mode')
+    ap.add_argument('--no-other-mode', action='store_true', help='measure only the headline compute mode')
     ap.add_argument('--no-gemm-timing', action='store_true', help='(diagnostic) do not instrument GEMM launches with events')
     ap.add_argument('--no-clocks', action='store_true', help='(diagnostic) do not sample nvidia-smi during the timed region')
     args = ap.parse_args()

@@ -67,6 +67,7 @@ typedef struct TgpParams {           /* device pointers to the model parameters 
 /* layout (in doubles) of the packed buffer that ranks all-reduce between tgp_qf_backward and tgp_chain_backward */
 typedef struct TgpReduceLayout {
     long ell_sum, dlogvar, dos, dls, dtheta, dm, dZ, Gbar, Cbar, total;
+    long packed_total;   /* doubles of the tril-packed form that travels in the all-reduce (tgp_reduce_pack) */
 } TgpReduceLayout;
 
 const char* tgp_last_error(void);
@@ -114,12 +115,66 @@ int tgp_chain_backward(const TgpModel* model, const TgpParams* params, void* ste
                        double gE, double gK, const double* g_dev, void* dZ, void* draw_lengthscale, void* draw_outputscale, void* dm,
                        void* dL_raw, void* dlog_var_noise, void* dtheta, void* stream);
 
+/* The exchange format of the one collective per step.  The reduce buffer holds two (padded) M x M blocks
+ * of which only the lower triangles are populated in TGP_F64 mode (Gbar and dL_S; in TGP_F32 mode the second block, Cbar,
+ * is dense): tgp_reduce_pack gathers [small vector | tril(Gbar) | tril or full second block] into `packed`
+ * (layout.packed_total doubles: 8.5 MB instead of 16.9 MB at M = 1024), ranks sum `packed`, tgp_reduce_unpack scatters it
+ * back for tgp_chain_backward. */
+int tgp_reduce_pack(const TgpModel* model, const double* reduce_buf, double* packed, void* stream);
+int tgp_reduce_unpack(const TgpModel* model, const double* packed, double* reduce_buf, void* stream);
+
 /* Test log-likelihood rows and predictive moments given (mu, v) (sparse_MF_SP.py:637-825; marginal_moments of the
  * three likelihoods).  rowparams: (R, n_mc, n_rowparams) for MC-dropout flows, n_mc = 1 otherwise.
  * bern_std: device scalar, batch-wide std of v (Bernoulli.py:120 defect, kept for parity). */
 int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu, const void* v, const void* Y,
                   const void* rowparams, long R, int n_mc, double y_std, const void* quad_t, const void* quad_w,
                   const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream);
+
+/* ---- single-call interface (the entry points SURVEY.md 8b proposes), thin over the stages above -------------------
+ * A TgpHandle is a HOST object created once per (model description, device, maximum minibatch rows): it remembers the
+ * model, the caller-owned workspace (ONE device allocation of tgp_workspace_bytes(), bound with tgp_bind_workspace and
+ * validated against the size the handle needs) and where the per-step / per-batch / reduce / per-row regions live in
+ * it.  The library still never allocates device memory.  Reference seam: the body of sparse_MF_SP.ELBO
+ * (sparse_MF_SP.py:552-598), its autograd backward (trainer_base.py:341) and test_log_likelihood (:637-825). */
+typedef struct TgpHandle TgpHandle;
+typedef struct TgpBatch {           /* one minibatch (device pointers) */
+    const void* X;                  /* (R, D) */
+    const void* Y;                  /* (R,)   */
+    const void* rowparams;          /* (R, n_rowparams) input-dependent flow parameters, NULL otherwise */
+    long R;
+    double scale;                   /* N / MB_global (sparse_MF_SP.py:626) */
+    const void* quad_t; const void* quad_w;     /* Gauss-Hermite rule (n_quad,), NULL for the closed-form likelihood */
+} TgpBatch;
+typedef struct TgpFwdOut {          /* device pointers; any of ell_rows / mu / v may be NULL */
+    double* terms;                  /* [0] = scale * sum_n ell_n (this rank's rows), [1] = KL */
+    int* status;                    /* 0, or 1-based index of the first non-positive pivot (caller drives the jitter ladder) */
+    void* ell_rows; void* mu; void* v;          /* (R,) each */
+} TgpFwdOut;
+typedef struct TgpGrads {           /* device pointers, raw parameterisation; same meaning as tgp_chain_backward's outputs */
+    void* dZ; void* draw_lengthscale; void* draw_outputscale; void* dm; void* dL_raw; void* dlog_var_noise; void* dtheta;
+    void* drowparams;               /* (R, n_rowparams), NULL when the flow is not input-dependent */
+} TgpGrads;
+/* Sum `count` doubles at `buf` over the ranks of the job, enqueued on `stream` (e.g. ncclAllReduce).  NULL = one rank. */
+typedef int (*TgpAllReduceFn)(double* buf, long count, void* user, void* stream);
+
+size_t tgp_workspace_bytes(const TgpModel* model, long max_rows);
+int tgp_create(const TgpModel* model, long max_rows, TgpHandle** out);
+void tgp_destroy(TgpHandle* h);
+int tgp_bind_workspace(TgpHandle* h, void* workspace, size_t bytes);
+/* forward of one minibatch: prepare (jitter on the K_zz diagonal) + marginals + expected log-likelihood; keeps what the
+ * backward needs in the workspace */
+int tgp_elbo_fwd(TgpHandle* h, const TgpParams* params, const TgpBatch* batch, double jitter, const TgpFwdOut* out,
+                 void* stream);
+/* backward of the last tgp_elbo_fwd on this handle: d(g[0] * ELL + g[1] * KL)/dparam with {g[0], g[1]} read from DEVICE
+ * memory `g_dev`; `allreduce` (may be NULL) is called once, between the batch pass and the replicated O(M^3) chain, on
+ * the tril-packed buffer */
+int tgp_elbo_bwd(TgpHandle* h, const TgpParams* params, const TgpBatch* batch, const double* g_dev,
+                 const TgpGrads* grads, TgpAllReduceFn allreduce, void* user, void* stream);
+/* test log-likelihood rows + predictive moments of one batch (prepare + marginals + tgp_test_rows); refactor = 0 reuses
+ * the factorisation already in the workspace (frozen parameters across evaluation batches) */
+int tgp_test_nll_fwd(TgpHandle* h, const TgpParams* params, const TgpBatch* batch, int refactor, int n_mc, double y_std,
+                     const double* bern_std, void* logp_rows, void* m1, void* m2, void* mu, void* v, int* status,
+                     void* stream);
 
 /* Library options.  TGP_OPT_FUSED_FORWARD (tensor-core mode): 1 = tgp_qf_forward is ONE kernel that generates the K_xz
  * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels.

@@ -90,6 +90,18 @@ def randomise(model, seed):
                 prm.add_(0.2 * torch.randn(prm.shape, generator=g))
 
 
+def randomise_big(model, seed):
+    """P1 state for the BASELINE-size fixtures.  Same distributions as `randomise`, except that the M x M variational
+    factor is drawn from a 17-level grid (0.5 I + 0.05 * k/8, k in -8..8, strictly lower part only; the upper triangle,
+    which the reference masks away at use, is zero) so that the stored parameter compresses to < 1 byte per entry."""
+    randomise(model, seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    M = model.M
+    with torch.no_grad():
+        q = torch.randint(-8, 9, (1, M, M), generator=g).double() / 8.0
+        model.q_U.chol_variational_covar.copy_((0.5 * torch.eye(M).unsqueeze(0) + 0.05 * q).tril())
+
+
 def flow_to_spec(flow, store, X=None, prefix='fl'):
     """Walk a reference CompositeFlow and emit the oracle layer list (JSON-able; arrays go to `store`)."""
     spec = []
@@ -134,7 +146,17 @@ def dropout_off(model):
 ONLY = set(sys.argv[1:])      # optional fixture names: write only these (the others are left untouched on disk)
 
 
-def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=None):
+def projection_basis(M, k=6):
+    """Deterministic (M, k) matrix of exact dyadic rationals (integer hash / 1024 - 0.5): bit-identical on every host."""
+    i = np.arange(M, dtype=np.int64)[:, None]
+    c = np.arange(k, dtype=np.int64)[None, :]
+    return (((i * 2654435761 + (c + 1) * 40503 + i * c * 97) % 1024).astype(np.float64) / 1024.0) - 0.5
+
+
+def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=None, big=False):
+    """big=True (fixtures at the BASELINE sizes M = 1024 / 2048): the M x M gradient of chol_variational_covar is stored
+    as checksums — G R, G^T R for the fixed basis R above, its diagonal and Frobenius norm — instead of 8-32 MB of
+    incompressible doubles (the parameter itself is low-entropy by construction, see randomise_big)."""
     if ONLY and name not in ONLY:
         return
     store = {}
@@ -149,7 +171,15 @@ def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=
     names = []
     for n, prm in model.named_parameters():
         store['param:' + n] = prm.detach().numpy().copy()
-        store['grad:' + n] = (torch.zeros_like(prm) if prm.grad is None else prm.grad).numpy().copy()
+        gr = (torch.zeros_like(prm) if prm.grad is None else prm.grad).numpy().copy()
+        if big and n.endswith('chol_variational_covar'):
+            G = gr[0]
+            R = projection_basis(G.shape[0])
+            store['gradproj:' + n] = np.stack([G @ R, G.T @ R])
+            store['graddiag:' + n] = np.diag(G).copy()
+            store['gradnorm:' + n] = np.linalg.norm(G)
+        else:
+            store['grad:' + n] = gr
         names.append(n)
     with torch.no_grad():
         mu, v = model.marginal_variational_qf_parameters(X, diagonal=True, is_duvenaud=False)
@@ -169,7 +199,7 @@ def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=
     model.set_is_training(True)
     meta = {'name': name, 'likelihood': likelihood, 'N': float(model.N), 'M': int(model.M), 'y_std': y_std,
             'n_quad': int(cg.quad_points), 'flow_train': spec_tr, 'flow_test': spec_te, 'param_names': names,
-            'id_flow': id_flow, 'dtype': 'float64'}
+            'id_flow': id_flow, 'dtype': 'float64', 'big': bool(big)}
     if extra:
         meta.update(extra)
     store['meta'] = np.array(json.dumps(meta))
@@ -272,5 +302,23 @@ def main():
     record('boston_tgp_steptanh154_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
 
 
+def main_big():
+    """Fixtures at the BASELINE.json sizes (configs[3]: D=8, M=1024, StepTanhL(1,3); configs[4]: Bernoulli, D=16, M=2048,
+    SAL(1)); row counts the CPU oracle replays in seconds.  Z = distinct data rows, as in bench.py."""
+    Xs, Ys = synthetic_regression(2048 + 256, 8, 1234)
+    m = build('TGP', Xs, 1024, 5.0e6, StepTanhL(1, 3, add_f0=True), seed=40)
+    randomise_big(m, 41)
+    record('synth_reg_d8_m1024_p1', m, Xs[:2048], Ys[:2048], Xs[2048:], Ys[2048:], 1.3, 'gauss_nonlinear', big=True)
+    Xc, Yc = synthetic_classification(4096, 16, 4321)
+    cg.quad_points = 100
+    m = build('TGP', Xc, 2048, 1.0e6, SAL(1), likelihood=Bernoulli(), seed=42)
+    randomise_big(m, 43)
+    record('synth_clf_d16_m2048_p1', m, Xc[:1024], Yc[:1024], Xc[1024:1152], Yc[1024:1152], 1.0, 'bernoulli', big=True)
+
+
 if __name__ == '__main__':
-    main()
+    if 'BIG' in ONLY:
+        ONLY.discard('BIG')
+        main_big()
+    else:
+        main()

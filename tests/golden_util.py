@@ -9,9 +9,13 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-def golden_names():
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
-                  if not os.path.basename(f).startswith('traj_'))
+def golden_names(big=None):
+    """Fixture names; big=False / True selects the small fixtures / the two at the BASELINE.json sizes (M = 1024, 2048)."""
+    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
+                   if not os.path.basename(f).startswith('traj_'))
+    if big is None:
+        return names
+    return [n for n in names if (('_m1024_' in n or '_m2048_' in n) == big)]
 
 
 def trajectory_names():
@@ -71,6 +75,8 @@ class Golden:
         g = {}
         names = self.meta['param_names']
         for n in names:
+            if 'grad:' + n not in self.z.files:      # BASELINE-size fixtures keep the M x M gradient as checksums
+                continue
             a = self.t('grad:' + n)
             if n == 'Z':
                 g['Z'] = a[0]
@@ -100,6 +106,30 @@ class Golden:
             assert len(keys) == len(vals), (keys, flow_names)
             g.update(dict(zip(keys, vals)))
         return g
+
+
+    def grad_errors(self, grads):
+        """L2-relative error of every gradient in `grads` (keyed like `ref_grads`) against the reference's.  For the
+        BASELINE-size fixtures the M x M gradient of chol_variational_covar is checked through the stored checksums
+        (G R, G^T R for oracle/make_golden.projection_basis, the diagonal and the Frobenius norm)."""
+        errs = {k: rel_err(torch.as_tensor(grads[k]).detach().cpu(), gr) for k, gr in self.ref_grads().items()}
+        key = [n for n in self.meta['param_names'] if n.endswith('chol_variational_covar')][0]
+        if 'gradproj:' + key in self.z.files:
+            G = torch.as_tensor(grads['L_raw']).detach().cpu().double()
+            R = torch.tensor(projection_basis(G.shape[0]))
+            proj = self.t('gradproj:' + key)
+            errs['L_raw.GR'] = rel_err(G @ R, proj[0])
+            errs['L_raw.GtR'] = rel_err(G.t() @ R, proj[1])
+            errs['L_raw.diag'] = rel_err(torch.diagonal(G), self.t('graddiag:' + key))
+            errs['L_raw.norm'] = rel_err(G.norm(), self.t('gradnorm:' + key))
+        return errs
+
+
+def projection_basis(M, k=6):
+    """Same matrix as oracle/make_golden.projection_basis (exact dyadic rationals, identical on every host)."""
+    i = np.arange(M, dtype=np.int64)[:, None]
+    c = np.arange(k, dtype=np.int64)[None, :]
+    return (((i * 2654435761 + (c + 1) * 40503 + i * c * 97) % 1024).astype(np.float64) / 1024.0) - 0.5
 
 
 def rel_err(a, b):

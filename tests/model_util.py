@@ -19,7 +19,7 @@ def build_from_golden(g, device):
     M, D = meta['M'], X.shape[1]
     K = instance_kernel('scale_rbf', ard_num_dim=D, num_multioutput=1, kernel_is_shared=False,
                         init_params={'length_scale': 2.0, 'kernel_scale': 2.0, 'noisy_variance': 1e-6})
-    Z = X[:M].clone()
+    Z = torch.tensor(np.asarray(g.z['param:Z']), dtype=torch.float64)[0].clone()      # placeholder of the right shape
     ip = {'variational_distribution': {'variance_scale': 1e-5, 'mean_scale': 0.0}}
     lik_kind = meta['likelihood']
     if lik_kind == 'gauss_linear':

@@ -32,9 +32,13 @@ def _worker(rank, world, port, ret):
     ell = scale * O.ell_rows(mu, v, Y[sl], p, g.meta['likelihood'], g.meta['n_quad']).sum()
     grads = torch.autograd.grad(ell, list(leaves.values()), allow_unused=True)
     grads = [torch.zeros_like(t) if gr is None else gr for t, gr in zip(leaves.values(), grads)]
-    buf = D.pack([ell.detach().reshape(1)] + grads)
-    D.allreduce_sum_(buf)                                   # the one collective of the step
-    parts = D.unpack(buf, [ell.detach().reshape(1)] + grads)
+    like = [ell.detach().reshape(1)] + grads
+    buf = torch.cat([t.reshape(-1) for t in like])
+    dist.all_reduce(buf)                                    # the one collective of the step
+    parts, o = [], 0
+    for t in like:
+        parts.append(buf[o:o + t.numel()].reshape(t.shape))
+        o += t.numel()
     if rank == 0:
         ret['ell'] = parts[0].clone()
         ret['grads'] = {k: t.clone() for k, t in zip(leaves.keys(), parts[1:])}
@@ -72,3 +76,37 @@ def test_shard_bounds_cover_ragged_batches():
             b = D.shard_bounds(n, w)
             assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(w))
             assert max(b[i + 1] - b[i] for i in range(w)) - min(b[i + 1] - b[i] for i in range(w)) <= 1
+
+
+def _mlp_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tgp.pytorch_b200 import dist as D
+    from tgp.pytorch_b200 import functional as Fn
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.Tanh(), torch.nn.Linear(6, 1)).double()
+    X = torch.randn(37, 4, dtype=torch.float64)
+    w = torch.randn(37, dtype=torch.float64)
+    sl = D.local_slice(37, rank, world)
+    out = Fn.synced_module_call(net, X[sl]).squeeze(-1)          # product path: rank-local rows, gradients summed over ranks
+    (out * w[sl]).sum().backward()
+    with Fn.local_only():                                        # yardstick: the whole batch on this rank, no collective
+        ref = [p.grad.clone() for p in net.parameters()]
+        for p in net.parameters():
+            p.grad = None
+        (Fn.synced_module_call(net, X).squeeze(-1) * w).sum().backward()
+        full = [p.grad.clone() for p in net.parameters()]
+    ret[rank] = max(float((a - b).abs().max()) for a, b in zip(ref, full))
+    dist.destroy_process_group()
+
+
+def test_flow_mlp_gradients_are_summed_over_ranks():
+    """ID_TGP under row sharding: the flow MLPs see rank-local rows; `functional.synced_module_call` must
+    deliver the global-batch gradient to every rank."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_mlp_worker, args=(world, 29547, ret), nprocs=world, join=True)
+    assert all(ret[r] < 1e-13 for r in range(world)), dict(ret)

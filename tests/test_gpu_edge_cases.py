@@ -8,6 +8,7 @@ from oracle import tgp_oracle as O
 from tests.golden_util import rel_err
 
 pytestmark = pytest.mark.gpu
+EDGE_TOL = 1e-10      # north_star's FP64 tolerance, values and gradients alike (measured: see profiles/r02_parity_residuals.json)
 DEV = 'cuda:0'
 
 
@@ -58,7 +59,9 @@ def _cuda_vs_oracle(X, y, p, N, lik='gauss_nonlinear', nq=30, compute='f64'):
 def test_shapes_around_tile_and_block_boundaries(R, M, D):
     X, y, p = _problem(R, M, D, seed=R * 7 + M * 3 + D)
     err = _cuda_vs_oracle(X, y, p, N=10.0 * R)
-    bad = {k: e for k, e in err.items() if not e < 1e-8}
+    from tests.conftest import record_residuals
+    record_residuals('edge_shapes', err)
+    bad = {k: e for k, e in err.items() if not e < EDGE_TOL}
     assert not bad, (bad, err)
 
 
@@ -117,7 +120,7 @@ def test_two_output_model_matches_sum_of_single_output_oracles(shared):
         gZ.append(gr['Z'])
     assert rel_err(ELBO.detach().cpu(), total) < 1e-10
     ref_gZ = (gZ[0] + gZ[1]).unsqueeze(0) if shared else torch.stack(gZ)
-    assert rel_err(model.Z.grad.cpu(), ref_gZ) < 1e-8
+    assert rel_err(model.Z.grad.cpu(), ref_gZ) < EDGE_TOL
 
 
 @pytest.mark.parametrize('chunk', [128, 384])
@@ -133,6 +136,8 @@ def test_batch_contractions_in_several_ragged_row_chunks(chunk):
         err = _cuda_vs_oracle(X, y, p, N=25000.0)
     finally:
         _lib.check(lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 32768), 'tgp_set_option')
-    bad = {k: e for k, e in err.items() if not e < 1e-8}
+    from tests.conftest import record_residuals
+    record_residuals('edge_row_chunks', err)
+    bad = {k: e for k, e in err.items() if not e < EDGE_TOL}
     assert not bad, (bad, err)
     assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 1) != 0            # refused: below one GEMM tile

@@ -15,7 +15,7 @@ DEV = 'cuda:0'
 
 def _tols(g):
     bern = g.meta['likelihood'] == 'bernoulli'
-    return (1e-7 if bern else 1e-10), (1e-6 if bern else 1e-8)
+    return (1e-7 if bern else 1e-10), (1e-6 if bern else 1e-10)      # Bernoulli: tests/test_bernoulli_conditioning.py
 
 
 @pytest.mark.parametrize('name', golden_names())
@@ -39,6 +39,10 @@ def test_model_elbo_and_named_gradients(name):
         return
     worst = {}
     for n, prm in model.named_parameters():
+        if 'grad:' + n not in g.z.files:       # BASELINE-size fixtures: the M x M gradient is stored as checksums
+            errs = g.grad_errors({'L_raw': -prm.grad.detach()[0]})
+            worst.update({k: e for k, e in errs.items() if k.startswith('L_raw.')})
+            continue
         ref = -g.t('grad:' + n)
         got = torch.zeros_like(ref) if prm.grad is None else prm.grad.detach().cpu().reshape(ref.shape)
         if float(ref.norm()) == 0.0:
@@ -46,6 +50,8 @@ def test_model_elbo_and_named_gradients(name):
             assert float(got.norm()) < 1e-12 * abs(float(g.t('ELBO'))), n
             continue
         worst[n] = rel_err(got, ref)
+    from tests.conftest import record_residuals
+    record_residuals('model_api:' + name, worst)
     bad = {k: e for k, e in worst.items() if not e < gtol}
     assert not bad, bad
 

@@ -1,8 +1,10 @@
 """GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the golden fixtures.
 
-Tolerances: FP64 path, L2-relative 1e-10 on ELBO / ELL / KLD / per-row terms / marginals, 1e-9 on gradients of
-well-conditioned fixtures (north_star: 1e-10; the reference's own cholesky_solve formulation carries ~cond(Kzz)*eps
-of forward error), checked per tensor.
+Tolerances (north_star: 1e-10 in FP64), L2-relative per tensor: 1e-10 on ELBO / ELL / per-row terms / mu / every
+gradient, 1e-9 on v (v = s - |a|^2 + |b|^2 cancels; the reference's own cholesky_solve form carries ~cond(K_zz) eps),
+1e-12 on KLD.  Exceptions, each with its measured reason: the Bernoulli fixtures (GRAD_TOL_BERNOULLI below and
+tests/test_bernoulli_conditioning.py) and the singular-K_zz jitter fixture.  The fixtures include two recorded at
+the BASELINE.json sizes (M = 1024 / D = 8 / StepTanhL(1,3) and M = 2048 / D = 16 / Bernoulli / SAL(1)).
 """
 import pytest
 import torch
@@ -12,6 +14,10 @@ from tests.golden_util import Golden, golden_names, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
+# Bernoulli ELL: log(1 - Phi(g)) is formed by cancellation in the reference (BCELoss of the probit), so the result is
+# conditioned like 1 / (1 - Phi): tests/test_bernoulli_conditioning.py measures, against a 50-digit evaluation, that the
+# reference's own FP64 result is only good to ~1e-8 there; two correct FP64 implementations cannot agree better.
+GRAD_TOL_BERNOULLI = 1e-6
 
 
 def _gemm_ref(A, B, al, bl, M, N, K):
@@ -138,12 +144,22 @@ def test_elbo_against_reference_fixture(name):
     lik, nq = g.meta['likelihood'], g.meta['n_quad']
     rows = O.elbo(g.t('X'), g.t('Y').view(-1), p, g.meta['N'], lik, nq)[3]
     assert rel_err(out['rows'].cpu(), rows) < (1e-6 if lik == 'bernoulli' else tol)
-    ref = g.ref_grads()
-    worst = {}
-    for k, gr in ref.items():
-        worst[k] = rel_err(out['grads'][k].detach().cpu(), gr)
-    bad = {k: e for k, e in worst.items() if not e < (1e-6 if g.meta['likelihood'] == 'bernoulli' else 1e-8)}
+    worst = g.grad_errors(out['grads'])
+    from tests.conftest import record_residuals
+    record_residuals('fixture:' + name, dict(worst, ELBO=rel_err(out['ELBO'].cpu(), g.t('ELBO')), mu=rel_err(out['mu'].cpu(), g.t('mu')),
+                                             v=rel_err(out['v'].cpu(), g.t('v')), rows=rel_err(out['rows'].cpu(), rows)))
+    if g.meta.get('expects_jitter'):
+        gtol = 1e-6                  # K_zz singular to working precision: the solve amplifies the 1e-8 jitter's round-off
+    else:
+        gtol = GRAD_TOL_BERNOULLI if lik == 'bernoulli' else 1e-10
+    bad = {k: e for k, e in worst.items() if not e < gtol}
     assert not bad, (bad, worst)
+    if g.meta.get('big'):
+        # BASELINE-size fixtures store the M x M gradient as checksums: compare it entry-wise with the oracle (which the
+        # CPU suite pins to the same checksums), evaluated here on the host
+        og = O.elbo_and_grads(g.t('X'), g.t('Y').view(-1), p, g.meta['N'], lik, nq)[4]
+        assert rel_err(out['grads']['L_raw'].cpu(), og['L_raw']) < gtol
+        assert rel_err(out['grads']['Z'].cpu(), og['Z']) < gtol
 
 
 def test_jitter_ladder_matches_reference():

@@ -34,7 +34,25 @@ class TgpParams(C.Structure):
 
 class TgpReduceLayout(C.Structure):
     _fields_ = [(n, C.c_long) for n in ('ell_sum', 'dlogvar', 'dos', 'dls', 'dtheta', 'dm', 'dZ', 'Gbar', 'Cbar',
-                                        'total')]
+                                        'total', 'packed_total')]
+
+
+class TgpBatch(C.Structure):
+    _fields_ = [('X', C.c_void_p), ('Y', C.c_void_p), ('rowparams', C.c_void_p), ('R', C.c_long), ('scale', C.c_double),
+                ('quad_t', C.c_void_p), ('quad_w', C.c_void_p)]
+
+
+class TgpFwdOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('terms', 'status', 'ell_rows', 'mu', 'v')]
+
+
+class TgpGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('dZ', 'draw_lengthscale', 'draw_outputscale', 'dm', 'dL_raw', 'dlog_var_noise',
+                                          'dtheta', 'drowparams')]
+
+
+# int (*TgpAllReduceFn)(double* buf, long count, void* user, void* stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p)
 
 
 # name -> (restype, argtypes); the exported-symbol test walks this table against include/tgp_b200.h
@@ -54,6 +72,15 @@ SIGNATURES = {
                                 _P, _P]),
     'tgp_test_rows': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _P, _L, _I, _D, _P, _P, _P, _P, _P,
                            _P, _P]),
+    'tgp_reduce_pack': (_I, [C.POINTER(TgpModel), _P, _P, _P]),
+    'tgp_reduce_unpack': (_I, [C.POINTER(TgpModel), _P, _P, _P]),
+    'tgp_workspace_bytes': (C.c_size_t, [C.POINTER(TgpModel), _L]),
+    'tgp_create': (_I, [C.POINTER(TgpModel), _L, C.POINTER(_P)]),
+    'tgp_destroy': (None, [_P]),
+    'tgp_bind_workspace': (_I, [_P, _P, C.c_size_t]),
+    'tgp_elbo_fwd': (_I, [_P, C.POINTER(TgpParams), C.POINTER(TgpBatch), _D, C.POINTER(TgpFwdOut), _P]),
+    'tgp_elbo_bwd': (_I, [_P, C.POINTER(TgpParams), C.POINTER(TgpBatch), _P, C.POINTER(TgpGrads), ALLREDUCE_FN, _P, _P]),
+    'tgp_test_nll_fwd': (_I, [_P, C.POINTER(TgpParams), C.POINTER(TgpBatch), _I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P]),
     'tgp_set_option': (_I, [_I, _I]),
     'tgp_launch_count': (_L, []),
     'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),

@@ -47,6 +47,20 @@ __device__ __forceinline__ T warp_max(T v) {
 
 __host__ __device__ inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per DEVICE: one-time kernel configuration is tracked per (site, device), so that a second GPU
+// used from the same process gets its own opt-in to large dynamic shared memory.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // softplus and its derivative as torch.nn.functional.softplus (beta=1, threshold=20) evaluates them
 __device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
 __device__ __forceinline__ double sigmoid_d(double x) { return x > 20.0 ? 1.0 : 1.0 / (1.0 + exp(-x)); }

@@ -365,8 +365,8 @@ inline int gemm_f64(const GemmArgs& g, cudaStream_t st) {
     if (g.splitk > 1 && (g.batch != 1 || g.beta != 1.0)) return set_error(-3, "split-k GEMM needs batch == 1 and beta == 1");
     dim3 grid((unsigned)cdiv(g.M, GBM), (unsigned)cdiv(g.N, GBN), (unsigned)(g.splitk > 1 ? g.splitk : g.batch));
     if (grid.y > 65535) return set_error(-3, "too many column tiles");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         auto setup = [](const void* f) {
             cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
             cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // room for GEMM_CTAS_PER_SM CTAs
@@ -375,7 +375,6 @@ inline int gemm_f64(const GemmArgs& g, cudaStream_t st) {
         setup((const void*)gemm_f64_kernel<0, 1>);
         setup((const void*)gemm_f64_kernel<1, 0>);
         setup((const void*)gemm_f64_kernel<1, 1>);
-        attr_set = true;
     }
     const bool timed = g_gemm_timer.enabled;
     if (timed) g_gemm_timer.begin(g.tag, st);

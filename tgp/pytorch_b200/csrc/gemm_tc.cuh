@@ -307,8 +307,29 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D K-major FP32 matrix (rows x cols, leading dimension ld floats, ld % 4 == 0), box = 32 floats x box_rows, 128B swizzle
+// 2D K-major FP32 matrix (rows x cols, leading dimension ld floats, ld % 4 == 0), box = 32 floats x box_rows, 128B swizzle.
+// Encoded descriptors are cached (the step re-uses the same workspaces every iteration, so after the first step every
+// launch finds its four maps here instead of calling into the driver).
+struct MapKey { const float* base; long rows, cols, ld; int box_rows; };
+struct MapCache {
+    static constexpr int N = 64;
+    MapKey key[N]; CUtensorMap map[N]; int used = 0, next = 0;
+    const CUtensorMap* find(const MapKey& k) const {
+        for (int i = 0; i < used; ++i)
+            if (key[i].base == k.base && key[i].rows == k.rows && key[i].cols == k.cols && key[i].ld == k.ld && key[i].box_rows == k.box_rows)
+                return &map[i];
+        return nullptr;
+    }
+    void put(const MapKey& k, const CUtensorMap& m) {
+        const int i = used < N ? used++ : (next = (next + 1) % N);
+        key[i] = k; map[i] = m;
+    }
+};
+inline MapCache& map_cache() { static MapCache c; return c; }
+
 inline int make_map(CUtensorMap* map, const float* base, long rows, long cols, long ld, int box_rows) {
+    const MapKey mk{base, rows, cols, ld, box_rows};
+    if (const CUtensorMap* hit = map_cache().find(mk)) { *map = *hit; return 0; }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(-101, "cuTensorMapEncodeTiled not available from the driver");
     if ((ld & 3) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(-2, "TMA operand must be 16-byte aligned with ld % 4 == 0");
@@ -320,6 +341,7 @@ inline int make_map(CUtensorMap* map, const float* base, long rows, long cols, l
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(-102, "cuTensorMapEncodeTiled failed");
+    map_cache().put(mk, *map);
     return 0;
 }
 
@@ -332,11 +354,8 @@ inline int gemm_tf32x3(const Operand& A, const Operand& B, Params p, cudaStream_
     TGP_TRY(make_map(&mAl, A.lo, A.rows, A.cols, A.ld, BM));
     TGP_TRY(make_map(&mB, B.hi, B.rows, B.cols, B.ld, BN));
     TGP_TRY(make_map(&mBl, B.lo, B.rows, B.cols, B.ld, BN));
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        attr = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     const long tiles = (long)cdiv(p.Mrows, BM) * cdiv(p.Ncols, BN) * (p.splitk > 1 ? p.splitk : 1);
     int sms = 148;
     const int grid = (int)(tiles < sms ? tiles : sms);

@@ -119,11 +119,8 @@ inline int launch_rbf(const double* X, const double* Zs, const double* ls, const
 #undef TGP_RBF
     const size_t smem = (size_t)(RBF_TR + RBF_TC) * (D + 1) * sizeof(double);
     if (smem > 200 * 1024) return set_error(-2, "input dimension too large for the RBF tile kernel");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024)       // generic kernel for D > 64 only: set per call (per-device attribute, rare path)
         cudaFuncSetAttribute(k_rbf_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
     k_rbf_tile<<<grid, RBF_THREADS, smem, st>>>(X, Zs, ls, os, R, M, D, x_scaled, out, ldo, Rp, Mp, jitter);
     return check_launch("k_rbf_tile");
 }
@@ -320,11 +317,8 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
                        bool need_C, cudaStream_t st) {
     const int M = v.M, Mp = v.Mp, D = v.D, NB = POTRF_NB, nb = Mp / NB;
     const size_t mm = (size_t)Mp * Mp;
-    static bool potrf_attr = false;
-    if (!potrf_attr) {
-        cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
-        potrf_attr = true;
-    }
+    static PerDeviceOnce potrf_once;
+    if (potrf_once.first()) cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
     cudaMemsetAsync(status, 0, sizeof(int), st);
     cudaMemsetAsync(v.kl3, 0, 8 * sizeof(double), st);
     cudaMemsetAsync(v.L, 0, 2 * mm * sizeof(double), st);          // L and Linv are contiguous

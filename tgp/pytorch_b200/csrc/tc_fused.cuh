@@ -287,12 +287,11 @@ inline int fwd_fused(const Operand& W, const FusedFwdParams& p, cudaStream_t st)
     CUtensorMap mB, mBl;
     TGP_TRY(make_map(&mB, W.hi, W.rows, W.cols, W.ld, BN));
     TGP_TRY(make_map(&mBl, W.lo, W.rows, W.cols, W.ld, BN));
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(fwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
         cudaFuncSetAttribute(fwd_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
         cudaFuncSetAttribute(fwd_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
-        attr = true;
     }
     const int tiles = (p.R + BM - 1) / BM;
     const int grid = tiles < 148 ? tiles : 148;

@@ -50,7 +50,33 @@ inline TgpReduceLayout reduce_layout(const TgpModel* md) {
     l.Gbar = l.dZ + even((long)md->M * md->D);
     l.Cbar = l.Gbar + Mp * Mp;
     l.total = l.Cbar + Mp * Mp;
+    const long M = md->M, tri = M * (M + 1) / 2;
+    l.packed_total = l.Gbar + tri + (md->dtype == TGP_F32 ? M * M : tri);
     return l;
+}
+
+// reduce buffer <-> tril-packed exchange buffer (one CTA per matrix row; dir 0 = pack, 1 = unpack)
+__global__ void __launch_bounds__(256) k_reduce_pack(double* __restrict__ rb, double* __restrict__ packed, long small, long offG,
+                                                     long offC, int M, long Mp, int second_dense, int dir) {
+    const long tri = (long)M * (M + 1) / 2;
+    const int r = blockIdx.x;
+    if (r == M) {                                   // the small leading vector
+        for (long i = threadIdx.x; i < small; i += blockDim.x) { if (dir) rb[i] = packed[i]; else packed[i] = rb[i]; }
+        return;
+    }
+    double* pg = packed + small + (long)r * (r + 1) / 2;
+    double* g = rb + offG + (long)r * Mp;
+    for (int c = threadIdx.x; c <= r; c += blockDim.x) { if (dir) g[c] = pg[c]; else pg[c] = g[c]; }
+    double* pc = packed + small + tri + (second_dense ? (long)r * M : (long)r * (r + 1) / 2);
+    double* cc = rb + offC + (long)r * Mp;
+    const int nc = second_dense ? M : r + 1;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) { if (dir) cc[c] = pc[c]; else pc[c] = cc[c]; }
+}
+
+inline int reduce_pack(const TgpModel* md, double* rb, double* packed, int dir, cudaStream_t st) {
+    const TgpReduceLayout l = reduce_layout(md);
+    k_reduce_pack<<<md->M + 1, 256, 0, st>>>(rb, packed, l.Gbar, l.Gbar, l.Cbar, md->M, pad_M(md->M), md->dtype == TGP_F32, dir);
+    return check_launch("k_reduce_pack");
 }
 
 inline int validate(const TgpModel* md) {
@@ -354,6 +380,155 @@ int tgp_test_rows(const TgpModel* md, const TgpParams* p, const void* mu, const 
     fill_flow(a.flow, md);
     k_row_test<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(a);
     return check_launch("k_row_test");
+}
+
+int tgp_reduce_pack(const TgpModel* md, const double* reduce_buf, double* packed, void* stream) {
+    TGP_TRY(validate(md));
+    if (!reduce_buf || !packed) return set_error(-1, "NULL argument to tgp_reduce_pack");
+    return reduce_pack(md, const_cast<double*>(reduce_buf), packed, 0, (cudaStream_t)stream);
+}
+
+int tgp_reduce_unpack(const TgpModel* md, const double* packed, double* reduce_buf, void* stream) {
+    TGP_TRY(validate(md));
+    if (!reduce_buf || !packed) return set_error(-1, "NULL argument to tgp_reduce_unpack");
+    return reduce_pack(md, reduce_buf, const_cast<double*>(packed), 1, (cudaStream_t)stream);
+}
+
+// ---- single-call interface ------------------------------------------------------------------------------------------
+struct TgpHandle {
+    TgpModel model;
+    long max_rows;
+    size_t need_bytes, bound_bytes;
+    // regions of the bound workspace
+    char* base;
+    size_t off_step, off_batch, off_reduce, off_packed, off_rows;
+    long last_R;                 // rows of the last forward (the backward must match)
+    bool prepared;
+};
+
+namespace tgp {
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+inline size_t row_region_bytes(long max_rows) { return align256((size_t)(max_rows + 16) * sizeof(double)); }
+inline void handle_layout(TgpHandle* h) {
+    const TgpModel* md = &h->model;
+    const TgpReduceLayout l = reduce_layout(md);
+    size_t o = 0;
+    h->off_step = o;   o += align256(tgp_step_workspace_bytes(md));
+    h->off_batch = o;  o += align256(tgp_batch_workspace_bytes(md, h->max_rows));
+    h->off_reduce = o; o += align256((size_t)l.total * sizeof(double));
+    h->off_packed = o; o += align256((size_t)l.packed_total * sizeof(double));
+    h->off_rows = o;   o += row_region_bytes(h->max_rows) * 5;   // mu, v, g_mu, g_v, [8 scratch doubles | ell_rows]
+    h->need_bytes = o;
+}
+inline double* row_region(TgpHandle* h, int i) {
+    return reinterpret_cast<double*>(h->base + h->off_rows + (size_t)i * row_region_bytes(h->max_rows));
+}
+__global__ void k_fwd_terms(const double* __restrict__ rb_ell, const double* __restrict__ kl, double scale, double* __restrict__ terms) {
+    terms[0] = scale * rb_ell[0];
+    terms[1] = kl[0];
+}
+inline int handle_ready(TgpHandle* h, const TgpBatch* b) {
+    if (!h) return set_error(-1, "handle is NULL");
+    if (!h->base) return set_error(-1, "no workspace bound: call tgp_bind_workspace first");
+    if (!b || b->R < 0 || b->R > h->max_rows) return set_error(-1, "batch rows exceed the max_rows the handle was created for");
+    return 0;
+}
+}  // namespace tgp
+
+size_t tgp_workspace_bytes(const TgpModel* md, long max_rows) {
+    if (validate(md) || max_rows < 1) return 0;
+    TgpHandle h{};
+    h.model = *md; h.max_rows = max_rows;
+    handle_layout(&h);
+    return h.need_bytes;
+}
+
+int tgp_create(const TgpModel* md, long max_rows, TgpHandle** out) {
+    TGP_TRY(validate(md));
+    if (!out || max_rows < 1) return set_error(-1, "tgp_create: out is NULL or max_rows < 1");
+    TgpHandle* h = new TgpHandle();
+    h->model = *md; h->max_rows = max_rows; h->base = nullptr; h->bound_bytes = 0; h->last_R = -1; h->prepared = false;
+    handle_layout(h);
+    *out = h;
+    return 0;
+}
+
+void tgp_destroy(TgpHandle* h) { delete h; }
+
+int tgp_bind_workspace(TgpHandle* h, void* workspace, size_t bytes) {
+    if (!h || !workspace) return set_error(-1, "NULL argument to tgp_bind_workspace");
+    handle_layout(h);            // the row-chunk option may have changed since tgp_create
+    if (bytes < h->need_bytes) return set_error(-1, "workspace smaller than tgp_workspace_bytes()");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return set_error(-2, "workspace must be 256-byte aligned");
+    h->base = reinterpret_cast<char*>(workspace); h->bound_bytes = bytes; h->prepared = false; h->last_R = -1;
+    return 0;
+}
+
+int tgp_elbo_fwd(TgpHandle* h, const TgpParams* p, const TgpBatch* b, double jitter, const TgpFwdOut* out, void* stream) {
+    TGP_TRY(handle_ready(h, b));
+    if (!p || !out || !out->terms || !out->status) return set_error(-1, "NULL argument to tgp_elbo_fwd");
+    const TgpModel* md = &h->model;
+    cudaStream_t st = (cudaStream_t)stream;
+    const TgpReduceLayout l = reduce_layout(md);
+    double* rb = reinterpret_cast<double*>(h->base + h->off_reduce);
+    double* kl = row_region(h, 4);               // 8 scratch doubles at the head of the fifth row region
+    void* step_ws = h->base + h->off_step;
+    void* batch_ws = h->base + h->off_batch;
+    double* mu = out->mu ? (double*)out->mu : row_region(h, 0);
+    double* v = out->v ? (double*)out->v : row_region(h, 1);
+    double* rows = out->ell_rows ? (double*)out->ell_rows : row_region(h, 4) + 8;
+    cudaMemsetAsync(rb, 0, (size_t)l.total * sizeof(double), st);
+    TGP_TRY(tgp_prepare(md, p, jitter, step_ws, kl, out->status, stream));
+    h->prepared = true;
+    TGP_TRY(tgp_qf_forward(md, step_ws, batch_ws, b->X, b->R, mu, v, stream));
+    TGP_TRY(tgp_ell_forward(md, p, mu, v, b->Y, b->rowparams, b->R, b->scale, b->quad_t, b->quad_w, 1, rows, row_region(h, 2),
+                            row_region(h, 3), nullptr, rb, stream));
+    k_fwd_terms<<<1, 1, 0, st>>>(rb + l.ell_sum, kl, b->scale, out->terms);
+    h->last_R = b->R;
+    return check_launch("k_fwd_terms");
+}
+
+int tgp_elbo_bwd(TgpHandle* h, const TgpParams* p, const TgpBatch* b, const double* g_dev, const TgpGrads* g,
+                 TgpAllReduceFn allreduce, void* user, void* stream) {
+    TGP_TRY(handle_ready(h, b));
+    if (!p || !g || !g_dev) return set_error(-1, "NULL argument to tgp_elbo_bwd");
+    if (h->last_R != b->R) return set_error(-1, "tgp_elbo_bwd must follow tgp_elbo_fwd on the same batch");
+    const TgpModel* md = &h->model;
+    if (md->n_rowparams > 0)
+        return set_error(-1, "input-dependent flows: use the staged entry points (drowparams flows back to the caller's MLP)");
+    const TgpReduceLayout l = reduce_layout(md);
+    double* rb = reinterpret_cast<double*>(h->base + h->off_reduce);
+    void* step_ws = h->base + h->off_step;
+    TGP_TRY(tgp_qf_backward(md, p, step_ws, h->base + h->off_batch, b->X, b->R, row_region(h, 2), row_region(h, 3), rb, stream));
+    if (allreduce) {
+        double* packed = reinterpret_cast<double*>(h->base + h->off_packed);
+        TGP_TRY(tgp_reduce_pack(md, rb, packed, stream));
+        if (allreduce(packed, l.packed_total, user, stream) != 0) return set_error(-103, "the all-reduce callback failed");
+        TGP_TRY(tgp_reduce_unpack(md, packed, rb, stream));
+    }
+    h->last_R = -1;
+    return tgp_chain_backward(md, p, step_ws, rb, 0.0, 0.0, g_dev, g->dZ, g->draw_lengthscale, g->draw_outputscale, g->dm,
+                              g->dL_raw, g->dlog_var_noise, g->dtheta, stream);
+}
+
+int tgp_test_nll_fwd(TgpHandle* h, const TgpParams* p, const TgpBatch* b, int refactor, int n_mc, double y_std,
+                     const double* bern_std, void* logp_rows, void* m1, void* m2, void* mu_out, void* v_out, int* status,
+                     void* stream) {
+    TGP_TRY(handle_ready(h, b));
+    if (!p || !logp_rows || !m1 || !m2) return set_error(-1, "NULL argument to tgp_test_nll_fwd");
+    const TgpModel* md = &h->model;
+    void* step_ws = h->base + h->off_step;
+    if (refactor || !h->prepared) {
+        if (!status) return set_error(-1, "status required when the factorisation is (re)computed");
+        TGP_TRY(tgp_prepare(md, p, 0.0, step_ws, row_region(h, 4), status, stream));
+        h->prepared = true;
+    }
+    double* mu = mu_out ? (double*)mu_out : row_region(h, 0);
+    double* v = v_out ? (double*)v_out : row_region(h, 1);
+    TGP_TRY(tgp_qf_forward(md, step_ws, h->base + h->off_batch, b->X, b->R, mu, v, stream));
+    h->last_R = -1;
+    return tgp_test_rows(md, p, mu, v, b->Y, b->rowparams, b->R, n_mc, y_std, b->quad_t, b->quad_w, bern_std, logp_rows, m1,
+                         m2, stream);
 }
 
 long tgp_launch_count(void) { return g_launch_count; }

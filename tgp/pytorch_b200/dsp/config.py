@@ -41,6 +41,9 @@ compute = 'f64'                # 'f64': FP64 DMMA path (parity mode, what main.p
 cache_factorisation_in_eval = True   # consecutive no-grad evaluations with unchanged parameters reuse L, L^-1 (the cache
                                      # is keyed on tensor identity + in-place version; mutate parameters through
                                      # `.data` in-place only after set_is_training() / ELBO(), which drop it)
+sync_elbo_in_forward = True     # row-sharded training: True = ELBO() returns the GLOBAL value on every rank (a second, 8-byte
+                                # collective per step); False = it returns this rank's share and the global value is
+                                # read from the one packed all-reduce after backward (sparse_MF_SP.last_global_elbo())
 check_cholesky_status = True    # False: skip the 4-byte status read-back after the factorisation (no host sync)
 
 device = check_device()

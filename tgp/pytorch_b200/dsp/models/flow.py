@@ -185,7 +185,10 @@ class _RowParamMixin:
         return [getattr(self, 'NNets_' + n) for n in self._names]
 
     def _net_outputs(self, X):
-        return [net(X).squeeze(dim=-1) for net in self._nets()]
+        # under row sharding each rank evaluates the MLPs on its own rows: their parameter gradients are summed over
+        # ranks in the backward (functional.synced_module_call); single process: a plain module call
+        from ...functional import synced_module_call
+        return [synced_module_call(net, X).squeeze(dim=-1) for net in self._nets()]
 
     def forward_initializer(self, X):
         if not self.input_dependent:

@@ -46,7 +46,7 @@ class sparse_MF_SP(nn.Module):
         self.likelihood = likelihood
         self.fully_bayesian = be_fully_bayesian
         self.init_params = get_init_params(init_params)
-        self.standard_sampler = td.MultivariateNormal(torch.zeros(1, ).to(cg.device), torch.eye(1).to(cg.device))
+        self._standard_sampler = None     # built on first use (the reference builds it eagerly, sparse_MF_SP.py:96-97)
         self.is_training = True
         self.quad_points = likelihood.quad_points if isinstance(likelihood, GaussianNonLinearMean) else cg.quad_points
         self.quad = GaussHermiteQuadrature1D(self.quad_points)
@@ -59,8 +59,17 @@ class sparse_MF_SP(nn.Module):
         self.l2_regularize = False
         self.global_batch_rows = None     # row-sharded training: rows of the GLOBAL minibatch (default MB * world)
         self._engines = {}
+        self._last = None
 
     # ---- configuration -------------------------------------------------------------------------------------------
+    @property
+    def standard_sampler(self):
+        """N(0, I_1), the reference's attribute of the same name; scale_tril is given explicitly so that constructing it
+        factorises nothing."""
+        if self._standard_sampler is None:
+            self._standard_sampler = td.MultivariateNormal(torch.zeros(1, device=cg.device), scale_tril=torch.eye(1, device=cg.device))
+        return self._standard_sampler
+
     def be_fully_bayesian(self, mode):
         self.fully_bayesian = mode
 
@@ -167,6 +176,13 @@ class sparse_MF_SP(nn.Module):
     def _compute(self):
         return cg.compute if self.Z.dtype == torch.float64 else 'tf32x3'
 
+    def _jitter(self):
+        """(constant jitter, ladder base) of psd_safe_cholesky as the reference configures it: cg.constant_jitter is added
+        to the K_zz diagonal before every factorisation (utils.py:237), cg.global_jitter is the base of the failure
+        ladder (sparse_MF_SP.py:330), defaulting to 1e-8 for float64 and 1e-6 for float32 models (utils.py:258)."""
+        base = cg.global_jitter if cg.global_jitter is not None else (1e-8 if self.Z.dtype == torch.float64 else 1e-6)
+        return (float(cg.constant_jitter) if cg.constant_jitter is not None else 0.0, float(base))
+
     def _rows3(self, X):
         if len(X.shape) == 2:
             X = X.unsqueeze(0).expand(self.out_dim, -1, -1)
@@ -174,11 +190,12 @@ class sparse_MF_SP(nn.Module):
         return X
 
     def _global_scale(self, MB):
+        from ...dist import global_scale
         dist = Fn._world()
         rows = self.global_batch_rows
         if rows is None:
             rows = MB * (dist.get_world_size() if dist is not None else 1)
-        return self.N / rows
+        return global_scale(self.N, rows)
 
     # ---- model computation ---------------------------------------------------------------------------------------
     def marginal_variational_qf_parameters(self, X, diagonal, is_duvenaud, init_Z=None):
@@ -198,7 +215,7 @@ class sparse_MF_SP(nn.Module):
             if not cg.cache_factorisation_in_eval:
                 eng.prepared_key = None
             mu, v = Fn.qf_marginals(eng, X[dy].to(torch.float64).contiguous(), Z, raw_ls, raw_os, m, L_raw,
-                                    cg.check_cholesky_status)
+                                    cg.check_cholesky_status, self._jitter())
             mus.append(mu)
             vs.append(v)
         return torch.stack(mus).unsqueeze(2).to(self.Z.dtype), torch.stack(vs).unsqueeze(2).to(self.Z.dtype)
@@ -235,7 +252,9 @@ class sparse_MF_SP(nn.Module):
             eng = self._engine(dy, layout, Xd.device)
             y = Y[:, dy].to(torch.float64).contiguous()
             ell, kl, _rows_ll, _mu, _v = Fn.elbo_terms(eng, Xd, y, scale, Z, raw_ls, raw_os, m, L_raw, self._noise(dy),
-                                                       theta, rowp, cg.check_cholesky_status)
+                                                       theta, rowp, cg.check_cholesky_status, self._jitter(),
+                                                       cg.sync_elbo_in_forward)
+            self._last = (eng, scale, kl)
             ELL = ELL + ell
             KLD = KLD + kl
         KLD_flow = 0.0
@@ -244,6 +263,14 @@ class sparse_MF_SP(nn.Module):
         ELBO = ELL - KLD - KLD_flow
         out = self.Z.dtype
         return ELBO.to(out), ELL.to(out), (KLD + KLD_flow).to(out)
+
+    def last_global_elbo(self):
+        """Row-sharded training with cg.sync_elbo_in_forward = False: the ELBO over the GLOBAL minibatch of the last step,
+        read (after backward()) from slot 0 of the one all-reduced buffer — no extra collective.  Single-output models."""
+        eng, scale, kl = self._last
+        if eng.last_ell_sum is None:
+            raise RuntimeError('last_global_elbo() is valid after backward() of the last ELBO')
+        return scale * eng.last_ell_sum - kl.detach()
 
     def ELL(self, X, Y, mean, cov):
         """(N/MB) * E_q(f)[log p(y|G(f))] per output from given marginals (Dy,MB,1)."""

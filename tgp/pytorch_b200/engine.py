@@ -76,8 +76,22 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on_device(fn):
+    """Engine methods enqueue on the ENGINE's device: make it current for the call (kernel launches, per-device function
+    attributes and the stream lookup all depend on the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 def _chk(t, name, shape=None):
@@ -99,6 +113,8 @@ class Engine:
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('tgp.pytorch_b200 runs on CUDA devices only (no CPU fallback)')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.M, self.D = int(M), int(D)
         self.likelihood = likelihood
         self.flow = flow_layout
@@ -121,7 +137,9 @@ class Engine:
         self.kl = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._batch_ws = None
-        self._batch_rows = -1
+        self._rb = None
+        self._packed = None
+        self.last_ell_sum = None
         self._params = None
         self._keep = None
         self.generation = 0          # bumped by every prepare(); backward passes check it
@@ -130,14 +148,32 @@ class Engine:
 
     # -- helpers ------------------------------------------------------------------------------------------------
     def batch_ws(self, R):
-        if self._batch_ws is None or self._batch_rows < R:
-            nbytes = self.lib.tgp_batch_workspace_bytes(self.model, R)
+        # the size is asked for on every call: it depends on library options (TGP_OPT_ROW_CHUNK) as well as on R
+        nbytes = self.lib.tgp_batch_workspace_bytes(self.model, R)
+        if self._batch_ws is None or self._batch_ws.numel() < nbytes:
             self._batch_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._batch_rows = R
         return self._batch_ws
 
-    def new_reduce_buffer(self):
-        return torch.zeros(self.layout.total, dtype=torch.float64, device=self.device)
+    def new_reduce_buffer(self, fresh=True):
+        """The packed pre-chain accumulator, zeroed.  fresh=False re-uses one persistent buffer per engine (the training
+        step: its previous contents are dead once the previous backward has been enqueued)."""
+        if fresh:
+            return torch.zeros(self.layout.total, dtype=torch.float64, device=self.device)
+        if self._rb is None:
+            self._rb = torch.empty(self.layout.total, dtype=torch.float64, device=self.device)
+        return self._rb.zero_()
+
+    @_on_device
+    def pack_reduce(self, rb):
+        if self._packed is None:
+            self._packed = torch.empty(self.layout.packed_total, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.tgp_reduce_pack(self.model, _ptr(rb), _ptr(self._packed), _stream(self.device)), 'tgp_reduce_pack')
+        return self._packed
+
+    @_on_device
+    def unpack_reduce(self, packed, rb):
+        _lib.check(self.lib.tgp_reduce_unpack(self.model, _ptr(packed), _ptr(rb), _stream(self.device)), 'tgp_reduce_unpack')
+        return rb
 
     def set_params(self, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta):
         M, D = self.M, self.D
@@ -153,10 +189,11 @@ class Engine:
         self._keep = (Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta)     # keep the storage alive
 
     # -- the C-ABI stages ---------------------------------------------------------------------------------------
+    @_on_device
     def prepare(self, jitter=0.0):
         self.generation += 1
         _lib.check(self.lib.tgp_prepare(self.model, self._params, float(jitter), _ptr(self.step_ws), _ptr(self.kl),
-                                        _ptr(self.status), _stream()), 'tgp_prepare')
+                                        _ptr(self.status), _stream(self.device)), 'tgp_prepare')
         return self.kl, self.status
 
     def status_reader(self):
@@ -180,15 +217,17 @@ class Engine:
             return int(self._status_host[0])
         return read
 
+    @_on_device
     def qf_forward(self, X):
         R = X.shape[0]
         _chk(X, 'X', (R, self.D))
         mu = torch.empty(R, dtype=torch.float64, device=self.device)
         v = torch.empty(R, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.tgp_qf_forward(self.model, _ptr(self.step_ws), _ptr(self.batch_ws(R)), _ptr(X), R, _ptr(mu),
-                                           _ptr(v), _stream()), 'tgp_qf_forward')
+                                           _ptr(v), _stream(self.device)), 'tgp_qf_forward')
         return mu, v
 
+    @_on_device
     def ell_forward(self, mu, v, Y, rowparams, scale, reduce_buf, want_grad=True):
         R = mu.shape[0]
         _chk(mu, 'mu', (R,)); _chk(v, 'v', (R,)); _chk(Y, 'Y', (R,))
@@ -202,16 +241,18 @@ class Engine:
         _lib.check(self.lib.tgp_ell_forward(self.model, self._params, _ptr(mu), _ptr(v), _ptr(Y),
                                             _ptr(rowparams) if nrp else None, R, float(scale), _ptr(self.qt),
                                             _ptr(self.qw), 1 if want_grad else 0, _ptr(ell_rows), _ptr(g_mu), _ptr(g_v),
-                                            _ptr(drow), _ptr(reduce_buf), _stream()), 'tgp_ell_forward')
+                                            _ptr(drow), _ptr(reduce_buf), _stream(self.device)), 'tgp_ell_forward')
         return ell_rows, g_mu, g_v, drow
 
+    @_on_device
     def qf_backward(self, X, g_mu, g_v, reduce_buf):
         R = X.shape[0]
         _chk(g_mu, 'g_mu', (R,)); _chk(g_v, 'g_v', (R,))
         _lib.check(self.lib.tgp_qf_backward(self.model, self._params, _ptr(self.step_ws), _ptr(self.batch_ws(R)),
-                                            _ptr(X), R, _ptr(g_mu), _ptr(g_v), _ptr(reduce_buf), _stream()),
+                                            _ptr(X), R, _ptr(g_mu), _ptr(g_v), _ptr(reduce_buf), _stream(self.device)),
                    'tgp_qf_backward')
 
+    @_on_device
     def chain_backward(self, reduce_buf, gE=1.0, gK=-1.0, g_dev=None):
         M, D, dev = self.M, self.D, self.device
         f64 = torch.float64
@@ -222,10 +263,11 @@ class Engine:
         _lib.check(self.lib.tgp_chain_backward(self.model, self._params, _ptr(self.step_ws), _ptr(reduce_buf), float(gE),
                                                float(gK), _ptr(g_dev), _ptr(out['Z']), _ptr(out['raw_ls']), _ptr(out['raw_os']),
                                                _ptr(out['m']), _ptr(out['L_raw']), _ptr(out['log_var_noise']),
-                                               _ptr(out['theta']) if self.flow.n_theta else None, _stream()),
+                                               _ptr(out['theta']) if self.flow.n_theta else None, _stream(self.device)),
                    'tgp_chain_backward')
         return out
 
+    @_on_device
     def test_rows(self, mu, v, Y, rowparams, n_mc, y_std, bern_std=None):
         R = mu.shape[0]
         _chk(mu, 'mu', (R,)); _chk(v, 'v', (R,)); _chk(Y, 'Y', (R,))
@@ -238,14 +280,15 @@ class Engine:
         m2 = torch.empty(R, dtype=f64, device=self.device)
         _lib.check(self.lib.tgp_test_rows(self.model, self._params, _ptr(mu), _ptr(v), _ptr(Y),
                                           _ptr(rowparams) if nrp else None, R, int(n_mc), float(y_std), _ptr(self.qt),
-                                          _ptr(self.qw), _ptr(bern_std), _ptr(logp), _ptr(m1), _ptr(m2), _stream()),
+                                          _ptr(self.qw), _ptr(bern_std), _ptr(logp), _ptr(m1), _ptr(m2), _stream(self.device)),
                    'tgp_test_rows')
         return logp, m1, m2
 
+    @_on_device
     def export_step(self):
         M = self.M
         L, Li, Cm = (torch.empty(M, M, dtype=torch.float64, device=self.device) for _ in range(3))
-        _lib.check(self.lib.tgp_debug_export_step(self.model, _ptr(self.step_ws), _ptr(L), _ptr(Li), _ptr(Cm), _stream()),
+        _lib.check(self.lib.tgp_debug_export_step(self.model, _ptr(self.step_ws), _ptr(L), _ptr(Li), _ptr(Cm), _stream(self.device)),
                    'tgp_debug_export_step')
         return L, Li, Cm
 

@@ -23,31 +23,47 @@ class NumericalWarning(RuntimeWarning):
     """Stand-in for gpytorch.utils.warnings.NumericalWarning (code/dsp/utils.py:266)."""
 
 
+_LOCAL_ONLY = [False]
+
+
+class local_only:
+    """Context manager: inside it the path behaves as a single rank even when torch.distributed is initialised (no
+    collective is issued) — e.g. to evaluate a whole global minibatch on one rank as the yardstick of a parity check."""
+
+    def __enter__(self):
+        self._old = _LOCAL_ONLY[0]
+        _LOCAL_ONLY[0] = True
+
+    def __exit__(self, *exc):
+        _LOCAL_ONLY[0] = self._old
+
+
 def _world():
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if not _LOCAL_ONLY[0] and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist
     return None
 
 
-def _jitter_ladder(engine, fail, base_jitter=None):
-    """The failure branch of psd_safe_cholesky (code/dsp/utils.py:241-270): NaN check, then jitter 1e-8 * 10^i."""
+def _jitter_ladder(engine, fail, base_jitter=None, constant_jitter=0.0):
+    """The failure branch of psd_safe_cholesky (code/dsp/utils.py:241-270): NaN check, then jitter base * 10^i on top of
+    the constant jitter; base = cg.global_jitter (sparse_MF_SP.py:330) or 1e-8 (1e-6 for float32 models)."""
     Z = engine._keep[0]
     if torch.isnan(Z).any() or torch.isnan(engine._keep[1]).any() or torch.isnan(engine._keep[2]).any():
         raise NanError('cholesky: the kernel matrix has NaN entries')
     jitter = 1e-8 if base_jitter is None else base_jitter
     for i in range(3):
         j = jitter * (10 ** i)
-        kl, status = engine.prepare(j)
+        kl, status = engine.prepare(constant_jitter + j)
         if int(status.item()) == 0:
             warnings.warn('A not p.d., added jitter of %g to the diagonal' % j, NumericalWarning)
             return kl, j
     raise RuntimeError('cholesky: matrix not positive definite after 3 jitter escalations (first bad pivot %d)' % fail)
 
 
-def prepare_then(engine, work, check=True, base_jitter=None):
-    """Reference semantics of psd_safe_cholesky (code/dsp/utils.py:222-270): factorise without jitter; only on failure
-    add 1e-8 * 10^i (FP64), i = 0..2, warning each time; raise after the third failure.
+def prepare_then(engine, work, check=True, base_jitter=None, constant_jitter=0.0):
+    """Reference semantics of psd_safe_cholesky (code/dsp/utils.py:222-270): factorise with cg.constant_jitter only (None =
+    0, :237); on failure add base * 10^i, i = 0..2, warning each time; raise after the third failure.
 
     `work()` enqueues everything that consumes the factorisation.  The 4-byte pivot status is copied to the host on a
     side stream that waits for the factorisation only, and is read AFTER `work()` has been enqueued: the host blocks
@@ -55,7 +71,7 @@ def prepare_then(engine, work, check=True, base_jitter=None):
     always successful) check costs no pipeline bubble; on failure the ladder runs and `work()` is enqueued again on the
     jittered factor.  `check=False` skips the read-back altogether."""
     engine.prepared_key = None
-    kl, status = engine.prepare(0.0)
+    kl, status = engine.prepare(constant_jitter)
     if not check:
         return kl, work()
     read_status = engine.status_reader()        # D2H of the status on a side stream, ordered after prepare only
@@ -63,7 +79,7 @@ def prepare_then(engine, work, check=True, base_jitter=None):
     fail = read_status()
     if fail == 0:
         return kl, out
-    kl, _ = _jitter_ladder(engine, fail, base_jitter)
+    kl, _ = _jitter_ladder(engine, fail, base_jitter, constant_jitter)
     return kl, work()
 
 
@@ -78,10 +94,50 @@ def _check_generation(ctx):
                            'has been overwritten; call backward() before the next ELBO / marginal evaluation')
 
 
+def allreduce_packed(engine, rb):
+    """THE collective of a training step: sum over ranks of the pre-chain reduce buffer.  The two
+    lower-triangular M x M blocks travel tril-packed (tgp_reduce_pack / tgp_reduce_unpack: 2 M^2 -> M (M + 1) doubles,
+    16.9 -> 8.5 MB at M = 1024); slot 0 carries the ELL sum, so no second collective is needed for the loss value."""
+    dist = _world()
+    if dist is None:
+        return rb
+    packed = engine.pack_reduce(rb)
+    dist.all_reduce(packed)
+    engine.unpack_reduce(packed, rb)
+    return rb
+
+
+class _SumGradAcrossRanks(torch.autograd.Function):
+    """Identity whose backward all-reduces (sum) the gradient: wraps parameters that are used on rank-local rows only."""
+
+    @staticmethod
+    def forward(ctx, p):
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        dist = _world()
+        if dist is not None:
+            g = g.contiguous().clone()
+            dist.all_reduce(g)
+        return g
+
+
+def synced_module_call(module, X):
+    """module(X), such that under row sharding every parameter of `module` receives the gradient summed over ranks.
+    Used for the input-dependent flow MLPs (ID_TGP): they see only this rank's rows, and their gradients do not travel
+    in the packed reduce buffer."""
+    if _world() is None:
+        return module(X)
+    params = {n: _SumGradAcrossRanks.apply(p) for n, p in module.named_parameters()}
+    return torch.func.functional_call(module, params, (X,))
+
+
 class _ElboTerms(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, X, Y, scale, check_status, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta, rowparams):
-        need_grad = any(ctx.needs_input_grad[5:])
+    def forward(ctx, engine, X, Y, scale, check_status, jitter, sync_ell, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta,
+                rowparams):
+        need_grad = any(ctx.needs_input_grad[7:])
         engine.set_params(Z.detach(), raw_ls.detach(), raw_os.detach(), m.detach(), L_raw.detach(),
                           None if log_var_noise is None else log_var_noise.detach(),
                           None if theta is None else theta.detach())
@@ -89,14 +145,15 @@ class _ElboTerms(torch.autograd.Function):
 
         def work():
             mu, v = engine.qf_forward(X)
-            rb = engine.new_reduce_buffer()
+            rb = engine.new_reduce_buffer(fresh=False)
             return (mu, v, rb) + tuple(engine.ell_forward(mu, v, Y, rp, scale, rb, want_grad=need_grad))
 
-        kl, (mu, v, rb, ell_rows, g_mu, g_v, drow) = prepare_then(engine, work, check=check_status)
+        kl, (mu, v, rb, ell_rows, g_mu, g_v, drow) = prepare_then(engine, work, check=check_status,
+                                                                  base_jitter=jitter[1], constant_jitter=jitter[0])
         ell = rb[engine.layout.ell_sum:engine.layout.ell_sum + 1].clone()
         dist = _world()
-        if dist is not None:
-            dist.all_reduce(ell)
+        if dist is not None and sync_ell:
+            dist.all_reduce(ell)                   # every rank returns the GLOBAL ELL (cg.sync_elbo_in_forward)
         ctx.engine, ctx.X, ctx.rb, ctx.g = engine, X, rb, (g_mu, g_v, drow)
         ctx.generation = engine.generation
         ctx.has = (log_var_noise is not None, theta is not None, rowparams is not None)
@@ -111,39 +168,44 @@ class _ElboTerms(torch.autograd.Function):
             raise RuntimeError('backward called on an ELBO evaluated without gradients')
         _check_generation(ctx)
         engine.qf_backward(X, g_mu, g_v, rb)
-        dist = _world()
-        if dist is not None:
-            dist.all_reduce(rb)                    # the one collective of the step
+        allreduce_packed(engine, rb)               # the one collective of the step
+        engine.last_ell_sum = rb[engine.layout.ell_sum]        # global sum_n ell_n (unscaled), valid after backward
         zero = torch.zeros((), dtype=torch.float64, device=rb.device)
         g_dev = torch.stack([g_ell if g_ell is not None else zero, g_kl if g_kl is not None else zero]).contiguous()
         out = engine.chain_backward(rb, 0.0, 0.0, g_dev=g_dev)
         has_noise, has_theta, has_rowp = ctx.has
         g_rowp = drow * g_dev[0] if (has_rowp and drow is not None) else None
-        return (None, None, None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw'],
+        return (None, None, None, None, None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw'],
                 out['log_var_noise'] if has_noise else None, out['theta'] if has_theta else None, g_rowp)
 
 
 def elbo_terms(engine, X, Y, scale, Z, raw_ls, raw_os, m, L_raw, log_var_noise, theta, rowparams=None,
-               check_status=True):
-    """Returns (ELL, KLD, ell_rows, mu, v): ELL = scale * sum_n ell_n (summed over ranks when distributed)."""
-    return _ElboTerms.apply(engine, X, Y, float(scale), bool(check_status), Z, raw_ls, raw_os, m, L_raw, log_var_noise,
-                            theta, rowparams)
+               check_status=True, jitter=(0.0, None), sync_ell=True):
+    """Returns (ELL, KLD, ell_rows, mu, v): ELL = scale * sum_n ell_n.
+
+    Row-sharded (torch.distributed initialised): `sync_ell=True` sums ELL over ranks in the forward (every rank returns
+    the global value, a second small collective per step); `sync_ell=False` returns the rank-local share — the global
+    sum then rides in slot 0 of the one packed all-reduce of the backward (`engine.last_ell_sum`).  Gradients are the
+    global ones in both cases.  `jitter` = (constant jitter, ladder base or None) — cg.constant_jitter / cg.global_jitter."""
+    return _ElboTerms.apply(engine, X, Y, float(scale), bool(check_status), tuple(jitter), bool(sync_ell), Z, raw_ls,
+                            raw_os, m, L_raw, log_var_noise, theta, rowparams)
 
 
 class _QfMarginals(torch.autograd.Function):
     """mu, v of q(f) with a hand-written backward (used by marginal_variational_qf_parameters when called alone)."""
 
     @staticmethod
-    def forward(ctx, engine, X, check_status, Z, raw_ls, raw_os, m, L_raw):
+    def forward(ctx, engine, X, check_status, jitter, Z, raw_ls, raw_os, m, L_raw):
         engine.set_params(Z.detach(), raw_ls.detach(), raw_os.detach(), m.detach(), L_raw.detach(), None, None)
-        key = _param_key((Z, raw_ls, raw_os, m, L_raw))
+        key = _param_key((Z, raw_ls, raw_os, m, L_raw)) + (tuple(jitter),)
         if not any(ctx.needs_input_grad) and engine.prepared_key == key:
             # evaluation over many batches with frozen parameters: the factorisation in the step workspace is still
             # valid (the reference refactorises K_zz for every batch, sparse_MF_SP.py:330)
             engine.generation += 1
             mu, v = engine.qf_forward(X)
         else:
-            _, (mu, v) = prepare_then(engine, lambda: engine.qf_forward(X), check=check_status)
+            _, (mu, v) = prepare_then(engine, lambda: engine.qf_forward(X), check=check_status, base_jitter=jitter[1],
+                                      constant_jitter=jitter[0])
             engine.prepared_key = key if check_status else None
         ctx.engine, ctx.X = engine, X
         ctx.generation = engine.generation
@@ -157,8 +219,8 @@ class _QfMarginals(torch.autograd.Function):
         zeros = torch.zeros(X.shape[0], dtype=torch.float64, device=X.device)
         engine.qf_backward(X, zeros if g_mu is None else g_mu.contiguous(), zeros if g_v is None else g_v.contiguous(), rb)
         out = engine.chain_backward(rb, 1.0, 0.0)
-        return None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw']
+        return None, None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw']
 
 
-def qf_marginals(engine, X, Z, raw_ls, raw_os, m, L_raw, check_status=True):
-    return _QfMarginals.apply(engine, X, bool(check_status), Z, raw_ls, raw_os, m, L_raw)
+def qf_marginals(engine, X, Z, raw_ls, raw_os, m, L_raw, check_status=True, jitter=(0.0, None)):
+    return _QfMarginals.apply(engine, X, bool(check_status), tuple(jitter), Z, raw_ls, raw_os, m, L_raw)

@@ -61,6 +61,9 @@ class GraphedElboStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        # the replayed optimiser step changed the parameters in place without touching their `_version`: drop any
+        # factorisation cached for evaluation batches (functional._QfMarginals keys it on identity + version)
+        self.model._invalidate_eval_cache()
         return self.loss
 
     def eager_step(self, x, y):
@@ -69,6 +72,7 @@ class GraphedElboStep:
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.opt.step()
+        self.model._invalidate_eval_cache()
         return loss.detach()
 
     def check(self):
