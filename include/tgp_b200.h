@@ -130,6 +130,27 @@ int tgp_test_rows(const TgpModel* model, const TgpParams* params, const void* mu
                   const void* rowparams, long R, int n_mc, double y_std, const void* quad_t, const void* quad_w,
                   const double* bern_std, void* logp_rows, void* m1, void* m2, void* stream);
 
+/* ---- input-dependent flow parameters (ID_TGP) ------------------------------------------------------------------------
+ * The MLPs theta(x_n) of an input-dependent flow layer (models/flow.py:853-871 builds them, :949-950 evaluates them once
+ * per call on X; dropout active in training, sparse_MF_SP.py:133-134).  n_nets independent nets x -> R, each
+ * n_hidden_layers x [Linear(.., hidden) -> activation -> Dropout(p)] + Linear(hidden, 1).  Weights are packed per net as
+ * [W0 (hidden x n_in), b0 (hidden), W1 (hidden x hidden), b1, ..., w_out (hidden), b_out] (torch Linear.weight order).
+ * mask_mode: 0 = no dropout; 1 = Philox-4x32-10 stream (seed, *offset_dev; the forward bumps *offset_dev and EXPORTS the
+ * keep-mask to mask_out, which must be non-NULL); 2 = explicit keep-mask mask_in.  Mask layout (n_nets, n_hidden_layers, R,
+ * hidden) bytes.  The backward consumes the mask of the forward (NULL for mode 0) and ACCUMULATES into dweights. */
+typedef struct TgpMlp {
+    int n_nets, n_in, hidden, n_hidden_layers;
+    int activation;                  /* 0 relu, 1 tanh, 2 sigmoid, 3 linear */
+    int mask_mode;
+    double p_drop;
+} TgpMlp;
+long tgp_flow_mlp_net_doubles(const TgpMlp* mlp);
+int tgp_flow_mlp_forward(const TgpMlp* mlp, const void* weights, const void* X, long R, const unsigned char* mask_in,
+                         unsigned char* mask_out, unsigned long long seed, unsigned long long* offset_dev, void* out,
+                         void* stream);
+int tgp_flow_mlp_backward(const TgpMlp* mlp, const void* weights, const void* X, long R, const unsigned char* mask,
+                          const void* dout, void* dweights, void* stream);
+
 /* ---- single-call interface (the entry points SURVEY.md 8b proposes), thin over the stages above -------------------
  * A TgpHandle is a HOST object created once per (model description, device, maximum minibatch rows): it remembers the
  * model, the caller-owned workspace (ONE device allocation of tgp_workspace_bytes(), bound with tgp_bind_workspace and

@@ -1,0 +1,126 @@
+"""CPU restatement of the integer-residue (CRT) FP64 contraction of csrc/gemm_i8.cuh — test infrastructure.
+
+C = A B^T for FP64 A (m x k), B (n x k), evaluated as the tcgen05 kind::i8 path does it ("Ozaki scheme II"):
+  1. integerise: A'[i,:] = rint(A[i,:] * 2^(b - eA_i)), 2^eA_i >= max_j |A_ij| (per row; likewise B), |A'| <= 2^b;
+  2. residues: A_t = A' mod p_t (centred, int8) for T pairwise coprime moduli p_t <= 256;
+  3. T independent int8 GEMMs with exact int32 accumulation, reduced mod p_t: R_t = (A_t B_t^T) mod p_t (int8 again);
+  4. CRT: C' = sum_t R_t w_t mod P  (w_t = (P/p_t) * ((P/p_t)^-1 mod p_t)) in 40-bit words whose partial sums are exact in
+     FP64 (|R_t| <= 128, 16 terms, words < 2^40: sums < 2^51); the multiple of P is rint(sum_t R_t w_t / P);
+  5. C = C' * 2^(eA_i + eB_j - 2b).
+The integer product is EXACT; the only error is the truncation of the operands to b bits below their row maximum.
+This file mirrors the device arithmetic step by step (same words, same order) with numpy int64 / float64, and offers the
+same computation in exact Python integers for cross-checking."""
+import numpy as np
+
+MODULI = (256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193)
+WORD_BITS = 40
+N_WORDS = 4
+
+
+def crt_constants(T):
+    """Per modulus: weight words w_tk (k < N_WORDS, each < 2^40), fraction w_t / P; and the words of P."""
+    ps = MODULI[:T]
+    P = 1
+    for p in ps:
+        P *= p
+    words = np.zeros((T, N_WORDS), dtype=np.float64)
+    frac = np.zeros(T, dtype=np.float64)
+    for t, p in enumerate(ps):
+        q = P // p
+        w = q * pow(q % p, -1, p)
+        frac[t] = float(w) / float(P) if False else (w / P)      # Python int true division: correctly rounded
+        for k in range(N_WORDS):
+            words[t, k] = float((w >> (WORD_BITS * k)) & ((1 << WORD_BITS) - 1))
+    Pw = np.array([float((P >> (WORD_BITS * k)) & ((1 << WORD_BITS) - 1)) for k in range(N_WORDS)])
+    return P, words, frac, Pw
+
+
+def max_bits(T, k_red):
+    """Largest b (bits per operand, both equal) such that 2 * k_red * 2^(2b) < P * (1 - 2^-30)."""
+    P = crt_constants(T)[0]
+    b = 0
+    while 2 * k_red * (1 << (2 * (b + 1))) < P - (P >> 30):
+        b += 1
+    return min(b, 53)
+
+
+def integerise(A, b):
+    """rows of A -> (int64 A' with |A'| <= 2^b, exponents e): A ~= A' * 2^(e - b)."""
+    amax = np.abs(A).max(axis=1)
+    e = np.where(amax > 0, np.ceil(np.log2(np.where(amax > 0, amax, 1.0))), 0.0).astype(np.int64)
+    e = np.where(np.ldexp(1.0, e) < amax, e + 1, e)          # guard log2 rounding
+    Ai = np.rint(np.ldexp(A, (b - e)[:, None])).astype(np.int64)
+    return Ai, e
+
+
+def residues(Ai, T):
+    """(T, rows, cols) int8 centred residues, with the device's arithmetic: q = rint(x / p), r = x - q p, one fix-up."""
+    out = np.empty((T,) + Ai.shape, dtype=np.int8)
+    x = Ai.astype(np.float64)
+    for t, p in enumerate(MODULI[:T]):
+        q = np.rint(x * (1.0 / p))
+        r = x - q * p                                  # exact: fma on the device
+        r = np.where(r > p / 2 - 0.25, r - p, r)
+        r = np.where(r < -p / 2 - 0.25, r + p, r)
+        assert np.all(np.abs(r) <= 128)
+        out[t] = np.where(r == 128, -128, r).astype(np.int8) if p == 256 else r.astype(np.int8)
+    return out
+
+
+def gemm_mod(Ar, Br, T):
+    """R_t = (A_t B_t^T) mod p_t, centred int8 (exact integer accumulation)."""
+    out = np.empty((T, Ar.shape[1], Br.shape[1]), dtype=np.int8)
+    for t, p in enumerate(MODULI[:T]):
+        acc = Ar[t].astype(np.int64) @ Br[t].astype(np.int64).T
+        assert np.abs(acc).max() < 2 ** 31
+        q = np.rint(acc.astype(np.float64) * (1.0 / p)).astype(np.int64)
+        r = acc - q * p
+        r = np.where(r > p // 2, r - p, r)
+        r = np.where(r < -(p // 2) - (1 if p == 256 else 0), r + p, r)
+        r = np.where(r == 128, -128, r)
+        out[t] = r.astype(np.int8)
+    return out
+
+
+def combine(R, eA, eB, bA, bB, T):
+    """CRT reconstruction in FP64 words (device arithmetic) and scaling back: (rows, cols) float64."""
+    _, words, frac, Pw = crt_constants(T)
+    r = R.astype(np.float64)
+    S = [np.zeros(R.shape[1:]) for _ in range(N_WORDS)]
+    mf = np.zeros(R.shape[1:])
+    for t in range(T):
+        for k in range(N_WORDS):
+            S[k] = S[k] + r[t] * words[t, k]           # exact (< 2^51)
+        mf = mf + r[t] * frac[t]
+    m = np.rint(mf)
+    D = [S[k] - m * Pw[k] for k in range(N_WORDS)]     # exact (< 2^52)
+    two = float(1 << WORD_BITS)
+    for k in range(N_WORDS - 1):                        # carry normalisation: |D_k| <= 2^39 for k < top
+        c = np.rint(D[k] / two)
+        D[k] = D[k] - c * two
+        D[k + 1] = D[k + 1] + c
+    val = D[N_WORDS - 1]
+    for k in range(N_WORDS - 2, -1, -1):
+        val = val * two + D[k]
+    return np.ldexp(val, (eA[:, None] + eB[None, :] - bA - bB))
+
+
+def crt_matmul(A, B, T=16, bits=None):
+    """A (m, k) @ B (n, k)^T through the residue pipeline."""
+    b = max_bits(T, A.shape[1]) if bits is None else bits
+    Ai, eA = integerise(A, b)
+    Bi, eB = integerise(B, b)
+    R = gemm_mod(residues(Ai, T), residues(Bi, T), T)
+    return combine(R, eA, eB, b, b, T)
+
+
+def exact_matmul_of_truncated(A, B, b):
+    """Exact (Python integer) product of the b-bit truncated operands — what crt_matmul must equal up to final rounding."""
+    Ai, eA = integerise(A, b)
+    Bi, eB = integerise(B, b)
+    C = Ai.astype(object) @ Bi.astype(object).T
+    out = np.empty(C.shape)
+    for i in range(C.shape[0]):
+        for j in range(C.shape[1]):
+            out[i, j] = float(C[i, j]) * 2.0 ** float(eA[i] + eB[j] - 2 * b) if abs(int(eA[i] + eB[j] - 2 * b)) < 1000 else 0.0
+    return out

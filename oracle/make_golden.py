@@ -64,7 +64,7 @@ def build(kind, X, M, N, flow=None, likelihood=None, seed=0):
                         False, ip)
 
 
-def randomise(model, seed):
+def randomise(model, seed, nnet_scale=0.2):
     """P1 'mid-training' state: nothing at its trivial initial value."""
     g = torch.Generator().manual_seed(seed)
     M = model.M
@@ -87,7 +87,7 @@ def randomise(model, seed):
             elif 'G_matrix' in n and 'NNets' not in n:
                 prm.add_(0.3 * torch.randn(prm.shape, generator=g))
             elif 'NNets' in n:
-                prm.add_(0.2 * torch.randn(prm.shape, generator=g))
+                prm.add_(nnet_scale * torch.randn(prm.shape, generator=g))
 
 
 def randomise_big(model, seed):
@@ -143,6 +143,39 @@ def dropout_off(model):
             m.eval()
 
 
+class DropoutTape:
+    """MC-dropout with RECORDED masks.  While active, nn.Dropout.forward draws its keep-mask with torch.bernoulli from the
+    global RNG (the distribution nn.Dropout uses: keep with probability 1 - p, scale by 1 / (1 - p)) and stores it
+    ('record'), or re-applies the stored masks in call order ('replay').  The reference's code path is untouched: the
+    dropout layers live in the pytorchlib stand-in (oracle/ref_shims/pytorchlib), whose source is unavailable offline."""
+
+    def __init__(self):
+        self.masks, self.mode, self.i = [], 'record', 0
+
+    def __enter__(self):
+        tape = self
+        self._orig = torch.nn.Dropout.forward
+
+        def fwd(mod, x):
+            if not mod.training:
+                return x
+            if tape.mode == 'record':
+                mask = torch.bernoulli(torch.full_like(x, 1.0 - mod.p))
+                tape.masks.append(mask.to(torch.uint8))
+            else:
+                mask = tape.masks[tape.i].to(x.dtype)
+                tape.i += 1
+            return x * mask / (1.0 - mod.p)
+        torch.nn.Dropout.forward = fwd
+        return self
+
+    def __exit__(self, *exc):
+        torch.nn.Dropout.forward = self._orig
+
+    def replay(self):
+        self.mode, self.i = 'replay', 0
+
+
 ONLY = set(sys.argv[1:])      # optional fixture names: write only these (the others are left untouched on disk)
 
 
@@ -153,7 +186,7 @@ def projection_basis(M, k=6):
     return (((i * 2654435761 + (c + 1) * 40503 + i * c * 97) % 1024).astype(np.float64) / 1024.0) - 0.5
 
 
-def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=None, big=False):
+def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=None, big=False, tape=None):
     """big=True (fixtures at the BASELINE sizes M = 1024 / 2048): the M x M gradient of chol_variational_covar is stored
     as checksums — G R, G^T R for the fixed basis R above, its diagonal and Frobenius norm — instead of 8-32 MB of
     incompressible doubles (the parameter itself is low-entropy by construction, see randomise_big)."""
@@ -186,7 +219,21 @@ def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=
         store['mu'], store['v'] = mu.view(-1).numpy(), v.view(-1).numpy()
         flow = model.G_matrix[0]
         comp = flow if isinstance(flow, CompositeFlow) else CompositeFlow([flow])
-        spec_tr = flow_to_spec(comp, store, X, 'fl')
+        if tape is not None:
+            # dropout ON: the per-row flow parameters of the training batch are those of the recorded masks (replayed);
+            # masks are stored per input-dependent layer as (n_nets, n_hidden_layers, rows, hidden) in evaluation order
+            # (reference flow.py:949-950: NNets_a then NNets_b, hidden layers front to back)
+            tape.replay()
+            spec_tr = flow_to_spec(comp, store, X, 'fl')
+            assert tape.i == len(tape.masks)
+            id_layers = [i for i, fl in enumerate(comp.flow_arr) if isinstance(fl, Sinh_ArcsinhFlow) and fl.input_dependent]
+            per = len(tape.masks) // len(id_layers)
+            for j, li in enumerate(id_layers):
+                mk = torch.stack(tape.masks[j * per:(j + 1) * per])              # (2 * L, rows, hidden)
+                store['dropmask:%d' % li] = mk.view(2, per // 2, mk.shape[1], mk.shape[2]).numpy()
+            dropout_off(model)                # the test side of the fixture is the point-estimate (dropout off) path
+        else:
+            spec_tr = flow_to_spec(comp, store, X, 'fl')
         spec_te = flow_to_spec(comp, store, Xte, 'flte')
     model.set_is_training(False)
     lp, mom = model.test_log_likelihood(Xte, Yte if likelihood != 'bernoulli' else Yte.long(),
@@ -199,7 +246,7 @@ def record(name, model, X, Y, Xte, Yte, y_std, likelihood, id_flow=False, extra=
     model.set_is_training(True)
     meta = {'name': name, 'likelihood': likelihood, 'N': float(model.N), 'M': int(model.M), 'y_std': y_std,
             'n_quad': int(cg.quad_points), 'flow_train': spec_tr, 'flow_test': spec_te, 'param_names': names,
-            'id_flow': id_flow, 'dtype': 'float64', 'big': bool(big)}
+            'id_flow': id_flow, 'dtype': 'float64', 'big': bool(big), 'dropout': tape is not None}
     if extra:
         meta.update(extra)
     store['meta'] = np.array(json.dumps(meta))
@@ -302,6 +349,29 @@ def main():
     record('boston_tgp_steptanh154_p1', m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear')
 
 
+def main_dropout():
+    """cfg3 in TRAINING mode: ID_TGP with MC-dropout ACTIVE (nn.Module.training stays True in the reference's training loop,
+    sparse_MF_SP.py:133-134), masks recorded so that another implementation can be fed the same ones."""
+    Xb, Yb, Xbt, Ybt, ysb = load_uci('boston')
+    Xp, Yp, Xpt, Ypt, ysp = load_uci('power')
+    for tag, (X, Y, Xt, Yt, ys), nb, cfgd, sd in (
+            ('boston', (Xb, Yb, Xbt, Ybt, ysb), 1,
+             dict(hidden_activation='tanh', num_hidden_layers=1, dropout=0.5, batch_norm=0, hidden_dim=25), 6),
+            ('power', (Xp[:1024], Yp[:1024], Xpt[:128], Ypt[:128], ysp), 3,
+             dict(hidden_activation='relu', num_hidden_layers=2, dropout=0.25, batch_norm=0, hidden_dim=50), 7)):
+        spec = SAL(nb, input_dependent=True, input_dim=X.shape[1], inference='MC_dropout', **cfgd)
+        torch.manual_seed(sd); np.random.seed(sd)  # noqa: E702
+        fl = instance_flow(spec)
+        fl.turn_off_initializer_parameters()
+        m = build('TGP', X, 100, float(X.shape[0]), fl, seed=sd)
+        # three composed sinh-arcsinh blocks with 1 / (1 - p)-scaled hidden units overflow to ~1e21 with the 0.2 weight
+        # noise of the dropout-off fixtures; 0.05 keeps the ELBO at the magnitude of a training run
+        randomise(m, 20 + sd, nnet_scale=0.2 if tag == 'boston' else 0.05)
+        torch.manual_seed(100 + sd)
+        with DropoutTape() as tape:
+            record('%s_idtgp_drop_p1' % tag, m, X, Y, Xt, Yt, ys, 'gauss_nonlinear', id_flow=True, tape=tape)
+
+
 def main_big():
     """Fixtures at the BASELINE.json sizes (configs[3]: D=8, M=1024, StepTanhL(1,3); configs[4]: Bernoulli, D=16, M=2048,
     SAL(1)); row counts the CPU oracle replays in seconds.  Z = distinct data rows, as in bench.py."""
@@ -320,5 +390,8 @@ if __name__ == '__main__':
     if 'BIG' in ONLY:
         ONLY.discard('BIG')
         main_big()
+    elif 'DROPOUT' in ONLY:
+        ONLY.discard('DROPOUT')
+        main_dropout()
     else:
         main()

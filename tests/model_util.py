@@ -55,3 +55,19 @@ def build_from_golden(g, device):
         for n in meta['param_names']:
             own[n].copy_(torch.tensor(np.asarray(g.z['param:' + n]), dtype=torch.float64).reshape(own[n].shape))
     return model.to(device)
+
+
+def set_dropout_mode(model, g):
+    """Fixtures recorded with dropout OFF: put the dropout layers in eval mode.  Fixtures recorded in TRAINING mode
+    (meta['dropout']): keep them active and hand every input-dependent layer the reference's recorded keep-masks."""
+    if not g.meta['id_flow']:
+        return
+    if g.meta.get('dropout'):
+        for li, layer in enumerate(model.G_matrix[0].flow_arr):
+            key = 'dropmask:%d' % li
+            if key in g.z.files:
+                layer.dropout_masks = torch.tensor(np.asarray(g.z[key]), dtype=torch.uint8)
+        return
+    for m in model.modules():
+        if 'Dropout' in type(m).__name__:
+            m.eval()

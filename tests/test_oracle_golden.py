@@ -65,3 +65,26 @@ def test_row_shards_sum_to_single():
     for world in (2, 4, 8):
         Ew = O.elbo_rows_sharded(X, Y, p, g.meta['N'], world, g.meta['likelihood'], g.meta['n_quad'])[0]
         assert rel_err(Ew, E1) < 1e-12
+
+
+def _mlp_weights(g, li, net):
+    """[(W, b), ...] of NNets_<net> of input-dependent layer `li`, by the reference's parameter names."""
+    pre = 'param:G_matrix.0.flow_arr.%d.NNets_%s.' % (li, net)
+    ks = sorted({int(k[len(pre):].split('.')[0]) for k in g.z.files if k.startswith(pre)})
+    return [(g.t(pre + '%d.forward_lin.0.weight' % k), g.t(pre + '%d.forward_lin.0.bias' % k)) for k in ks]
+
+
+@pytest.mark.parametrize('name,act,p', [('boston_idtgp_drop_p1', 'tanh', 0.5), ('power_idtgp_drop_p1', 'relu', 0.25)])
+def test_dropout_fixture_masks_reproduce_the_per_row_flow_parameters(name, act, p):
+    """ID_TGP recorded in TRAINING mode (MC-dropout active): the oracle's MLP with the recorded keep-masks must give the
+    per-row a(x), b(x) the reference evaluated (stored as the fixture's per-row flow layers)."""
+    g = Golden(name)
+    assert g.meta['dropout']
+    X = g.t('X')
+    for li, lay in enumerate(g.meta['flow_train']):
+        if lay[0] != 'sal' or 'dropmask:%d' % li not in g.z.files:
+            continue
+        masks = g.t('dropmask:%d' % li, torch.uint8)                    # (2, L, rows, H)
+        for ni, net in enumerate('ab'):
+            out = O.flow_mlp(X, _mlp_weights(g, li, net), act, p, [masks[ni, l] for l in range(masks.shape[1])])
+            assert rel_err(out, g.t(lay[1 + ni])) < 1e-13, (li, net)

@@ -51,6 +51,11 @@ class TgpGrads(C.Structure):
                                           'dtheta', 'drowparams')]
 
 
+class TgpMlp(C.Structure):
+    _fields_ = [('n_nets', C.c_int), ('n_in', C.c_int), ('hidden', C.c_int), ('n_hidden_layers', C.c_int),
+                ('activation', C.c_int), ('mask_mode', C.c_int), ('p_drop', C.c_double)]
+
+
 # int (*TgpAllReduceFn)(double* buf, long count, void* user, void* stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p)
 
@@ -81,6 +86,9 @@ SIGNATURES = {
     'tgp_elbo_fwd': (_I, [_P, C.POINTER(TgpParams), C.POINTER(TgpBatch), _D, C.POINTER(TgpFwdOut), _P]),
     'tgp_elbo_bwd': (_I, [_P, C.POINTER(TgpParams), C.POINTER(TgpBatch), _P, C.POINTER(TgpGrads), ALLREDUCE_FN, _P, _P]),
     'tgp_test_nll_fwd': (_I, [_P, C.POINTER(TgpParams), C.POINTER(TgpBatch), _I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'tgp_flow_mlp_net_doubles': (_L, [C.POINTER(TgpMlp)]),
+    'tgp_flow_mlp_forward': (_I, [C.POINTER(TgpMlp), _P, _P, _L, _P, _P, C.c_ulonglong, _P, _P, _P]),
+    'tgp_flow_mlp_backward': (_I, [C.POINTER(TgpMlp), _P, _P, _L, _P, _P, _P, _P]),
     'tgp_set_option': (_I, [_I, _I]),
     'tgp_launch_count': (_L, []),
     'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),

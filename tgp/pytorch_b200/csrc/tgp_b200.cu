@@ -7,6 +7,7 @@
 #include "row_kernels.cuh"
 #include "backward_kernels.cuh"
 #include "tc_driver.cuh"
+#include "flow_mlp.cuh"
 
 namespace tgp {
 char g_last_error[512] = "";
@@ -392,6 +393,45 @@ int tgp_reduce_unpack(const TgpModel* md, const double* packed, double* reduce_b
     TGP_TRY(validate(md));
     if (!reduce_buf || !packed) return set_error(-1, "NULL argument to tgp_reduce_unpack");
     return reduce_pack(md, reduce_buf, const_cast<double*>(packed), 1, (cudaStream_t)stream);
+}
+
+long tgp_flow_mlp_net_doubles(const TgpMlp* m) {
+    if (mlp_validate(m)) return 0;
+    return mlp_net_size(m->n_in, m->hidden, m->n_hidden_layers);
+}
+
+int tgp_flow_mlp_forward(const TgpMlp* m, const void* weights, const void* X, long R, const unsigned char* mask_in,
+                         unsigned char* mask_out, unsigned long long seed, unsigned long long* offset_dev, void* out,
+                         void* stream) {
+    TGP_TRY(mlp_validate(m));
+    if (R <= 0) return 0;
+    if (!weights || !X || !out) return set_error(-1, "NULL argument to tgp_flow_mlp_forward");
+    if (m->mask_mode == 1 && (!mask_out || !offset_dev)) return set_error(-1, "Philox dropout needs mask_out and offset_dev");
+    if (m->mask_mode == 2 && !mask_in) return set_error(-1, "explicit dropout needs mask_in");
+    MlpArgs a{};
+    a.n_nets = m->n_nets; a.n_in = m->n_in; a.H = m->hidden; a.L = m->n_hidden_layers; a.act = m->activation;
+    a.mask_mode = m->mask_mode; a.p_drop = m->p_drop; a.R = R;
+    a.W = (const double*)weights; a.X = (const double*)X; a.mask_in = mask_in; a.mask_out = mask_out; a.seed = seed;
+    a.offset_dev = offset_dev; a.out = (double*)out;
+    TGP_TRY(launch_flow_mlp(m, a, false, (cudaStream_t)stream));
+    if (m->mask_mode == 1) {
+        k_bump_offset<<<1, 1, 0, (cudaStream_t)stream>>>(offset_dev);
+        TGP_TRY(check_launch("k_bump_offset"));
+    }
+    return 0;
+}
+
+int tgp_flow_mlp_backward(const TgpMlp* m, const void* weights, const void* X, long R, const unsigned char* mask,
+                          const void* dout, void* dweights, void* stream) {
+    TGP_TRY(mlp_validate(m));
+    if (R <= 0) return 0;
+    if (!weights || !X || !dout || !dweights) return set_error(-1, "NULL argument to tgp_flow_mlp_backward");
+    if (m->mask_mode != 0 && !mask) return set_error(-1, "the backward needs the keep-mask of the forward");
+    MlpArgs a{};
+    a.n_nets = m->n_nets; a.n_in = m->n_in; a.H = m->hidden; a.L = m->n_hidden_layers; a.act = m->activation;
+    a.mask_mode = m->mask_mode; a.p_drop = m->p_drop; a.R = R;
+    a.W = (const double*)weights; a.X = (const double*)X; a.mask_in = mask; a.dout = (const double*)dout; a.dW = (double*)dweights;
+    return launch_flow_mlp(m, a, true, (cudaStream_t)stream);
 }
 
 // ---- single-call interface ------------------------------------------------------------------------------------------

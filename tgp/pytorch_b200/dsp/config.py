@@ -44,6 +44,7 @@ cache_factorisation_in_eval = True   # consecutive no-grad evaluations with unch
 sync_elbo_in_forward = True     # row-sharded training: True = ELBO() returns the GLOBAL value on every rank (a second, 8-byte
                                 # collective per step); False = it returns this rank's share and the global value is
                                 # read from the one packed all-reduce after backward (sparse_MF_SP.last_global_elbo())
+flow_mlp_in_kernel = True       # ID_TGP: evaluate the input-dependent flow MLPs (and their backward) in the fused CUDA kernel
 check_cholesky_status = True    # False: skip the 4-byte status read-back after the factorisation (no host sync)
 
 device = check_device()

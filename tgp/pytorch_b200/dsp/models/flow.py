@@ -184,11 +184,26 @@ class _RowParamMixin:
     def _nets(self):
         return [getattr(self, 'NNets_' + n) for n in self._names]
 
+    dropout_masks = None          # parity mode: explicit keep-mask (n_nets, n_hidden_layers, rows, hidden) for the next calls
+    last_dropout_masks = None     # the keep-mask the last fused evaluation used (exported by the kernel)
+
     def _net_outputs(self, X):
+        """theta(x_n) of this layer's MLPs (reference flow.py:949-950), one tensor (rows,) per parameter.
+
+        CUDA inputs run the fused kernel (tgp_flow_mlp_forward / _backward: all nets of the layer in one launch, MC-dropout
+        from a Philox stream with the mask exported to `last_dropout_masks`, or from `dropout_masks` when set — the
+        reference's masks come from torch's global RNG, so bit-parity needs them passed in; analytic backward).  Anything
+        the kernel does not cover (batch-norm nets, CPU tensors used by the initialisers) runs the torch modules."""
+        from ... import functional as Fn
+        nets = self._nets()
+        if X.is_cuda and X.dim() == 2 and cg.flow_mlp_in_kernel:
+            spec = Fn.mlp_spec(nets)
+            if spec is not None:
+                out = Fn.flow_mlp(self, nets, spec, X, self.dropout_masks)
+                return [out[:, i] for i in range(len(nets))]
         # under row sharding each rank evaluates the MLPs on its own rows: their parameter gradients are summed over
         # ranks in the backward (functional.synced_module_call); single process: a plain module call
-        from ...functional import synced_module_call
-        return [synced_module_call(net, X).squeeze(dim=-1) for net in self._nets()]
+        return [Fn.synced_module_call(net, X).squeeze(dim=-1) for net in nets]
 
     def forward_initializer(self, X):
         if not self.input_dependent:

@@ -224,3 +224,128 @@ class _QfMarginals(torch.autograd.Function):
 
 def qf_marginals(engine, X, Z, raw_ls, raw_os, m, L_raw, check_status=True, jitter=(0.0, None)):
     return _QfMarginals.apply(engine, X, bool(check_status), tuple(jitter), Z, raw_ls, raw_os, m, L_raw)
+
+
+# ---- input-dependent flow MLPs on the device (tgp_flow_mlp_forward / _backward) ---------------------------------------
+_ACT_CODE = {'ReLU': 0, 'Tanh': 1, 'Sigmoid': 2, 'Identity': 3}
+_PHILOX_OFFSET = {}
+
+
+def mlp_spec(nets):
+    """Architecture of a list of flow MLPs if the fused kernel covers it, else None: every net =
+    num_H x [Linear -> activation -> (Dropout)] + [Linear(H, 1)], identical shapes, no batch-norm, H <= 64, n_in <= 64."""
+    import torch.nn as nn
+    spec = None
+    for net in nets:
+        blocks = [list(b.forward_lin) if hasattr(b, 'forward_lin') else None for b in net]
+        if any(b is None for b in blocks) or len(blocks) < 2:
+            return None
+        hidden, last = blocks[:-1], blocks[-1]
+        if not (isinstance(last[0], nn.Linear) and last[0].out_features == 1 and all(isinstance(m, nn.Identity) for m in last[1:])):
+            return None
+        p, act, drops = 0.0, None, []
+        for b in hidden:
+            if not isinstance(b[0], nn.Linear) or len(b) < 2 or type(b[1]).__name__ not in _ACT_CODE:
+                return None
+            rest = b[2:]
+            if len(rest) > 1 or (rest and 'Dropout' not in type(rest[0]).__name__):
+                return None
+            if rest:
+                p = float(rest[0].p)
+                drops.append(rest[0])
+            act = type(b[1]).__name__ if act is None else act
+            if type(b[1]).__name__ != act:
+                return None
+        H, n_in = hidden[0][0].out_features, hidden[0][0].in_features
+        if any(b[0].out_features != H for b in hidden) or H > 64 or n_in > 64 or len(hidden) > 4 or last[0].in_features != H:
+            return None
+        if drops and len(drops) != len(hidden):
+            return None
+        cur = dict(n_in=n_in, H=H, L=len(hidden), act=_ACT_CODE[act], p=p, training=bool(drops) and any(d.training for d in drops))
+        if spec is None:
+            spec = cur
+        elif spec != cur:
+            return None
+    return spec
+
+
+def _mlp_weights(nets):
+    ws = []
+    for net in nets:
+        for b in net:
+            lin = b.forward_lin[0]
+            ws += [lin.weight, lin.bias]
+    return ws
+
+
+class _FlowMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, spec, mask_in, owner, n_nets, *weights):
+        import ctypes as C
+        lib = _lib.load()
+        dev = X.device
+        m = _lib.TgpMlp()
+        m.n_nets, m.n_in, m.hidden, m.n_hidden_layers, m.activation = n_nets, spec['n_in'], spec['H'], spec['L'], spec['act']
+        drop = spec['training'] and spec['p'] > 0.0
+        m.mask_mode = 0 if not drop else (2 if mask_in is not None else 1)
+        m.p_drop = spec['p'] if drop else 0.0
+        Xc = X.detach().to(torch.float64).contiguous()
+        R = Xc.shape[0]
+        Wp = torch.cat([w.detach().reshape(-1).to(torch.float64) for w in weights]).contiguous()
+        assert Wp.numel() == n_nets * lib.tgp_flow_mlp_net_doubles(m), 'flow MLP weight packing does not match the kernel layout'
+        out = torch.empty(R, n_nets, dtype=torch.float64, device=dev)
+        mask = None
+        if m.mask_mode == 2:
+            mask = mask_in.to(device=dev, dtype=torch.uint8).contiguous()
+            if tuple(mask.shape) != (n_nets, spec['L'], R, spec['H']):
+                raise ValueError('dropout mask must have shape (n_nets, n_hidden_layers, rows, hidden) = %s, got %s'
+                                 % ((n_nets, spec['L'], R, spec['H']), tuple(mask.shape)))
+        mask_out = torch.empty(n_nets, spec['L'], R, spec['H'], dtype=torch.uint8, device=dev) if m.mask_mode == 1 else None
+        off = None
+        if m.mask_mode == 1:
+            key = str(dev)
+            if key not in _PHILOX_OFFSET:
+                _PHILOX_OFFSET[key] = torch.zeros(1, dtype=torch.int64, device=dev)
+            off = _PHILOX_OFFSET[key]
+        from .dsp import config as cg
+        dist = _world()
+        seed = (int(cg.config_seed) * 0x9E3779B97F4A7C15 + (dist.get_rank() if dist is not None else 0) * 0xD1B54A32D192ED03 + 0x1234567) % (1 << 64)
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.tgp_flow_mlp_forward(m, Wp.data_ptr(), Xc.data_ptr(), R, None if mask is None else mask.data_ptr(),
+                                                None if mask_out is None else mask_out.data_ptr(), seed,
+                                                None if off is None else off.data_ptr(), out.data_ptr(), st), 'tgp_flow_mlp_forward')
+        used = mask if m.mask_mode == 2 else mask_out
+        if owner is not None:
+            owner.last_dropout_masks = used                  # exported keep-mask of this call (None when dropout is off)
+        ctx.m, ctx.Xc, ctx.Wp, ctx.mask, ctx.shapes, ctx.dtypes = m, Xc, Wp, used, [w.shape for w in weights], [w.dtype for w in weights]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        lib = _lib.load()
+        dev = ctx.Xc.device
+        dW = torch.zeros_like(ctx.Wp)
+        d = dout.to(torch.float64).contiguous()
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.tgp_flow_mlp_backward(ctx.m, ctx.Wp.data_ptr(), ctx.Xc.data_ptr(), ctx.Xc.shape[0],
+                                                 None if ctx.mask is None else ctx.mask.data_ptr(), d.data_ptr(), dW.data_ptr(), st),
+                       'tgp_flow_mlp_backward')
+        dist = _world()
+        if dist is not None:
+            dist.all_reduce(dW)          # each rank saw its own rows only: ONE collective for all MLP weights of the layer
+        grads, o = [], 0
+        for shp, dt in zip(ctx.shapes, ctx.dtypes):
+            n = 1
+            for k in shp:
+                n *= k
+            grads.append(dW[o:o + n].reshape(shp).to(dt))
+            o += n
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def flow_mlp(owner, nets, spec, X, mask_in=None):
+    """theta(x_n) of `len(nets)` flow MLPs in one kernel: (R, n_nets).  Differentiable w.r.t. the MLP weights."""
+    return _FlowMlp.apply(X, spec, mask_in, owner, len(nets), *_mlp_weights(nets))
