@@ -413,7 +413,7 @@ def run_ours(args):
     parity = dist_parity() if world > 1 else None
     # the secondary mode runs first: on a fresh box the first seconds of a process are not steady (cold clocks, lazy
     # module loads), and the headline should not absorb that
-    second = 'tf32x3' if args.compute == 'f64' else 'f64'
+    second = args.other or ('tf32x3' if args.compute == 'f64' else 'f64')
     other = None
     if not args.no_other_mode:
         measure(second, False)                      # discarded: absorbs the cold start of a fresh box
@@ -590,7 +590,9 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: 65536 rows per GPU per step; strong: 65536 rows per step in total')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
-    ap.add_argument('--compute', default='f64', choices=['f64', 'tf32x3'], help='f64: DMMA path (what main.py runs); tf32x3: tcgen05 mode')
+    ap.add_argument('--compute', default='f64', choices=['f64', 'tf32x3', 'i8crt'],
+                    help='f64: FP64 DMMA; i8crt: FP64-accurate on the tcgen05 integer path (CRT residues); tf32x3: tcgen05 3xTF32')
+    ap.add_argument('--other', default=None, choices=['f64', 'tf32x3', 'i8crt'], help='secondary mode reported as other_mode')
     ap.add_argument('--no-other-mode', action='store_true', help='measure only the headline compute mode')
     ap.add_argument('--no-gemm-timing', action='store_true', help='(diagnostic) do not instrument GEMM launches with events')
     ap.add_argument('--no-clocks', action='store_true', help='(diagnostic) do not sample nvidia-smi during the timed region')

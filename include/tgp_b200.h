@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-enum { TGP_F64 = 0, TGP_F32 = 1 };
+enum { TGP_F64 = 0, TGP_F32 = 1, TGP_F64_I8 = 2 };
 enum { TGP_LIK_GAUSS_LINEAR = 0,     /* likelihoods/GaussianLinearMean.py:60-87   (SVGP, closed form)      */
        TGP_LIK_GAUSS_NONLINEAR = 1,  /* likelihoods/GaussianNonLinearMean.py:113-150 (Gauss-Hermite)       */
        TGP_LIK_BERNOULLI = 2 };      /* likelihoods/Bernoulli.py:50-95                                      */
@@ -43,8 +43,12 @@ typedef struct TgpFlowLayer {
 
 typedef struct TgpModel {            /* host struct; describes one output GP */
     int dtype;                       /* TGP_F64: all FP64 (DMMA).  TGP_F32: batch contractions as 3xTF32 on
-                                      * tcgen05 with FP32 TMEM accumulators; per-step factorisation, chain and the
-                                      * row epilogue stay FP64; inputs / outputs are FP64 in both modes          */
+                                      * tcgen05 with FP32 TMEM accumulators.  TGP_F64_I8: batch contractions on the
+                                      * tcgen05 INTEGER path (kind::i8, exact s32 accumulation in TMEM) over 15-16
+                                      * residue planes, rebuilt by the Chinese remainder theorem — FP64-accurate
+                                      * (operands truncated at 52-53 bits below their row maximum).  Per-step
+                                      * factorisation, chain and the row epilogue are FP64 in every mode; inputs /
+                                      * outputs are FP64 in every mode                                            */
     int M, D;                        /* inducing points, input dimension                                   */
     int likelihood;                  /* TGP_LIK_*                                                          */
     int n_quad;                      /* Gauss-Hermite points (config.py:45,58: 100 in FP64, 50 in FP32)    */
@@ -221,6 +225,11 @@ int tgp_debug_gemm_f64(int M, int N, int K, const double* A, long lda, int a_lay
 int tgp_debug_gemm_tf32x3(int Mrows, int Ncols, int K, const float* Ahi, const float* Alo, long lda, const float* Bhi,
                           const float* Blo, long ldb, float* Cf, double* Cd, long ldc, int out_mode, int tri_mode,
                           int tri_rows, int lower_rows, int splitk, void* stream);
+/* Test hook: C (+)= A B^T (A: M x K, B: N x K, row-major FP64) through the integer-residue pipeline of TGP_F64_I8 with T
+ * moduli; tri_mode / tri_rows / lower_rows as in the tf32x3 hook; scratch: tgp_debug_gemm_crt_bytes() device bytes. */
+size_t tgp_debug_gemm_crt_bytes(long M, long N, long K, int T);
+int tgp_debug_gemm_crt(long M, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc,
+                       int T, int tri_mode, int tri_rows, int lower_rows, int accumulate, void* scratch, void* stream);
 /* Test hook: copies L, L^-1, C (each M x M, row-major, ld = M) out of a prepared step workspace. */
 int tgp_debug_export_step(const TgpModel* model, const void* step_ws, double* L, double* Linv, double* C,
                           void* stream);

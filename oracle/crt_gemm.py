@@ -1,7 +1,7 @@
 """CPU restatement of the integer-residue (CRT) FP64 contraction of csrc/gemm_i8.cuh — test infrastructure.
 
 C = A B^T for FP64 A (m x k), B (n x k), evaluated as the tcgen05 kind::i8 path does it ("Ozaki scheme II"):
-  1. integerise: A'[i,:] = rint(A[i,:] * 2^(b - eA_i)), 2^eA_i >= max_j |A_ij| (per row; likewise B), |A'| <= 2^b;
+  1. integerise: A'[i,:] = rint(A[i,:] * 2^(b - eA_i)), 2^eA_i > max_j |A_ij| (per row; likewise B), |A'| <= 2^b;
   2. residues: A_t = A' mod p_t (centred, int8) for T pairwise coprime moduli p_t <= 256;
   3. T independent int8 GEMMs with exact int32 accumulation, reduced mod p_t: R_t = (A_t B_t^T) mod p_t (int8 again);
   4. CRT: C' = sum_t R_t w_t mod P  (w_t = (P/p_t) * ((P/p_t)^-1 mod p_t)) in 40-bit words whose partial sums are exact in
@@ -28,7 +28,7 @@ def crt_constants(T):
     for t, p in enumerate(ps):
         q = P // p
         w = q * pow(q % p, -1, p)
-        frac[t] = float(w) / float(P) if False else (w / P)      # Python int true division: correctly rounded
+        frac[t] = w / P                                   # Python int true division: correctly rounded
         for k in range(N_WORDS):
             words[t, k] = float((w >> (WORD_BITS * k)) & ((1 << WORD_BITS) - 1))
     Pw = np.array([float((P >> (WORD_BITS * k)) & ((1 << WORD_BITS) - 1)) for k in range(N_WORDS)])
@@ -47,8 +47,7 @@ def max_bits(T, k_red):
 def integerise(A, b):
     """rows of A -> (int64 A' with |A'| <= 2^b, exponents e): A ~= A' * 2^(e - b)."""
     amax = np.abs(A).max(axis=1)
-    e = np.where(amax > 0, np.ceil(np.log2(np.where(amax > 0, amax, 1.0))), 0.0).astype(np.int64)
-    e = np.where(np.ldexp(1.0, e) < amax, e + 1, e)          # guard log2 rounding
+    e = np.where(amax > 0, np.frexp(amax)[1], 0).astype(np.int64)        # 2^e > max |A_ij| (frexp: max = f 2^e, f in [0.5, 1))
     Ai = np.rint(np.ldexp(A, (b - e)[:, None])).astype(np.int64)
     return Ai, e
 

@@ -1,0 +1,106 @@
+"""Compute mode 'i8crt' (TGP_F64_I8): FP64-accurate contractions on the tcgen05 integer tensor path (csrc/gemm_i8.cuh).
+
+The stand-alone product against an FP64 matmul and, entry for entry, against the CPU restatement oracle/crt_gemm.py; then
+the whole ELBO path against the reference fixtures at the FP64 tolerances."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crt_gemm as G
+from oracle import tgp_oracle as O
+from tests.golden_util import Golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _ab(M, N, K, seed, spread=3.0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp(spread * torch.randn(M, 1, generator=g, dtype=torch.float64))
+    B = torch.randn(N, K, generator=g, dtype=torch.float64) * torch.exp(spread * torch.randn(N, 1, generator=g, dtype=torch.float64))
+    return A, B
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 128), (100, 37, 53), (455, 100, 100), (257, 513, 1024), (1, 1, 1), (300, 2048, 1024)])
+@pytest.mark.parametrize('T', [16, 15])
+def test_crt_gemm_matches_fp64_matmul(M, N, K, T):
+    from tgp.pytorch_b200.engine import debug_gemm_crt
+    A, B = _ab(M, N, K, M + N + K + T)
+    out = torch.full((M, N + 3), 7.0, dtype=torch.float64, device=DEV)
+    debug_gemm_crt(A.to(DEV), B.to(DEV), out[:, :N], T=T)
+    ref = A @ B.t()
+    assert rel_err(out[:, :N].cpu(), ref) < 5e-15
+    # per-row accuracy too (rows differ in scale by e^3): every row is as good as FP64
+    rows = (out[:, :N].cpu() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-300)
+    assert float(rows.max()) < 1e-13
+    assert torch.all(out[:, N:] == 7.0)
+
+
+def test_crt_gemm_equals_the_cpu_restatement_entry_for_entry():
+    from tgp.pytorch_b200.engine import debug_gemm_crt
+    A, B = _ab(70, 45, 333, 5)
+    A[3] = 0.0
+    out = torch.zeros(70, 45, dtype=torch.float64, device=DEV)
+    debug_gemm_crt(A.to(DEV), B.to(DEV), out, T=16)
+    cpu = G.crt_matmul(A.numpy(), B.numpy(), 16)
+    assert np.array_equal(out.cpu().numpy(), cpu)          # same integers, same words, same final rounding
+
+
+def test_crt_gemm_triangular_lower_and_accumulate():
+    from tgp.pytorch_b200.engine import debug_gemm_crt
+    g = torch.Generator().manual_seed(9)
+    n = 512
+    Lo = torch.randn(n, n, generator=g, dtype=torch.float64).tril()
+    De = torch.randn(300, n, generator=g, dtype=torch.float64)
+    # tri_mode 1: B rows are lower triangular (k <= n): only the needed k-blocks are loaded
+    out = torch.zeros(300, n, dtype=torch.float64, device=DEV)
+    debug_gemm_crt(De.to(DEV), Lo.to(DEV), out, T=15, tri_mode=1, tri_rows=n)
+    assert rel_err(out.cpu(), De @ Lo.t()) < 5e-15
+    # tri_mode 2: B[n, k] nonzero only for k >= n
+    Up = Lo.t().contiguous()
+    out = torch.zeros(300, n, dtype=torch.float64, device=DEV)
+    debug_gemm_crt(De.to(DEV), Up.to(DEV), out, T=15, tri_mode=2, tri_rows=n)
+    assert rel_err(out.cpu(), De @ Up.t()) < 5e-15
+    # lower-only output, accumulated on top of existing values
+    S = torch.randn(n, 700, generator=g, dtype=torch.float64)
+    out = torch.ones(n, n, dtype=torch.float64, device=DEV)
+    debug_gemm_crt(S.to(DEV), S.to(DEV), out, T=16, lower_rows=n, accumulate=True)
+    ref = (S @ S.t()).tril() + 1.0
+    assert rel_err(out.cpu(), ref) < 5e-15
+
+
+REG = ['synth_reg_d8_m64_p1', 'boston_tgp_steptanh13_p1', 'boston_svgp_p1', 'power_tgp_sal2_p1', 'boston_tgp_sal2_p0',
+       'synth_reg_d8_m1024_p1', 'power_idtgp_nodrop_p1', 'boston_tgp_steptanh102_p1']
+
+
+@pytest.mark.parametrize('name', REG)
+def test_i8crt_mode_reproduces_the_reference_at_fp64_tolerances(name):
+    from tests.gpu_util import engine_inputs, make_engine
+    from tgp.pytorch_b200 import functional as Fn
+    from tests.conftest import record_residuals
+    g = Golden(name)
+    p = g.oracle_params('train')
+    lik, nq = g.meta['likelihood'], g.meta['n_quad']
+    eng, theta, rowp, names = make_engine(p, lik, nq, DEV, compute='i8crt')
+    ei = engine_inputs(p, DEV)
+    X, Y = g.t('X').to(DEV).contiguous(), g.t('Y').view(-1).to(DEV).contiguous()
+    leaves = [ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta] + ([rowp] if rowp is not None else [])
+    for t in leaves:
+        t.requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ELL, KLD, rows, mu, v = Fn.elbo_terms(eng, X, Y, g.meta['N'] / X.shape[0], ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'],
+                                              ei['L_raw'], ei['log_var_noise'], theta, rowp)
+        (ELL - KLD).backward()
+    grads = dict(Z=ei['Z'].grad, raw_lengthscale=ei['raw_ls'].grad, raw_outputscale=ei['raw_os'].grad.view(()), m=ei['m'].grad,
+                 L_raw=ei['L_raw'].grad, log_var_noise=ei['log_var_noise'].grad.view(()))
+    for i, n in enumerate(names):
+        grads[n] = theta.grad[i]
+    errs = g.grad_errors(grads)
+    vals = dict(ELBO=rel_err((ELL - KLD).detach().cpu(), g.t('ELBO')), mu=rel_err(mu.cpu(), g.t('mu')), v=rel_err(v.cpu(), g.t('v')))
+    record_residuals('i8crt:' + name, dict(errs, **vals))
+    assert vals['ELBO'] < 1e-10 and vals['mu'] < 1e-10 and vals['v'] < 1e-9, vals
+    bad = {k: e for k, e in errs.items() if not e < 1e-10}
+    assert not bad, (bad, errs)

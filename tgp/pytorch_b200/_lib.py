@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TGP_B200_LIB', os.path.join(_HERE, 'libtgp_b200.so'))
 
-TGP_F64, TGP_F32 = 0, 1
+TGP_F64, TGP_F32, TGP_F64_I8 = 0, 1, 2
 LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
 FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL = 0, 1, 2, 3
 FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
@@ -94,6 +94,8 @@ SIGNATURES = {
     'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'tgp_debug_gemm_f64': (_I, [_I, _I, _I, _P, _L, _I, _P, _L, _I, _P, _L, _D, _D, _I, _I, _I, _P]),
     'tgp_debug_gemm_tf32x3': (_I, [_I, _I, _I, _P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    'tgp_debug_gemm_crt_bytes': (C.c_size_t, [_L, _L, _L, _I]),
+    'tgp_debug_gemm_crt': (_I, [_L, _L, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P]),
     'tgp_debug_export_step': (_I, [C.POINTER(TgpModel), _P, _P, _P, _P, _P]),
 }
 

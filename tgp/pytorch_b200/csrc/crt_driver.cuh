@@ -1,0 +1,280 @@
+// Host-side orchestration of compute mode TGP_F64_I8: FP64-accurate batch contractions on the tcgen05 integer tensor path
+// (gemm_i8.cuh).  Same mathematics and reduce-buffer contents as the tensor-core mode of tc_driver.cuh (two independent
+// contractions of the K tile with the stacked operand W = [L^-1; C], C = L_S^T L^-1), but every product is exact up to a
+// 52/53-bit truncation of the operands, so the results carry the FP64 parity tolerances.
+#pragma once
+#include "step_kernels.cuh"
+#include "backward_kernels.cuh"
+#include "row_kernels.cuh"
+#include "gemm_i8.cuh"
+
+namespace tgp {
+namespace crt {
+
+using i8::Planes;
+constexpr long CRT_ROW_CHUNK = 16384;
+constexpr int T_ALL = 16;                          // planes generated for operands shared with the weight contraction
+
+inline long pad16(long x) { return (x + 15) / 16 * 16; }
+inline long chunk_rows(long R) { return R < CRT_ROW_CHUNK ? R : CRT_ROW_CHUNK; }
+
+// bits left for the second operand when the first one carries `fixed` bits: 2 k 2^(fixed + b) < P
+inline int bits_other(int T, long k_red, int fixed) {
+    const int b = (int)floor(i8::crt_table(T).log2P - 1.0 - log2((double)(k_red > 1 ? k_red : 1)) - (double)fixed - 1e-6);
+    return b > 53 ? 53 : (b < 1 ? 1 : b);
+}
+// forward  [A | B] = K W^T, reduction M: K carries 53 bits (one scale for the whole matrix); 15 moduli if W keeps >= 52 bits
+inline int fwd_T(int M) { return bits_other(15, M, 53) >= 52 ? 15 : 16; }
+inline int fwd_bits_w(int M) { return bits_other(fwd_T(M), M, 53); }
+// backward-data  Kbar = ABbar Wt^T, reduction 2M: equal bits for both operands
+inline int bwd_T(int M) { return i8::crt_bits(15, 2L * M) >= 52 ? 15 : 16; }
+inline int bwd_bits(int M) { return i8::crt_bits(bwd_T(M), 2L * M); }
+// weight contraction  [Gbar; Cbar] += ABbar^T K, reduction = rows of the chunk: all 16 moduli, K^T carries 53 bits
+inline int wgt_bits(long rc) { return bits_other(T_ALL, rc, 53); }
+
+struct StepPlanes {               // per step: residues of W = [Linv; C] (2M x M) and of W^T (M x 2M)
+    double* Wst;                  // FP64 stacked operand (2M x M, ld M)
+    int8_t *W, *Wt;               // planes [T_ALL][2M][ldk], [T_ALL][M][ld2m]
+    int *w_row_exp, *w_col_exp, *k_exp;
+    long ldk, ld2m;
+};
+
+inline size_t step_bytes(int M) {
+    const long ldk = pad16(M), ld2m = pad16(2L * M);
+    return (size_t)2 * M * M * sizeof(double) + (size_t)T_ALL * (2L * M * ldk + (long)M * ld2m) + (size_t)(3L * M + 64) * sizeof(int) + 1024;
+}
+
+inline StepPlanes carve_step(void* region, int M) {
+    StepPlanes s;
+    s.ldk = pad16(M); s.ld2m = pad16(2L * M);
+    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(region) + 255) & ~uintptr_t(255));
+    s.Wst = reinterpret_cast<double*>(p); p += (size_t)2 * M * M * sizeof(double);
+    s.W = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
+    s.Wt = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * (long)M * s.ld2m;
+    p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+    s.w_row_exp = reinterpret_cast<int*>(p); p += (size_t)2 * M * sizeof(int);
+    s.w_col_exp = reinterpret_cast<int*>(p); p += (size_t)M * sizeof(int);
+    s.k_exp = reinterpret_cast<int*>(p);
+    return s;
+}
+
+struct BatchView {
+    double *AB;                   // (R x 2M) FP64, forward -> backward ([A | B], turned into [Abar | Bbar] in place)
+    double *Kbuf;                 // (R x M) FP64 K_xz (kernel gradients read it)
+    double *Kbar;                 // (Rc x M)
+    int8_t *Kp;                   // planes [T_ALL][R][ldk]           K_xz residues (forward operand)
+    int8_t *KTp;                  // per chunk: planes [T_ALL][M][ldt]  transposed (weight contraction operand)
+    int8_t *Op;                   // planes [T][Rc][ld2m]             result residues of the forward / operand residues of ABbar
+    int8_t *PTp;                  // planes [T_ALL][2M][ldt]          ABbar^T residues
+    int8_t *Kbp;                  // planes [T][Rc][ldk]              Kbar result residues
+    int8_t *Gp;                   // planes [T_ALL][2M][ldk]          weight-contraction result residues
+    int *row_exp, *col_exp;       // (Rc), (2M)
+    long Rc, ldk, ld2m, ldt, nch;
+};
+
+inline size_t batch_bytes(int M, long R) {
+    const long Rc = chunk_rows(R), ldk = pad16(M), ld2m = pad16(2L * M), ldt = pad16(Rc), nch = (R + Rc - 1) / Rc;
+    size_t b = 0;
+    b += (size_t)R * 2 * M * 8 + (size_t)R * M * 8 + (size_t)Rc * M * 8;
+    b += (size_t)T_ALL * R * ldk + (size_t)nch * T_ALL * M * ldt;
+    b += (size_t)T_ALL * Rc * ld2m + (size_t)T_ALL * 2 * M * ldt + (size_t)T_ALL * Rc * ldk + (size_t)T_ALL * 2 * M * ldk;
+    b += (size_t)(Rc + 2L * M + 64) * sizeof(int) + 4096;
+    return b;
+}
+
+inline BatchView carve_batch(void* ws, int M, long R) {
+    BatchView b;
+    b.Rc = chunk_rows(R); b.ldk = pad16(M); b.ld2m = pad16(2L * M); b.ldt = pad16(b.Rc); b.nch = (R + b.Rc - 1) / b.Rc;
+    char* p = reinterpret_cast<char*>(ws);
+    auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
+    b.AB = reinterpret_cast<double*>(take((size_t)R * 2 * M * 8));
+    b.Kbuf = reinterpret_cast<double*>(take((size_t)R * M * 8));
+    b.Kbar = reinterpret_cast<double*>(take((size_t)b.Rc * M * 8));
+    b.Kp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * R * b.ldk));
+    b.KTp = reinterpret_cast<int8_t*>(take((size_t)b.nch * T_ALL * M * b.ldt));
+    b.Op = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
+    b.PTp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * 2 * M * b.ldt));
+    b.Kbp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ldk));
+    b.Gp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * 2 * M * b.ldk));
+    b.row_exp = reinterpret_cast<int*>(take((size_t)b.Rc * sizeof(int)));
+    b.col_exp = reinterpret_cast<int*>(take((size_t)2 * M * sizeof(int)));
+    return b;
+}
+
+// stacked FP64 operand Wst = [Linv; C] (ld M) from the padded step matrices (ld Mp)
+__global__ void k_stack_w(const double* __restrict__ Linv, const double* __restrict__ Cm, long ld, int M, double* __restrict__ Wst) {
+    const int r = blockIdx.x;
+    const double* src = r < M ? Linv + (long)r * ld : Cm + (long)(r - M) * ld;
+    for (int c = threadIdx.x; c < M; c += blockDim.x) Wst[(long)r * M + c] = src[c];
+}
+__global__ void k_exp_of_scalar(const double* __restrict__ x, int* __restrict__ e) { e[0] = i8::exp_above(x[0]); }
+
+inline int fill_int(int* p, long n, int v, cudaStream_t st) {
+    i8::k_fill_int<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(p, n, v);
+    return check_launch("k_fill_int");
+}
+
+inline int exponents(const double* src, long ld, long rows, int cols, int* row_exp, int* col_exp, cudaStream_t st) {
+    if (row_exp) TGP_TRY(fill_int(row_exp, rows, -100000, st));
+    if (col_exp) TGP_TRY(fill_int(col_exp, cols, -100000, st));
+    dim3 grid((unsigned)cdiv(cols, 256), (unsigned)cdiv(rows, 64));
+    i8::k_exponents<<<grid, 256, 0, st>>>(src, ld, rows, cols, row_exp, col_exp);
+    return check_launch("k_exponents");
+}
+
+inline int to_residues(const double* src, long ld, long rows, int cols, int scale_mode, const int* exps, int bits, int T,
+                       int8_t* planes, long ldp, long plane_stride, int8_t* planesT, long ldt, long plane_strideT, cudaStream_t st) {
+    dim3 grid((unsigned)cdiv(cols, i8::RS_TC), (unsigned)cdiv(rows, i8::RS_TR));
+    i8::k_to_residues<<<grid, 256, 0, st>>>(src, ld, rows, cols, scale_mode, exps, bits, i8::crt_table(T), planes, ldp, plane_stride,
+                                           planesT, ldt, plane_strideT);
+    return check_launch("k_to_residues");
+}
+
+inline int combine(const int8_t* R, long ldr, long plane_stride, long rows, int cols, int T, int bits2, const int* ea, int ea_mode,
+                   const int* eb, int eb_mode, double* out, long ldo, int accumulate, int lower_rows, cudaStream_t st) {
+    i8::k_crt_combine<<<i8::crt_grid(rows), 256, 0, st>>>(R, ldr, plane_stride, rows, cols, i8::crt_table(T), bits2, ea, ea_mode, eb,
+                                                         eb_mode, out, ldo, accumulate, lower_rows);
+    return check_launch("k_crt_combine");
+}
+
+// per step, after run_prepare: residues of W (per-row scale, forward) and of W^T (per-column scale of W, backward-data)
+inline int make_step_planes(const StepView& v, void* region, cudaStream_t st) {
+    const int M = v.M;
+    StepPlanes s = carve_step(region, M);
+    k_stack_w<<<2 * M, 256, 0, st>>>(v.Linv, v.Cm, v.Mp, M, s.Wst);
+    TGP_TRY(check_launch("k_stack_w"));
+    k_exp_of_scalar<<<1, 1, 0, st>>>(v.os, s.k_exp);
+    TGP_TRY(check_launch("k_exp_of_scalar"));
+    TGP_TRY(exponents(s.Wst, M, 2L * M, M, s.w_row_exp, s.w_col_exp, st));
+    TGP_TRY(to_residues(s.Wst, M, 2L * M, M, 0, s.w_row_exp, fwd_bits_w(M), fwd_T(M), s.W, s.ldk, 2L * M * s.ldk, nullptr, 0, 0, st));
+    TGP_TRY(to_residues(s.Wst, M, 2L * M, M, 1, s.w_col_exp, bwd_bits(M), bwd_T(M), nullptr, 0, 0, s.Wt, s.ld2m, (long)M * s.ld2m, st));
+    return 0;
+}
+
+// [A | B] + upstream row gradients -> [Abar | Bbar] IN PLACE (Abar = g_mu m - 2 g_v A, Bbar = 2 g_v B); accumulates
+// dm[j] += sum_n g_mu A[n,j] and dos += sum_n g_v.  64 rows x 128 columns per CTA.
+__global__ void __launch_bounds__(128) k_make_abbar_inplace(double* __restrict__ AB, const double* __restrict__ g_mu,
+                                                            const double* __restrict__ g_v, const double* __restrict__ m, long R,
+                                                            int M, double* __restrict__ dm, double* __restrict__ dos) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const long n0 = (long)blockIdx.y * 64, n1 = min(n0 + 64, R);
+    const double mj = j < M ? m[j] : 0.0;
+    double acc = 0.0, accv = 0.0;
+    for (long n = n0; n < n1; ++n) {
+        const double gm = g_mu[n], gv = g_v[n];
+        accv += gv;
+        if (j < M) {
+            double* row = AB + n * 2 * M;
+            const double a = row[j], b = row[M + j];
+            acc = fma(gm, a, acc);
+            row[j] = gm * mj - 2.0 * gv * a;
+            row[M + j] = 2.0 * gv * b;
+        }
+    }
+    if (j < M) atomicAdd(dm + j, acc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(dos, accv);
+}
+
+inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, const double* X, long R, double* mu, double* v,
+                      cudaStream_t st) {
+    const int M = s.M, D = s.D;
+    StepPlanes sp = carve_step(step_region, M);
+    BatchView b = carve_batch(batch_ws, M, R);
+    const int Tf = fwd_T(M), bits = fwd_bits_w(M);
+    for (long r0 = 0; r0 < R; r0 += b.Rc) {
+        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
+        double* Kc = b.Kbuf + r0 * M;
+        TGP_TRY(launch_rbf(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
+        // K residues: one scale for the whole matrix (0 <= k <= outputscale), shared by the forward and the weight contraction
+        int8_t* KTc = b.KTp + (r0 / b.Rc) * (long)T_ALL * M * b.ldt;
+        TGP_TRY(to_residues(Kc, M, rc, M, 2, sp.k_exp, 53, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, KTc, b.ldt, (long)M * b.ldt, st));
+        i8::Params p{};
+        p.Mrows = rc; p.Ncols = 2 * M; p.K = M; p.T = Tf; p.tri_mode = 1; p.tri_rows = M; p.lower_rows = 0;
+        p.C = b.Op; p.ldc = b.ld2m; p.plane_stride_c = (long)b.Rc * b.ld2m;
+        Planes A{b.Kp + r0 * b.ldk, rc, M, b.ldk, R * b.ldk};
+        Planes B{sp.W, 2L * M, M, sp.ldk, 2L * M * sp.ldk};
+        TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
+        TGP_TRY(combine(b.Op, b.ld2m, (long)b.Rc * b.ld2m, rc, 2 * M, Tf, 53 + bits, sp.k_exp, 2, sp.w_row_exp, 1, b.AB + r0 * 2 * M,
+                        2L * M, 0, 0, st));
+    }
+    k_row_stats<<<(unsigned)min((long)148 * 16, cdiv(R, ROW_THREADS / 32)), ROW_THREADS, 0, st>>>(b.AB, s.mvec, s.os, (int)R, M, mu, v);
+    return check_launch("k_row_stats");
+}
+
+inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, const double* X, long R, const double* g_mu,
+                       const double* g_v, double* dm, double* dos, double* dZ, double* dls, double* Gbar, double* Cbar,
+                       cudaStream_t st) {
+    const int M = s.M, D = s.D;
+    StepPlanes sp = carve_step(step_region, M);
+    BatchView b = carve_batch(batch_ws, M, R);
+    const int Tb = bwd_T(M), bits_b = bwd_bits(M);
+    for (long r0 = 0; r0 < R; r0 += b.Rc) {
+        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
+        double* ABc = b.AB + r0 * 2 * M;
+        {
+            dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rc, 64));
+            k_make_abbar_inplace<<<grid, 128, 0, st>>>(ABc, g_mu + r0, g_v + r0, s.mvec, rc, M, dm, dos);
+            TGP_TRY(check_launch("k_make_abbar_inplace"));
+        }
+        TGP_TRY(exponents(ABc, 2L * M, rc, 2 * M, b.row_exp, b.col_exp, st));
+        // row-scaled residues (operand of Kbar = ABbar W) and column-scaled transposed residues (operand of ABbar^T K)
+        TGP_TRY(to_residues(ABc, 2L * M, rc, 2 * M, 0, b.row_exp, bits_b, Tb, b.Op, b.ld2m, (long)b.Rc * b.ld2m, nullptr, 0, 0, st));
+        const int Tw = T_ALL, bits_w = wgt_bits(rc);
+        TGP_TRY(to_residues(ABc, 2L * M, rc, 2 * M, 1, b.col_exp, bits_w, Tw, nullptr, 0, 0, b.PTp, b.ldt, 2L * M * b.ldt, st));
+        {   // Kbar (rc x M) = ABbar (rc x 2M) * Wt (M x 2M)^T ; for k < M only k >= n contributes
+            i8::Params p{};
+            p.Mrows = rc; p.Ncols = M; p.K = 2 * M; p.T = Tb; p.tri_mode = 2; p.tri_rows = M; p.lower_rows = 0;
+            p.C = b.Kbp; p.ldc = b.ldk; p.plane_stride_c = (long)b.Rc * b.ldk;
+            Planes A{b.Op, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
+            Planes B{sp.Wt, M, 2L * M, sp.ld2m, (long)M * sp.ld2m};
+            TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
+            TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, 0, sp.w_col_exp, 1, b.Kbar, M, 0, 0, st));
+        }
+        TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
+        {   // [Gbar; Cbar] (2M x M) += ABbar^T K : operands ABbar^T (2M x rc) and K^T (M x rc), reduction over the chunk rows
+            const int8_t* KTc = b.KTp + (r0 / b.Rc) * (long)T_ALL * M * b.ldt;
+            i8::Params p{};
+            p.Mrows = 2 * M; p.Ncols = M; p.K = rc; p.T = Tw; p.tri_mode = 0; p.tri_rows = 0; p.lower_rows = M;
+            p.C = b.Gp; p.ldc = b.ldk; p.plane_stride_c = 2L * M * b.ldk;
+            Planes A{b.PTp, 2L * M, rc, b.ldt, 2L * M * b.ldt};
+            Planes B{KTc, M, rc, b.ldt, (long)M * b.ldt};
+            TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
+            // K^T residues were integerised with 53 bits (forward), ABbar^T with bits_w
+            TGP_TRY(combine(b.Gp, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_w + 53, b.col_exp, 0, sp.k_exp, 2, Gbar, s.Mp, 1, M, st));
+            TGP_TRY(combine(b.Gp + (long)M * b.ldk, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_w + 53, b.col_exp + M, 0, sp.k_exp, 2, Cbar,
+                            s.Mp, 1, 0, st));
+        }
+    }
+    return 0;
+}
+
+// ---- test hook: C = A B^T through the residue pipeline ------------------------------------------------------------------
+inline size_t debug_bytes(long Mr, long N, long K, int T) {
+    const long ldk = pad16(K), ldn = pad16(N);
+    return (size_t)T * (Mr * ldk + N * ldk + Mr * ldn) + (size_t)(Mr + N + 64) * sizeof(int) + 4096;
+}
+
+inline int debug_matmul(long Mr, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc, int T,
+                        int tri_mode, int tri_rows, int lower_rows, int accumulate, void* scratch, cudaStream_t st) {
+    const long ldk = pad16(K), ldn = pad16(N);
+    char* p = reinterpret_cast<char*>(scratch);
+    auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
+    int8_t* Ap = reinterpret_cast<int8_t*>(take((size_t)T * Mr * ldk));
+    int8_t* Bp = reinterpret_cast<int8_t*>(take((size_t)T * N * ldk));
+    int8_t* Cp = reinterpret_cast<int8_t*>(take((size_t)T * Mr * ldn));
+    int* ea = reinterpret_cast<int*>(take((size_t)Mr * sizeof(int)));
+    int* eb = reinterpret_cast<int*>(take((size_t)N * sizeof(int)));
+    const int bits = i8::crt_bits(T, K);
+    TGP_TRY(exponents(A, lda, Mr, (int)K, ea, nullptr, st));
+    TGP_TRY(exponents(B, ldb, N, (int)K, eb, nullptr, st));
+    TGP_TRY(to_residues(A, lda, Mr, (int)K, 0, ea, bits, T, Ap, ldk, Mr * ldk, nullptr, 0, 0, st));
+    TGP_TRY(to_residues(B, ldb, N, (int)K, 0, eb, bits, T, Bp, ldk, N * ldk, nullptr, 0, 0, st));
+    i8::Params q{};
+    q.Mrows = (int)Mr; q.Ncols = (int)N; q.K = (int)K; q.T = T; q.tri_mode = tri_mode; q.tri_rows = tri_rows; q.lower_rows = lower_rows;
+    q.C = Cp; q.ldc = ldn; q.plane_stride_c = Mr * ldn;
+    TGP_TRY(i8::gemm_i8_mod(Planes{Ap, Mr, K, ldk, Mr * ldk}, Planes{Bp, N, K, ldk, N * ldk}, q, st));
+    return combine(Cp, ldn, Mr * ldn, Mr, (int)N, T, 2 * bits, ea, 0, eb, 1, C, ldc, accumulate, lower_rows, st);
+}
+
+}  // namespace crt
+}  // namespace tgp

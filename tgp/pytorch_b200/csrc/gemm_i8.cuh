@@ -1,0 +1,516 @@
+// FP64-accurate contraction on the tcgen05 INTEGER tensor path (kind::i8, s8 x s8 -> s32 in TMEM): the batch contractions
+// of compute mode TGP_F64_I8.
+//
+// tcgen05 has no f64 kind, and a floating-point split (3xTF32, gemm_tc.cuh) is limited by the FP32 accumulator.  Integer
+// MMAs accumulate EXACTLY, so the product can be rebuilt exactly from residues (Chinese remainder theorem; "Ozaki scheme
+// II" in the literature):
+//   1. integerise  A'[i,:] = rint(A[i,:] 2^(b - eA_i)),  2^eA_i > max_j |A_ij|   (|A'| < 2^b, b <= 53; likewise B per row)
+//   2. residues    A_t = A' mod p_t  (centred, int8)  for T pairwise coprime moduli p_t <= 256            [k_to_residues]
+//   3. T independent int8 GEMMs with exact s32 accumulation, reduced mod p_t in the epilogue: R_t = A_t B_t^T mod p_t
+//      (int8 again)                                                                                      [gemm_i8_mod_kernel]
+//   4. CRT         C' = sum_t R_t w_t - m P   in 40-bit words whose partial sums are exact in FP64,  m = rint(sum_t R_t w_t/P)
+//   5. scale       C = C' 2^(eA_i + eB_j - 2b)                                                            [k_crt_combine]
+// The integer product is exact; the only error is the b-bit truncation of the operands below their row maximum
+// (b = 53 with T = 15 moduli for reductions up to 1024, T = 16 up to 2^17) — at or below FP64 GEMM rounding.
+// oracle/crt_gemm.py restates steps 1-5 in numpy / exact Python integers (tests/test_crt_oracle.py).
+//
+// gemm_i8_mod_kernel: persistent, warp-specialised, one CTA per SM (TMA producer warp, single-thread MMA issuer, eight
+// epilogue warps); tile 128 x 256 x 128 (one 128-byte swizzle row of int8 per k-block), 4-stage mbarrier ring (192 KiB),
+// two 256-column TMEM accumulators so that the mod-p epilogue of one (tile, modulus) overlaps the MMAs of the next.
+// N = 256 per MMA is what reaches the integer peak (scripts/microbench/mma_rate.cu: 4556 Tops/s at N = 256, 1991 at N = 64).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_f64.cuh"      // GemmTimer
+#include "gemm_tc.cuh"       // PTX wrappers (mbarrier, TMA, tcgen05 fences / commit), encode_fn
+
+namespace tgp {
+namespace i8 {
+
+constexpr int MAX_T = 16;
+constexpr int WORD_BITS = 40, N_WORDS = 4;
+constexpr int BM = 128, BN = 256, BK = 128;          // BK in bytes == int8 elements
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int UMMA_K = 32;                            // kind::i8: 32 bytes of K per MMA
+
+static const int MODULI[MAX_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
+
+struct CrtTable {                 // passed by value to the kernels (< 1 KiB)
+    int T;
+    int p[MAX_T];
+    float invp[MAX_T];
+    double w[MAX_T][N_WORDS];     // words of w_t = (P/p_t) * ((P/p_t)^-1 mod p_t)
+    double frac[MAX_T];           // w_t / P
+    double Pw[N_WORDS];           // words of P
+    double log2P;
+};
+
+inline const CrtTable& crt_table(int T) {
+    static CrtTable tabs[MAX_T + 1];
+    static bool have[MAX_T + 1] = {};
+    if (T < 1) T = 1;
+    if (T > MAX_T) T = MAX_T;
+    if (!have[T]) {
+        typedef unsigned __int128 u128;
+        CrtTable& c = tabs[T];
+        c.T = T;
+        u128 P = 1;
+        for (int t = 0; t < T; ++t) P *= (u128)MODULI[t];
+        const u128 mask = (((u128)1) << WORD_BITS) - 1;
+        auto to_ld = [](u128 x) { return (long double)(unsigned long long)(x >> 64) * 18446744073709551616.0L + (long double)(unsigned long long)x; };
+        for (int t = 0; t < T; ++t) {
+            const int p = MODULI[t];
+            c.p[t] = p; c.invp[t] = 1.0f / (float)p;
+            const u128 q = P / (u128)p;
+            const int qm = (int)(q % (u128)p);
+            int inv = 1;
+            while ((qm * inv) % p != 1) ++inv;
+            const u128 w = q * (u128)inv;
+            for (int k = 0; k < N_WORDS; ++k) c.w[t][k] = (double)(unsigned long long)((w >> (WORD_BITS * k)) & mask);
+            c.frac[t] = (double)(to_ld(w) / to_ld(P));
+        }
+        for (int k = 0; k < N_WORDS; ++k) c.Pw[k] = (double)(unsigned long long)((P >> (WORD_BITS * k)) & mask);
+        c.log2P = (double)log2l(to_ld(P));
+        have[T] = true;
+    }
+    return tabs[T];
+}
+
+// largest b (bits per operand) with 2 * k_red * 2^(2b) < P (and a 2^-30 margin for the rounding of m)
+inline int crt_bits(int T, long k_red) {
+    const double room = crt_table(T).log2P - 1.0 - log2((double)(k_red > 1 ? k_red : 1)) - 1e-6;
+    int b = (int)floor(room / 2.0);
+    return b > 53 ? 53 : (b < 1 ? 1 : b);
+}
+
+// ---- step 1 + 2: FP64 -> residue planes -----------------------------------------------------------------------------
+// exponent e with 2^e > |x| (e = 0 for x = 0)
+__device__ __forceinline__ int exp_above(double x) {
+    int e;
+    frexp(x, &e);
+    return x == 0.0 ? 0 : e;
+}
+
+// row_exp[r] = max over the row, col_exp[c] = max over the column (atomicMax; both optional, pre-set to a very small value)
+__global__ void __launch_bounds__(256) k_exponents(const double* __restrict__ src, long ld, long rows, int cols,
+                                                   int* __restrict__ row_exp, int* __restrict__ col_exp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256;
+    const long r0 = (long)blockIdx.y * 64;
+    int cmax[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cmax[i] = -100000;
+    for (long r = r0 + warp; r < min(r0 + 64, rows); r += 8) {
+        int rmax = -100000;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + lane + 32 * i;
+            if (c < cols) {
+                const int e = exp_above(src[r * ld + c]);
+                rmax = max(rmax, e);
+                cmax[i] = max(cmax[i], e);
+            }
+        }
+        if (row_exp) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+            if (lane == 0) atomicMax(row_exp + r, rmax);
+        }
+    }
+    if (col_exp) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + lane + 32 * i;
+            if (c < cols && cmax[i] > -100000) atomicMax(col_exp + c, cmax[i]);
+        }
+    }
+}
+
+__global__ void k_fill_int(int* __restrict__ p, long n, int v) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// centred residue of the integer-valued double x (|x| < 2^53) modulo p, as int in [-128, 127]
+__device__ __forceinline__ int residue_of(double x, int p, double invp) {
+    const double q = rint(x * invp);
+    double r = fma(-q, (double)p, x);                 // exact: |r| < 1.5 p
+    const double h = 0.5 * (double)p;
+    if (r >= h) r -= (double)p;
+    if (r < -h) r += (double)p;
+    return (int)r;                                    // [-p/2, p/2): fits int8 for p <= 256
+}
+
+// src (rows x cols, ld) -> planes[t][r][c] (ldp bytes per row, plane_stride bytes per plane) and / or transposed planes
+// planesT[t][c][r] (ldt, plane_strideT).  Scaling: x * 2^(bits - e) with e = row_exp[r] (scale_mode 0), col_exp[c] (1) or
+// the single exponent exp0[0] (2).  32 x 128 tile per CTA, staged through shared memory for the transposed write.
+constexpr int RS_TR = 32, RS_TC = 128;
+__global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ src, long ld, long rows, int cols, int scale_mode,
+                                                     const int* __restrict__ exps, int bits, CrtTable tab,
+                                                     int8_t* __restrict__ planes, long ldp, long plane_stride,
+                                                     int8_t* __restrict__ planesT, long ldt, long plane_strideT) {
+    __shared__ int8_t tile[RS_TR][RS_TC + 4];
+    const long r0 = (long)blockIdx.y * RS_TR;
+    const int c0 = blockIdx.x * RS_TC;
+    const int tid = threadIdx.x;
+    // each thread owns 16 elements of the tile: row tr = tid / 8, columns tc0 + 8 * i + ...; keep them as scaled doubles
+    const int tr = tid >> 3, tcb = (tid & 7) * 16;
+    double x[16];
+    const long r = r0 + tr;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = c0 + tcb + i;
+        double v = 0.0;
+        if (r < rows && c < cols) {
+            const int e = scale_mode == 0 ? exps[r] : (scale_mode == 1 ? exps[c] : exps[0]);
+            v = rint(scalbn(src[r * ld + c], bits - e));
+        }
+        x[i] = v;
+    }
+    for (int t = 0; t < tab.T; ++t) {
+        const int p = tab.p[t];
+        const double invp = 1.0 / (double)p;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) word |= ((uint32_t)(residue_of(x[4 * j + i], p, invp) & 0xff)) << (8 * i);
+            w[j] = word;
+        }
+        if (planes && r < rows && c0 + tcb < cols) {
+            int8_t* dst = planes + (long)t * plane_stride + r * ldp + c0 + tcb;       // zero residues pad the row up to ldp
+            if (c0 + tcb + 16 <= ldp) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            else for (int i = 0; i < 16 && c0 + tcb + i < ldp; ++i) dst[i] = (int8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xff);
+        }
+        if (planesT) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t*>(&tile[tr][tcb + 4 * j]) = w[j];
+            __syncthreads();
+            // transposed write: thread -> column tcT = tid / 2, 16 consecutive rows
+            const int cT = tid >> 1, rb = (tid & 1) * 16;
+            const int c = c0 + cT;
+            if (c < cols && r0 + rb < ldt) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    o[j] = ((uint32_t)(uint8_t)tile[rb + 4 * j][cT]) | ((uint32_t)(uint8_t)tile[rb + 4 * j + 1][cT] << 8) |
+                           ((uint32_t)(uint8_t)tile[rb + 4 * j + 2][cT] << 16) | ((uint32_t)(uint8_t)tile[rb + 4 * j + 3][cT] << 24);
+                int8_t* dst = planesT + (long)t * plane_strideT + (long)c * ldt + r0 + rb;
+                if (r0 + rb + 16 <= ldt) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+                else for (int i = 0; i < 16 && r0 + rb + i < ldt; ++i) dst[i] = (int8_t)((o[i >> 2] >> (8 * (i & 3))) & 0xff);
+            }
+        }
+    }
+}
+
+// ---- step 3: the int8 GEMMs ------------------------------------------------------------------------------------------
+struct Params {
+    int Mrows, Ncols, K, T;
+    int tri_mode, tri_rows;          // as gemm_tc.cuh: 1: B rows n < tri_rows are lower triangular (k <= n);  2: k < tri_rows needs k >= n
+    int lower_rows;                  // > 0: for output rows m < lower_rows tiles strictly above the diagonal are skipped
+    int8_t* C; long ldc, plane_stride_c;       // residue planes of the result [t][m][n]
+    int p[MAX_T]; float invp[MAX_T];
+};
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// kind::i8: signed 8-bit A and B, S32 accumulate, both K-major, M = 128, N = BN
+__device__ __forceinline__ uint32_t make_idesc_i8() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(tc::smem_u32(dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ int mod_centered(int acc, int p, float invp) {
+    // q within +-1 of acc / p (the float rounding of acc costs < 64 / 193 of a quotient step); r exact in integers
+    const int q = __float2int_rn((float)acc * invp);
+    int r = acc - q * p;
+    const int h = p >> 1;
+    r = r >= h ? r - p : r;
+    r = r < -h ? r + p : r;
+    r = r >= h ? r - p : r;
+    r = r < -h ? r + p : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.Mrows + BM - 1) / BM, tiles_n = (p.Ncols + BN - 1) / BN;
+    const long n_work = (long)p.T * tiles_m * tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item -> (modulus t, m-tile, n-tile, k-range); n fastest (the A row block is shared by consecutive CTAs),
+    // modulus slowest (one modulus' planes of both operands fit the L2)
+    auto decode = [&](long w, int& t, int& m0, int& n0, int& kb, int& ke) -> bool {
+        n0 = (int)(w % tiles_n) * BN;
+        const long r = w / tiles_n;
+        m0 = (int)(r % tiles_m) * BM;
+        t = (int)(r / tiles_m);
+        if (p.lower_rows > 0 && m0 < p.lower_rows && n0 > m0 + BM - 1) return false;
+        kb = 0; ke = p.K;
+        if (p.tri_mode == 1 && n0 < p.tri_rows) ke = min(p.K, n0 + BN);
+        if (p.tri_mode == 2 && n0 < p.tri_rows) kb = (n0 / BK) * BK;
+        return ke > kb;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int t, m0, n0, kb, ke;
+                if (!decode(w, t, m0, n0, kb, ke)) continue;
+                for (int k = kb; k < ke; k += BK) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_3d(st, &mapA, &full[stage], k, m0, t);
+                    tma_load_3d(st + A_BYTES, &mapB, &full[stage], k, n0, t);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8();
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t bphase = 0;
+            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int t, m0, n0, kb, ke;
+                if (!decode(w, t, m0, n0, kb, ke)) continue;
+                mbar_wait(&tempty[buf], bphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
+                uint32_t accum = 0;
+                for (int k = kb; k < ke; k += BK) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    uint8_t* st = smem + stage * STAGE_BYTES;
+                    const uint64_t dA = make_desc(st), dB = make_desc(st + A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * UMMA_K) >> 4);
+                        umma_i8(tmem_d, dA + adv, dB + adv, idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[buf]);
+                if (++buf == 2) { buf = 0; bphase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int buf = 0; uint32_t bphase = 0;
+        for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            int t, m0, n0, kb, ke;
+            if (!decode(w, t, m0, n0, kb, ke)) continue;
+            const int pm = p.p[t];
+            const float ip = p.invp[t];
+            mbar_wait(&tfull[buf], bphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)buf * BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
+            const int row = m0 + q * 32 + lane;
+            const int nbase = n0 + half * 128;
+            int8_t* dst = p.C + (long)t * p.plane_stride_c + (long)row * p.ldc + nbase;
+#pragma unroll
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t r[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)c));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t packed[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) word |= ((uint32_t)(mod_centered((int)r[4 * i + j], pm, ip) & 0xff)) << (8 * j);
+                    packed[i] = word;
+                }
+                if (row < p.Mrows) {
+                    if (nbase + c + 32 <= p.ldc) {
+                        *reinterpret_cast<uint4*>(dst + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        *reinterpret_cast<uint4*>(dst + c + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    } else {
+                        for (int i = 0; i < 32 && nbase + c + i < p.ldc; ++i) dst[c + i] = (int8_t)((packed[i >> 2] >> (8 * (i & 3))) & 0xff);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (++buf == 2) { buf = 0; bphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// 3D map over residue planes: (cols = K bytes, rows, T); box = 128 bytes x box_rows x 1, 128B swizzle
+struct PlaneMapKey { const void* base; long rows, cols, ld, plane_stride; int T, box_rows; };
+struct PlaneMapCache {
+    static constexpr int N = 32;
+    PlaneMapKey key[N]; CUtensorMap map[N]; int used = 0, next = 0;
+};
+inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long cols, long ld, long plane_stride, int T, int box_rows) {
+    static PlaneMapCache cache;
+    for (int i = 0; i < cache.used; ++i) {
+        const PlaneMapKey& k = cache.key[i];
+        if (k.base == base && k.rows == rows && k.cols == cols && k.ld == ld && k.plane_stride == plane_stride && k.T == T && k.box_rows == box_rows) {
+            *map = cache.map[i];
+            return 0;
+        }
+    }
+    tc::EncodeTiledFn fn = tc::encode_fn();
+    if (!fn) return set_error(-101, "cuTensorMapEncodeTiled not available from the driver");
+    if ((ld & 15) != 0 || (plane_stride & 15) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0)
+        return set_error(-2, "residue planes must be 16-byte aligned with 16-byte multiples as strides");
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)T};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld, (cuuint64_t)plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-102, "cuTensorMapEncodeTiled (residue planes) failed");
+    const int i = cache.used < PlaneMapCache::N ? cache.used++ : (cache.next = (cache.next + 1) % PlaneMapCache::N);
+    cache.key[i] = PlaneMapKey{base, rows, cols, ld, plane_stride, T, box_rows};
+    cache.map[i] = *map;
+    return 0;
+}
+
+struct Planes { const int8_t* base; long rows, cols, ld, plane_stride; };       // cols = reduction length (bytes)
+
+inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t st) {
+    if (p.Mrows <= 0 || p.Ncols <= 0 || p.K <= 0) return 0;
+    if ((long)p.K * 16384 >= 2147483648L) return set_error(-3, "int8 reduction too long for exact s32 accumulation (K < 131072)");
+    CUtensorMap mA, mB;
+    TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BM));
+    TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BN));
+    const CrtTable& tab = crt_table(p.T);
+    for (int t = 0; t < p.T; ++t) { p.p[t] = tab.p[t]; p.invp[t] = tab.invp[t]; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) cudaFuncSetAttribute(gemm_i8_mod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    const long tiles = (long)cdiv(p.Mrows, BM) * cdiv(p.Ncols, BN) * p.T;
+    const int grid = (int)(tiles < 148 ? tiles : 148);
+    const bool timed = g_gemm_timer.enabled;
+    if (timed) g_gemm_timer.begin(2, st);
+    gemm_i8_mod_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB, p);
+    if (timed) g_gemm_timer.end(st);
+    return check_launch("gemm_i8_mod_kernel");
+}
+
+// ---- step 4 + 5: CRT reconstruction -----------------------------------------------------------------------------------
+// value of sum_t r_t w_t mod P (centred) for one output element, as a double (relative error <= 3 * 2^-53)
+__device__ __forceinline__ double crt_value(const int* r, const CrtTable& tab) {
+    double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0, mf = 0.0;
+#pragma unroll
+    for (int t = 0; t < MAX_T; ++t) {
+        if (t < tab.T) {
+            const double rt = (double)r[t];
+            S0 = fma(rt, tab.w[t][0], S0);
+            S1 = fma(rt, tab.w[t][1], S1);
+            S2 = fma(rt, tab.w[t][2], S2);
+            S3 = fma(rt, tab.w[t][3], S3);
+            mf = fma(rt, tab.frac[t], mf);
+        }
+    }
+    const double m = rint(mf);
+    double D0 = fma(-m, tab.Pw[0], S0), D1 = fma(-m, tab.Pw[1], S1), D2 = fma(-m, tab.Pw[2], S2), D3 = fma(-m, tab.Pw[3], S3);
+    const double two = 1099511627776.0, inv = 9.094947017729282e-13;       // 2^40, 2^-40
+    double c = rint(D0 * inv); D0 = fma(-c, two, D0); D1 += c;
+    c = rint(D1 * inv); D1 = fma(-c, two, D1); D2 += c;
+    c = rint(D2 * inv); D2 = fma(-c, two, D2); D3 += c;
+    return fma(fma(fma(D3, two, D2), two, D1), two, D0);
+}
+
+// R planes [t][rows][ldr] -> out[r * ldo + c] = (or +=) crt * 2^(ea + eb - bits2)
+//   ea: row exponents (ea_mode 0) / one exponent ea[0] (ea_mode 2);  eb: per-column exponents (eb_mode 1) / eb[0] (2)
+//   accumulate = 1: FP64 atomicAdd (weight gradients summed over row chunks); lower_rows > 0: rows r < lower_rows only c <= r
+// one warp per row, four consecutive columns per lane per step
+__global__ void __launch_bounds__(256) k_crt_combine(const int8_t* __restrict__ R, long ldr, long plane_stride, long rows, int cols,
+                                                     CrtTable tab, int bits2, const int* __restrict__ ea, int ea_mode,
+                                                     const int* __restrict__ eb, int eb_mode, double* __restrict__ out, long ldo,
+                                                     int accumulate, int lower_rows) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (long r = (long)blockIdx.x * wpb + wid; r < rows; r += (long)gridDim.x * wpb) {
+        const int era = ea_mode == 0 ? ea[r] : ea[0];
+        const int climit = (lower_rows > 0 && r < lower_rows) ? (int)min((long)cols, r + 1) : cols;
+        for (int c0 = lane * 4; c0 < climit; c0 += 128) {
+            uint32_t w[MAX_T];
+#pragma unroll
+            for (int t = 0; t < MAX_T; ++t)
+                w[t] = t < tab.T ? *reinterpret_cast<const uint32_t*>(R + (long)t * plane_stride + r * ldr + c0) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + i;
+                if (c >= climit) break;
+                int res[MAX_T];
+#pragma unroll
+                for (int t = 0; t < MAX_T; ++t) res[t] = (int)(int8_t)((w[t] >> (8 * i)) & 0xff);
+                const double v = scalbn(crt_value(res, tab), era + (eb_mode == 1 ? eb[c] : eb[0]) - bits2);
+                if (accumulate) atomicAdd(out + r * ldo + c, v);
+                else out[r * ldo + c] = v;
+            }
+        }
+    }
+}
+
+inline int crt_grid(long rows) {
+    const long blocks = cdiv(rows, 8);
+    return (int)(blocks < 148 * 8 ? (blocks < 1 ? 1 : blocks) : 148 * 8);
+}
+
+}  // namespace i8
+}  // namespace tgp

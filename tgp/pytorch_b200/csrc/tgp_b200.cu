@@ -8,6 +8,7 @@
 #include "backward_kernels.cuh"
 #include "tc_driver.cuh"
 #include "flow_mlp.cuh"
+#include "crt_driver.cuh"
 
 namespace tgp {
 char g_last_error[512] = "";
@@ -52,7 +53,7 @@ inline TgpReduceLayout reduce_layout(const TgpModel* md) {
     l.Cbar = l.Gbar + Mp * Mp;
     l.total = l.Cbar + Mp * Mp;
     const long M = md->M, tri = M * (M + 1) / 2;
-    l.packed_total = l.Gbar + tri + (md->dtype == TGP_F32 ? M * M : tri);
+    l.packed_total = l.Gbar + tri + (md->dtype != TGP_F64 ? M * M : tri);
     return l;
 }
 
@@ -76,13 +77,14 @@ __global__ void __launch_bounds__(256) k_reduce_pack(double* __restrict__ rb, do
 
 inline int reduce_pack(const TgpModel* md, double* rb, double* packed, int dir, cudaStream_t st) {
     const TgpReduceLayout l = reduce_layout(md);
-    k_reduce_pack<<<md->M + 1, 256, 0, st>>>(rb, packed, l.Gbar, l.Gbar, l.Cbar, md->M, pad_M(md->M), md->dtype == TGP_F32, dir);
+    k_reduce_pack<<<md->M + 1, 256, 0, st>>>(rb, packed, l.Gbar, l.Gbar, l.Cbar, md->M, pad_M(md->M), md->dtype != TGP_F64, dir);
     return check_launch("k_reduce_pack");
 }
 
 inline int validate(const TgpModel* md) {
     if (!md) return set_error(-1, "model is NULL");
-    if (md->dtype != TGP_F64 && md->dtype != TGP_F32) return set_error(-1, "dtype must be TGP_F64 or TGP_F32");
+    if (md->dtype != TGP_F64 && md->dtype != TGP_F32 && md->dtype != TGP_F64_I8)
+        return set_error(-1, "dtype must be TGP_F64, TGP_F32 or TGP_F64_I8");
     if (md->M < 1 || md->D < 1) return set_error(-1, "M and D must be positive");
     if (md->n_layers < 0 || md->n_layers > TGP_MAX_LAYERS) return set_error(-1, "too many flow layers");
     if (md->n_theta < 0 || md->n_theta > MAX_THETA) return set_error(-1, "too many global flow parameters");
@@ -131,6 +133,12 @@ inline int gemm_small(GemmArgs g, cudaStream_t st) {
     return gemm_f64(g, st);
 }
 
+// the integer-residue step region follows the FP64 matrices and the FP32 planes of the step workspace
+inline size_t crt_step_offset(const TgpModel* md) {
+    const size_t b = step_ws_doubles(md->M, md->D) * sizeof(double) + tc::step_plane_floats(md->M) * sizeof(float);
+    return (b + 255) / 256 * 256;
+}
+
 inline int row_grid(long R) {
     const long blocks = cdiv(R, ROW_THREADS / 32);
     return (int)(blocks < 148 * 16 ? blocks : 148 * 16);
@@ -146,12 +154,13 @@ int tgp_version(void) { return 100; }
 
 size_t tgp_step_workspace_bytes(const TgpModel* md) {
     if (validate(md)) return 0;
-    return step_ws_doubles(md->M, md->D) * sizeof(double) + tc::step_plane_floats(md->M) * sizeof(float);
+    return crt_step_offset(md) + (md->dtype == TGP_F64_I8 ? crt::step_bytes(md->M) : 0);
 }
 
 size_t tgp_batch_workspace_bytes(const TgpModel* md, long R) {
     if (validate(md) || R < 0) return 0;
     if (md->dtype == TGP_F32) return tc::batch_plane_floats(md->M, R) * sizeof(float);
+    if (md->dtype == TGP_F64_I8) return crt::batch_bytes(md->M, R);
     return batch_ws_doubles(md->M, R) * sizeof(double);
 }
 
@@ -168,9 +177,11 @@ int tgp_prepare(const TgpModel* md, const TgpParams* p, double jitter, void* ste
     if (!p || !step_ws || !kl_out || !status) return set_error(-1, "NULL argument to tgp_prepare");
     StepView v = carve_step(step_ws, md->M, md->D);
     TGP_TRY(run_prepare(v, (const double*)p->Z, (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale,
-                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, md->dtype == TGP_F32,
+                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, md->dtype != TGP_F64,
                         (cudaStream_t)stream));
     if (md->dtype == TGP_F32) TGP_TRY(tc::make_step_planes(v, step_ws, (cudaStream_t)stream));
+    if (md->dtype == TGP_F64_I8)
+        TGP_TRY(crt::make_step_planes(v, reinterpret_cast<char*>(step_ws) + crt_step_offset(md), (cudaStream_t)stream));
     return 0;
 }
 
@@ -184,6 +195,9 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
     StepView s = carve_step(const_cast<void*>(step_ws), M, D);
     if (md->dtype == TGP_F32)
         return tc::qf_forward(s, const_cast<void*>(step_ws), batch_ws, (const double*)X, R, (double*)mu, (double*)v, st);
+    if (md->dtype == TGP_F64_I8)
+        return crt::qf_forward(s, reinterpret_cast<char*>(const_cast<void*>(step_ws)) + crt_step_offset(md), batch_ws, (const double*)X,
+                               R, (double*)mu, (double*)v, st);
     BatchView b = carve_batch(batch_ws, M, R);
     const double* Xd = (const double*)X;
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
@@ -248,6 +262,10 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
     if (md->dtype == TGP_F32)
         return tc::qf_backward(s, const_cast<void*>(step_ws), batch_ws, Xd, R, (const double*)g_mu, (const double*)g_v,
                                reduce_buf + l.dm, reduce_buf + l.dos, reduce_buf + l.dZ, reduce_buf + l.dls, Gbar, Cbar, st);
+    if (md->dtype == TGP_F64_I8)
+        return crt::qf_backward(s, reinterpret_cast<char*>(const_cast<void*>(step_ws)) + crt_step_offset(md), batch_ws, Xd, R,
+                                (const double*)g_mu, (const double*)g_v, reduce_buf + l.dm, reduce_buf + l.dos, reduce_buf + l.dZ,
+                                reduce_buf + l.dls, Gbar, Cbar, st);
     // FP64 mode keeps the reference's two dependent triangular contractions (a = L^-1 k, b = L_S^T a):
     //   Bbar = 2 g_v B;  Abar = g_mu m - 2 g_v A + Bbar L_S^T;  Kbar = Abar L^-1;
     //   Gbar += tril(Abar^T K);  dL_S += tril(A^T Bbar)   (accumulated in the `Cbar` slot of the reduce buffer)
@@ -299,8 +317,8 @@ int tgp_chain_backward(const TgpModel* md, const TgpParams* p, void* step_ws, co
     double* Gtot = s.Kzz;                          // K_zz's buffer is free after the factorisation
     double* dZacc = s.S3;                          // (M*D) accumulators live at the head of S3 until Phi needs it
 
-    if (md->dtype == TGP_F32) {
-        // tensor-core mode carries C = L_S^T L^-1:  dLS = tril(Linv * Cbar^T),  Gtot = Gbar + tril(LS * Cbar)
+    if (md->dtype != TGP_F64) {
+        // tensor-core modes carry C = L_S^T L^-1:  dLS = tril(Linv * Cbar^T),  Gtot = Gbar + tril(LS * Cbar)
         GemmArgs a1 = make_gemm(M, M, M, s.Linv, Mp, 0, Cbar, Mp, 0, s.S0, Mp);
         a1.a_tri = 1; a1.c_lower = 1;
         cudaMemsetAsync(s.S0, 0, mm * sizeof(double), st);
@@ -613,6 +631,16 @@ int tgp_debug_gemm_tf32x3(int Mrows, int Ncols, int K, const float* Ahi, const f
     tc::Operand A{Ahi, Alo, Mrows, K, lda};
     tc::Operand B{Bhi, Blo, Ncols, K, ldb};
     return tc::gemm_tf32x3(A, B, p, (cudaStream_t)stream);
+}
+
+size_t tgp_debug_gemm_crt_bytes(long M, long N, long K, int T) { return crt::debug_bytes(M, N, K, T); }
+
+int tgp_debug_gemm_crt(long M, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc, int T,
+                       int tri_mode, int tri_rows, int lower_rows, int accumulate, void* scratch, void* stream) {
+    if (T < 1 || T > i8::MAX_T) return set_error(-1, "T must be in 1..16");
+    if (!A || !B || !C || !scratch) return set_error(-1, "NULL argument to tgp_debug_gemm_crt");
+    return crt::debug_matmul(M, N, K, A, lda, B, ldb, C, ldc, T, tri_mode, tri_rows, lower_rows, accumulate, scratch,
+                             (cudaStream_t)stream);
 }
 
 int tgp_debug_export_step(const TgpModel* md, const void* step_ws, double* L, double* Linv, double* C, void* stream) {

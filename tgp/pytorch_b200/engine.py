@@ -119,10 +119,10 @@ class Engine:
         self.likelihood = likelihood
         self.flow = flow_layout
         self.model = _lib.TgpModel()
-        if compute not in ('f64', 'tf32x3'):
-            raise ValueError("compute must be 'f64' or 'tf32x3'")
+        if compute not in ('f64', 'tf32x3', 'i8crt'):
+            raise ValueError("compute must be 'f64', 'tf32x3' or 'i8crt'")
         self.compute = compute
-        self.model.dtype = _lib.TGP_F64 if compute == 'f64' else _lib.TGP_F32
+        self.model.dtype = {'f64': _lib.TGP_F64, 'tf32x3': _lib.TGP_F32, 'i8crt': _lib.TGP_F64_I8}[compute]
         self.model.M, self.model.D = self.M, self.D
         self.model.likelihood = _LIK[likelihood]
         self.model.n_quad = int(n_quad)
@@ -324,3 +324,14 @@ def debug_gemm_tf32x3(A, B, out, out_mode=0, tri_mode=0, tri_rows=0, lower_rows=
                                          out.stride(0), out_mode, tri_mode, tri_rows, lower_rows, splitk, _stream()),
                'tgp_debug_gemm_tf32x3')
     return Ah, Al, Bh, Bl
+
+
+def debug_gemm_crt(A, B, out, T=16, tri_mode=0, tri_rows=0, lower_rows=0, accumulate=False):
+    """out (+)= A @ B.T through the integer-residue (CRT) pipeline of compute mode 'i8crt'; A (M, K), B (N, K), out (M, N) FP64."""
+    lib = _lib.load()
+    Mr, K = A.shape
+    N = B.shape[0]
+    scratch = torch.empty(lib.tgp_debug_gemm_crt_bytes(Mr, N, K, T), dtype=torch.uint8, device=A.device)
+    _lib.check(lib.tgp_debug_gemm_crt(Mr, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), T, tri_mode,
+                                      tri_rows, lower_rows, 1 if accumulate else 0, _ptr(scratch), _stream()), 'tgp_debug_gemm_crt')
+    return out
