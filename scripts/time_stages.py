@@ -5,11 +5,12 @@ import torch
 import bench
 from tests.gpu_util import engine_inputs, make_engine
 dev = 'cuda:0'
+WL = bench.WORKLOADS[os.environ.get('TGP_WORKLOAD', 'cfg4')]
 gen = torch.Generator().manual_seed(bench.SEED)
-X, Y = bench.synth(200000, bench.D, gen)
-p = bench.param_state(X, gen)
+X, Y = bench.synth(WL, 200000, gen)
+p = bench.param_state(WL, X, gen)
 xb, yb = X[:65536].to(dev), Y[:65536].view(-1).to(dev)
-scale = 5e6 / 65536
+scale = WL['N'] / 65536
 
 
 def timed(fn, n=10):
@@ -24,10 +25,10 @@ def timed(fn, n=10):
 from tgp.pytorch_b200 import _lib
 if os.environ.get('TGP_ROW_CHUNK'):
     _lib.load().tgp_set_option(_lib.OPT_ROW_CHUNK, int(os.environ['TGP_ROW_CHUNK']))
-for compute in sys.argv[1:] or ['f64', 'tf32x3', 'tf32x3+fused']:
+for compute in sys.argv[1:] or ['f64', 'i8crt', 'tf32x3']:
     _lib.load().tgp_set_option(_lib.OPT_FUSED_FORWARD, 1 if compute.endswith('+fused') else 0)
     label, compute = compute, compute.split('+')[0]
-    eng, theta, _, _ = make_engine(p, 'gauss_nonlinear', 100, dev, compute=compute)
+    eng, theta, _, _ = make_engine(p, WL['likelihood'], 100, dev, compute=compute)
     ei = engine_inputs(p, dev)
     eng.set_params(ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta)
     for _ in range(3):

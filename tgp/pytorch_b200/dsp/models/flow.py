@@ -98,6 +98,9 @@ class CompositeFlow(Flow):
 
 
 class IdentityFlow(Flow):
+    def __init__(self):
+        super().__init__()
+
     def forward(self, f0, X=None):
         return f0
 
