@@ -71,6 +71,20 @@ def test_crt_gemm_triangular_lower_and_accumulate():
     assert rel_err(out.cpu(), ref) < 5e-15
 
 
+@pytest.mark.parametrize('mn', [1, 2, 3])
+@pytest.mark.parametrize('M,N,K', [(128, 256, 128), (200, 300, 1000), (2048, 1024, 4096), (77, 513, 260)])
+def test_crt_gemm_mn_major_operands(M, N, K, mn):
+    """Operands handed over transposed (reduction over their ROWS): the tensor core reads the 128-byte-swizzled tile MN-major."""
+    from tgp.pytorch_b200.engine import debug_gemm_crt
+    A, B = _ab(M, N, K, M + N + K + mn, spread=2.0)
+    Ain = A.t().contiguous() if mn & 1 else A
+    Bin = B.t().contiguous() if mn & 2 else B
+    out = torch.zeros(M, N, dtype=torch.float64, device=DEV)
+    debug_gemm_crt(Ain.to(DEV), Bin.to(DEV), out, T=16, mn_major=mn)
+    # the transposed operand is scaled per column of what was passed = per row of the logical operand: same accuracy
+    assert rel_err(out.cpu(), A @ B.t()) < 5e-15
+
+
 REG = ['synth_reg_d8_m64_p1', 'boston_tgp_steptanh13_p1', 'boston_svgp_p1', 'power_tgp_sal2_p1', 'boston_tgp_sal2_p0',
        'synth_reg_d8_m1024_p1', 'power_idtgp_nodrop_p1', 'boston_tgp_steptanh102_p1']
 

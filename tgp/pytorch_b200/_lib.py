@@ -95,7 +95,7 @@ SIGNATURES = {
     'tgp_debug_gemm_f64': (_I, [_I, _I, _I, _P, _L, _I, _P, _L, _I, _P, _L, _D, _D, _I, _I, _I, _P]),
     'tgp_debug_gemm_tf32x3': (_I, [_I, _I, _I, _P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     'tgp_debug_gemm_crt_bytes': (C.c_size_t, [_L, _L, _L, _I]),
-    'tgp_debug_gemm_crt': (_I, [_L, _L, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P]),
+    'tgp_debug_gemm_crt': (_I, [_L, _L, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P, _P]),
     'tgp_debug_export_step': (_I, [C.POINTER(TgpModel), _P, _P, _P, _P, _P]),
 }
 

@@ -32,25 +32,27 @@ inline int bwd_bits(int M) { return i8::crt_bits(bwd_T(M), 2L * M); }
 // weight contraction  [Gbar; Cbar] += ABbar^T K, reduction = rows of the chunk: all 16 moduli, K^T carries 53 bits
 inline int wgt_bits(long rc) { return bits_other(T_ALL, rc, 53); }
 
-struct StepPlanes {               // per step: residues of W = [Linv; C] (2M x M) and of W^T (M x 2M)
+struct StepPlanes {               // per step: residues of W = [Linv; C] (2M x M), scaled per row and scaled per column
     double* Wst;                  // FP64 stacked operand (2M x M, ld M)
-    int8_t *W, *Wt;               // planes [T_ALL][2M][ldk], [T_ALL][M][ld2m]
+    int8_t *W;                    // planes [T][2M][ldk], per-row scale: forward operand (reduction over its columns, K-major)
+    int8_t *Wc;                   // planes [T][2M][ldk], per-column scale: backward-data operand Kbar = ABbar W (reduction over
+                                  // its ROWS: the tensor core reads it MN-major, no transposed copy)
     int *w_row_exp, *w_col_exp, *k_exp;
-    long ldk, ld2m;
+    long ldk;
 };
 
 inline size_t step_bytes(int M) {
-    const long ldk = pad16(M), ld2m = pad16(2L * M);
-    return (size_t)2 * M * M * sizeof(double) + (size_t)T_ALL * (2L * M * ldk + (long)M * ld2m) + (size_t)(3L * M + 64) * sizeof(int) + 1024;
+    const long ldk = pad16(M);
+    return (size_t)2 * M * M * sizeof(double) + (size_t)2 * T_ALL * 2L * M * ldk + (size_t)(3L * M + 64) * sizeof(int) + 1024;
 }
 
 inline StepPlanes carve_step(void* region, int M) {
     StepPlanes s;
-    s.ldk = pad16(M); s.ld2m = pad16(2L * M);
+    s.ldk = pad16(M);
     char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(region) + 255) & ~uintptr_t(255));
     s.Wst = reinterpret_cast<double*>(p); p += (size_t)2 * M * M * sizeof(double);
     s.W = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
-    s.Wt = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * (long)M * s.ld2m;
+    s.Wc = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
     p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
     s.w_row_exp = reinterpret_cast<int*>(p); p += (size_t)2 * M * sizeof(int);
     s.w_col_exp = reinterpret_cast<int*>(p); p += (size_t)M * sizeof(int);
@@ -62,38 +64,36 @@ struct BatchView {
     double *AB;                   // (R x 2M) FP64, forward -> backward ([A | B], turned into [Abar | Bbar] in place)
     double *Kbuf;                 // (R x M) FP64 K_xz (kernel gradients read it)
     double *Kbar;                 // (Rc x M)
-    int8_t *Kp;                   // planes [T_ALL][R][ldk]           K_xz residues (forward operand)
-    int8_t *KTp;                  // per chunk: planes [T_ALL][M][ldt]  transposed (weight contraction operand)
-    int8_t *Op;                   // planes [T][Rc][ld2m]             result residues of the forward / operand residues of ABbar
-    int8_t *PTp;                  // planes [T_ALL][2M][ldt]          ABbar^T residues
-    int8_t *Kbp;                  // planes [T][Rc][ldk]              Kbar result residues
-    int8_t *Gp;                   // planes [T_ALL][2M][ldk]          weight-contraction result residues
+    int8_t *Kp;                   // planes [T_ALL][R][ldk]   K_xz residues: forward operand AND weight-contraction operand
+    int8_t *Op;                   // planes [T][Rc][ld2m]     result residues of the forward; then ABbar scaled per row
+    int8_t *Pc;                   // planes [T_ALL][Rc][ld2m] ABbar scaled per column (weight-contraction operand, MN-major)
+    int8_t *Kbp;                  // planes [T][Rc][ldk]      Kbar result residues
+    int8_t *Gp;                   // planes [T_ALL][2M][ldk]  weight-contraction result residues
     int *row_exp, *col_exp;       // (Rc), (2M)
-    long Rc, ldk, ld2m, ldt, nch;
+    long Rc, ldk, ld2m;
 };
 
 inline size_t batch_bytes(int M, long R) {
-    const long Rc = chunk_rows(R), ldk = pad16(M), ld2m = pad16(2L * M), ldt = pad16(Rc), nch = (R + Rc - 1) / Rc;
+    const long Rc = chunk_rows(R), ldk = pad16(M), ld2m = pad16(2L * M);
     size_t b = 0;
     b += (size_t)R * 2 * M * 8 + (size_t)R * M * 8 + (size_t)Rc * M * 8;
-    b += (size_t)T_ALL * R * ldk + (size_t)nch * T_ALL * M * ldt;
-    b += (size_t)T_ALL * Rc * ld2m + (size_t)T_ALL * 2 * M * ldt + (size_t)T_ALL * Rc * ldk + (size_t)T_ALL * 2 * M * ldk;
+    b += (size_t)T_ALL * R * ldk;
+    b += (size_t)2 * T_ALL * Rc * ld2m + (size_t)T_ALL * Rc * ldk + (size_t)T_ALL * 2 * M * ldk;
     b += (size_t)(Rc + 2L * M + 64) * sizeof(int) + 4096;
     return b;
 }
 
 inline BatchView carve_batch(void* ws, int M, long R) {
     BatchView b;
-    b.Rc = chunk_rows(R); b.ldk = pad16(M); b.ld2m = pad16(2L * M); b.ldt = pad16(b.Rc); b.nch = (R + b.Rc - 1) / b.Rc;
+    b.Rc = chunk_rows(R); b.ldk = pad16(M); b.ld2m = pad16(2L * M);
     char* p = reinterpret_cast<char*>(ws);
     auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
     b.AB = reinterpret_cast<double*>(take((size_t)R * 2 * M * 8));
     b.Kbuf = reinterpret_cast<double*>(take((size_t)R * M * 8));
     b.Kbar = reinterpret_cast<double*>(take((size_t)b.Rc * M * 8));
     b.Kp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * R * b.ldk));
-    b.KTp = reinterpret_cast<int8_t*>(take((size_t)b.nch * T_ALL * M * b.ldt));
     b.Op = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
-    b.PTp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * 2 * M * b.ldt));
+    b.Pc = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
     b.Kbp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ldk));
     b.Gp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * 2 * M * b.ldk));
     b.row_exp = reinterpret_cast<int*>(take((size_t)b.Rc * sizeof(int)));
@@ -123,21 +123,41 @@ inline int exponents(const double* src, long ld, long rows, int cols, int* row_e
 }
 
 inline int to_residues(const double* src, long ld, long rows, int cols, int scale_mode, const int* exps, int bits, int T,
-                       int8_t* planes, long ldp, long plane_stride, int8_t* planesT, long ldt, long plane_strideT, cudaStream_t st) {
+                       int8_t* planes, long ldp, long plane_stride, cudaStream_t st, int scale_mode2 = 0, const int* exps2 = nullptr,
+                       int bits2 = 0, int T2 = 0, int8_t* planes2 = nullptr, long ldp2 = 0, long plane_stride2 = 0) {
     dim3 grid((unsigned)cdiv(cols, i8::RS_TC), (unsigned)cdiv(rows, i8::RS_TR));
-    i8::k_to_residues<<<grid, 256, 0, st>>>(src, ld, rows, cols, scale_mode, exps, bits, i8::crt_table(T), planes, ldp, plane_stride,
-                                           planesT, ldt, plane_strideT);
+    // the second set may use more moduli than the first: pass the longer table, the first set's count travels in tab.T
+    i8::CrtTable tab = i8::crt_table(T > T2 ? T : T2);
+    tab.T = T;
+    i8::k_to_residues<<<grid, 256, 0, st>>>(src, ld, rows, cols, scale_mode, exps, bits, tab, planes, ldp, plane_stride, scale_mode2,
+                                           exps2, bits2, T2, planes2, ldp2, plane_stride2);
     return check_launch("k_to_residues");
 }
 
 inline int combine(const int8_t* R, long ldr, long plane_stride, long rows, int cols, int T, int bits2, const int* ea, int ea_mode,
-                   const int* eb, int eb_mode, double* out, long ldo, int accumulate, int lower_rows, cudaStream_t st) {
+                   const int* eb, int eb_mode, double* out, long ldo, int accumulate, int lower_rows, cudaStream_t st,
+                   i8::RowStats stats = i8::RowStats{nullptr, nullptr, nullptr, nullptr, 0}) {
     i8::k_crt_combine<<<i8::crt_grid(rows), 256, 0, st>>>(R, ldr, plane_stride, rows, cols, i8::crt_table(T), bits2, ea, ea_mode, eb,
-                                                         eb_mode, out, ldo, accumulate, lower_rows);
+                                                         eb_mode, out, ldo, accumulate, lower_rows, stats);
     return check_launch("k_crt_combine");
 }
 
-// per step, after run_prepare: residues of W (per-row scale, forward) and of W^T (per-column scale of W, backward-data)
+// K_xz of a row chunk in one pass: FP64 values and residue planes (i8::k_rbf_residues)
+inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
+                        const int* kexp, int T, int8_t* planes, long ldp, long plane_stride, cudaStream_t st) {
+    dim3 grid((unsigned)cdiv(M, i8::RS_TC), (unsigned)cdiv(R, i8::RS_TR));
+    const i8::CrtTable& tab = i8::crt_table(T);
+#define TGP_RR(MD) i8::k_rbf_residues<MD><<<grid, 256, 0, st>>>(X, Zs, ls, os, R, M, D, Kout, M, kexp, 53, tab, planes, ldp, plane_stride)
+    if (D <= 4) TGP_RR(4);
+    else if (D <= 8) TGP_RR(8);
+    else if (D <= 16) TGP_RR(16);
+    else if (D <= 32) TGP_RR(32);
+    else return -7;              // wider inputs: the caller falls back to launch_rbf + to_residues
+#undef TGP_RR
+    return check_launch("k_rbf_residues");
+}
+
+// per step, after run_prepare: residues of W scaled per row (forward) and scaled per column (backward-data)
 inline int make_step_planes(const StepView& v, void* region, cudaStream_t st) {
     const int M = v.M;
     StepPlanes s = carve_step(region, M);
@@ -146,32 +166,47 @@ inline int make_step_planes(const StepView& v, void* region, cudaStream_t st) {
     k_exp_of_scalar<<<1, 1, 0, st>>>(v.os, s.k_exp);
     TGP_TRY(check_launch("k_exp_of_scalar"));
     TGP_TRY(exponents(s.Wst, M, 2L * M, M, s.w_row_exp, s.w_col_exp, st));
-    TGP_TRY(to_residues(s.Wst, M, 2L * M, M, 0, s.w_row_exp, fwd_bits_w(M), fwd_T(M), s.W, s.ldk, 2L * M * s.ldk, nullptr, 0, 0, st));
-    TGP_TRY(to_residues(s.Wst, M, 2L * M, M, 1, s.w_col_exp, bwd_bits(M), bwd_T(M), nullptr, 0, 0, s.Wt, s.ld2m, (long)M * s.ld2m, st));
-    return 0;
+    return to_residues(s.Wst, M, 2L * M, M, 0, s.w_row_exp, fwd_bits_w(M), fwd_T(M), s.W, s.ldk, 2L * M * s.ldk, st,
+                       1, s.w_col_exp, bwd_bits(M), bwd_T(M), s.Wc, s.ldk, 2L * M * s.ldk);
 }
 
 // [A | B] + upstream row gradients -> [Abar | Bbar] IN PLACE (Abar = g_mu m - 2 g_v A, Bbar = 2 g_v B); accumulates
 // dm[j] += sum_n g_mu A[n,j] and dos += sum_n g_v.  64 rows x 128 columns per CTA.
+// row_exp / col_exp (pre-set to a very small value): binary exponents above the row / column maxima of [Abar | Bbar], the
+// scales of its two integerisations.
 __global__ void __launch_bounds__(128) k_make_abbar_inplace(double* __restrict__ AB, const double* __restrict__ g_mu,
                                                             const double* __restrict__ g_v, const double* __restrict__ m, long R,
-                                                            int M, double* __restrict__ dm, double* __restrict__ dos) {
+                                                            int M, double* __restrict__ dm, double* __restrict__ dos,
+                                                            int* __restrict__ row_exp, int* __restrict__ col_exp) {
     const int j = blockIdx.x * 128 + threadIdx.x;
     const long n0 = (long)blockIdx.y * 64, n1 = min(n0 + 64, R);
     const double mj = j < M ? m[j] : 0.0;
     double acc = 0.0, accv = 0.0;
+    int ca = -100000, cb = -100000;
     for (long n = n0; n < n1; ++n) {
         const double gm = g_mu[n], gv = g_v[n];
         accv += gv;
+        int re = -100000;
         if (j < M) {
             double* row = AB + n * 2 * M;
             const double a = row[j], b = row[M + j];
             acc = fma(gm, a, acc);
-            row[j] = gm * mj - 2.0 * gv * a;
-            row[M + j] = 2.0 * gv * b;
+            const double abar = gm * mj - 2.0 * gv * a, bbar = 2.0 * gv * b;
+            row[j] = abar;
+            row[M + j] = bbar;
+            const int ea = i8::exp_above(abar), eb = i8::exp_above(bbar);
+            ca = max(ca, ea); cb = max(cb, eb);
+            re = max(ea, eb);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) re = max(re, __shfl_xor_sync(0xffffffffu, re, o));
+        if ((threadIdx.x & 31) == 0 && re > -100000) atomicMax(row_exp + n, re);
     }
-    if (j < M) atomicAdd(dm + j, acc);
+    if (j < M) {
+        atomicAdd(dm + j, acc);
+        atomicMax(col_exp + j, ca);
+        atomicMax(col_exp + M + j, cb);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(dos, accv);
 }
 
@@ -184,21 +219,22 @@ inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, cons
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         double* Kc = b.Kbuf + r0 * M;
-        TGP_TRY(launch_rbf(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
         // K residues: one scale for the whole matrix (0 <= k <= outputscale), shared by the forward and the weight contraction
-        int8_t* KTc = b.KTp + (r0 / b.Rc) * (long)T_ALL * M * b.ldt;
-        TGP_TRY(to_residues(Kc, M, rc, M, 2, sp.k_exp, 53, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, KTc, b.ldt, (long)M * b.ldt, st));
+        const int rr = rbf_residues(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, Kc, sp.k_exp, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, st);
+        if (rr == -7) {
+            TGP_TRY(launch_rbf(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
+            TGP_TRY(to_residues(Kc, M, rc, M, 2, sp.k_exp, 53, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, st));
+        } else if (rr != 0) return rr;
         i8::Params p{};
-        p.Mrows = rc; p.Ncols = 2 * M; p.K = M; p.T = Tf; p.tri_mode = 1; p.tri_rows = M; p.lower_rows = 0;
+        p.Mrows = rc; p.Ncols = 2 * M; p.K = M; p.T = Tf; p.tri_mode = 1; p.tri_rows = M; p.lower_rows = 0; p.mn_major = 0;
         p.C = b.Op; p.ldc = b.ld2m; p.plane_stride_c = (long)b.Rc * b.ld2m;
         Planes A{b.Kp + r0 * b.ldk, rc, M, b.ldk, R * b.ldk};
         Planes B{sp.W, 2L * M, M, sp.ldk, 2L * M * sp.ldk};
         TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
         TGP_TRY(combine(b.Op, b.ld2m, (long)b.Rc * b.ld2m, rc, 2 * M, Tf, 53 + bits, sp.k_exp, 2, sp.w_row_exp, 1, b.AB + r0 * 2 * M,
-                        2L * M, 0, 0, st));
+                        2L * M, 0, 0, st, i8::RowStats{s.mvec, s.os, mu + r0, v + r0, M}));
     }
-    k_row_stats<<<(unsigned)min((long)148 * 16, cdiv(R, ROW_THREADS / 32)), ROW_THREADS, 0, st>>>(b.AB, s.mvec, s.os, (int)R, M, mu, v);
-    return check_launch("k_row_stats");
+    return 0;
 }
 
 inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, const double* X, long R, const double* g_mu,
@@ -212,34 +248,35 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         double* ABc = b.AB + r0 * 2 * M;
         {
+            TGP_TRY(fill_int(b.row_exp, rc, -100000, st));
+            TGP_TRY(fill_int(b.col_exp, 2L * M, -100000, st));
             dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rc, 64));
-            k_make_abbar_inplace<<<grid, 128, 0, st>>>(ABc, g_mu + r0, g_v + r0, s.mvec, rc, M, dm, dos);
+            k_make_abbar_inplace<<<grid, 128, 0, st>>>(ABc, g_mu + r0, g_v + r0, s.mvec, rc, M, dm, dos, b.row_exp, b.col_exp);
             TGP_TRY(check_launch("k_make_abbar_inplace"));
         }
-        TGP_TRY(exponents(ABc, 2L * M, rc, 2 * M, b.row_exp, b.col_exp, st));
-        // row-scaled residues (operand of Kbar = ABbar W) and column-scaled transposed residues (operand of ABbar^T K)
-        TGP_TRY(to_residues(ABc, 2L * M, rc, 2 * M, 0, b.row_exp, bits_b, Tb, b.Op, b.ld2m, (long)b.Rc * b.ld2m, nullptr, 0, 0, st));
+        // one pass over [Abar | Bbar]: residues scaled per row (operand of Kbar = ABbar W) and per column (operand of ABbar^T K)
         const int Tw = T_ALL, bits_w = wgt_bits(rc);
-        TGP_TRY(to_residues(ABc, 2L * M, rc, 2 * M, 1, b.col_exp, bits_w, Tw, nullptr, 0, 0, b.PTp, b.ldt, 2L * M * b.ldt, st));
-        {   // Kbar (rc x M) = ABbar (rc x 2M) * Wt (M x 2M)^T ; for k < M only k >= n contributes
+        TGP_TRY(to_residues(ABc, 2L * M, rc, 2 * M, 0, b.row_exp, bits_b, Tb, b.Op, b.ld2m, (long)b.Rc * b.ld2m, st,
+                            1, b.col_exp, bits_w, Tw, b.Pc, b.ld2m, (long)b.Rc * b.ld2m));
+        {   // Kbar (rc x M) = ABbar (rc x 2M) * W (2M x M); for k < M only k >= n contributes.  A is K-major; the reduction runs
+            // over the ROWS of W, whose per-column-scaled row-major planes the tensor core reads MN-major (mn_major bit 1)
             i8::Params p{};
-            p.Mrows = rc; p.Ncols = M; p.K = 2 * M; p.T = Tb; p.tri_mode = 2; p.tri_rows = M; p.lower_rows = 0;
+            p.Mrows = rc; p.Ncols = M; p.K = 2 * M; p.T = Tb; p.tri_mode = 2; p.tri_rows = M; p.lower_rows = 0; p.mn_major = 2;
             p.C = b.Kbp; p.ldc = b.ldk; p.plane_stride_c = (long)b.Rc * b.ldk;
             Planes A{b.Op, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
-            Planes B{sp.Wt, M, 2L * M, sp.ld2m, (long)M * sp.ld2m};
+            Planes B{sp.Wc, 2L * M, M, sp.ldk, 2L * M * sp.ldk};
             TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
             TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, 0, sp.w_col_exp, 1, b.Kbar, M, 0, 0, st));
         }
         TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
-        {   // [Gbar; Cbar] (2M x M) += ABbar^T K : operands ABbar^T (2M x rc) and K^T (M x rc), reduction over the chunk rows
-            const int8_t* KTc = b.KTp + (r0 / b.Rc) * (long)T_ALL * M * b.ldt;
+        {   // [Gbar; Cbar] (2M x M) += ABbar^T K: reduction over the chunk rows; both operands are row-major planes read MN-major
             i8::Params p{};
-            p.Mrows = 2 * M; p.Ncols = M; p.K = rc; p.T = Tw; p.tri_mode = 0; p.tri_rows = 0; p.lower_rows = M;
+            p.Mrows = 2 * M; p.Ncols = M; p.K = rc; p.T = Tw; p.tri_mode = 0; p.tri_rows = 0; p.lower_rows = M; p.mn_major = 3;
             p.C = b.Gp; p.ldc = b.ldk; p.plane_stride_c = 2L * M * b.ldk;
-            Planes A{b.PTp, 2L * M, rc, b.ldt, 2L * M * b.ldt};
-            Planes B{KTc, M, rc, b.ldt, (long)M * b.ldt};
+            Planes A{b.Pc, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
+            Planes B{b.Kp + r0 * b.ldk, rc, M, b.ldk, R * b.ldk};
             TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
-            // K^T residues were integerised with 53 bits (forward), ABbar^T with bits_w
+            // K residues carry 53 bits, ABbar (per column) bits_w
             TGP_TRY(combine(b.Gp, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_w + 53, b.col_exp, 0, sp.k_exp, 2, Gbar, s.Mp, 1, M, st));
             TGP_TRY(combine(b.Gp + (long)M * b.ldk, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_w + 53, b.col_exp + M, 0, sp.k_exp, 2, Cbar,
                             s.Mp, 1, 0, st));
@@ -249,30 +286,46 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
 }
 
 // ---- test hook: C = A B^T through the residue pipeline ------------------------------------------------------------------
+// mn_major bit 0 / 1: A / B is passed TRANSPOSED ((K x Mr) / (K x N), row-major) and contracted over its rows
 inline size_t debug_bytes(long Mr, long N, long K, int T) {
-    const long ldk = pad16(K), ldn = pad16(N);
-    return (size_t)T * (Mr * ldk + N * ldk + Mr * ldn) + (size_t)(Mr + N + 64) * sizeof(int) + 4096;
+    const long ldk = pad16(K), ldn = pad16(N), ldm = pad16(Mr);
+    return (size_t)T * ((Mr > K ? Mr : K) * (ldk > ldm ? ldk : ldm) + (N > K ? N : K) * (ldk > ldn ? ldk : ldn) + Mr * ldn) +
+           (size_t)(Mr + N + 64) * sizeof(int) + 8192;
 }
 
 inline int debug_matmul(long Mr, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc, int T,
-                        int tri_mode, int tri_rows, int lower_rows, int accumulate, void* scratch, cudaStream_t st) {
-    const long ldk = pad16(K), ldn = pad16(N);
+                        int tri_mode, int tri_rows, int lower_rows, int accumulate, int mn_major, void* scratch, cudaStream_t st) {
+    const long ldk = pad16(K), ldn = pad16(N), ldm = pad16(Mr);
+    const bool at = mn_major & 1, bt = mn_major & 2;
     char* p = reinterpret_cast<char*>(scratch);
     auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
-    int8_t* Ap = reinterpret_cast<int8_t*>(take((size_t)T * Mr * ldk));
-    int8_t* Bp = reinterpret_cast<int8_t*>(take((size_t)T * N * ldk));
+    int8_t* Ap = reinterpret_cast<int8_t*>(take((size_t)T * (at ? K * ldm : Mr * ldk)));
+    int8_t* Bp = reinterpret_cast<int8_t*>(take((size_t)T * (bt ? K * ldn : N * ldk)));
     int8_t* Cp = reinterpret_cast<int8_t*>(take((size_t)T * Mr * ldn));
     int* ea = reinterpret_cast<int*>(take((size_t)Mr * sizeof(int)));
     int* eb = reinterpret_cast<int*>(take((size_t)N * sizeof(int)));
     const int bits = i8::crt_bits(T, K);
-    TGP_TRY(exponents(A, lda, Mr, (int)K, ea, nullptr, st));
-    TGP_TRY(exponents(B, ldb, N, (int)K, eb, nullptr, st));
-    TGP_TRY(to_residues(A, lda, Mr, (int)K, 0, ea, bits, T, Ap, ldk, Mr * ldk, nullptr, 0, 0, st));
-    TGP_TRY(to_residues(B, ldb, N, (int)K, 0, eb, bits, T, Bp, ldk, N * ldk, nullptr, 0, 0, st));
+    if (at) {
+        TGP_TRY(exponents(A, lda, K, (int)Mr, nullptr, ea, st));
+        TGP_TRY(to_residues(A, lda, K, (int)Mr, 1, ea, bits, T, Ap, ldm, K * ldm, st));
+    } else {
+        TGP_TRY(exponents(A, lda, Mr, (int)K, ea, nullptr, st));
+        TGP_TRY(to_residues(A, lda, Mr, (int)K, 0, ea, bits, T, Ap, ldk, Mr * ldk, st));
+    }
+    if (bt) {
+        TGP_TRY(exponents(B, ldb, K, (int)N, nullptr, eb, st));
+        TGP_TRY(to_residues(B, ldb, K, (int)N, 1, eb, bits, T, Bp, ldn, K * ldn, st));
+    } else {
+        TGP_TRY(exponents(B, ldb, N, (int)K, eb, nullptr, st));
+        TGP_TRY(to_residues(B, ldb, N, (int)K, 0, eb, bits, T, Bp, ldk, N * ldk, st));
+    }
     i8::Params q{};
     q.Mrows = (int)Mr; q.Ncols = (int)N; q.K = (int)K; q.T = T; q.tri_mode = tri_mode; q.tri_rows = tri_rows; q.lower_rows = lower_rows;
+    q.mn_major = mn_major;
     q.C = Cp; q.ldc = ldn; q.plane_stride_c = Mr * ldn;
-    TGP_TRY(i8::gemm_i8_mod(Planes{Ap, Mr, K, ldk, Mr * ldk}, Planes{Bp, N, K, ldk, N * ldk}, q, st));
+    const Planes PA = at ? Planes{Ap, K, Mr, ldm, K * ldm} : Planes{Ap, Mr, K, ldk, Mr * ldk};
+    const Planes PB = bt ? Planes{Bp, K, N, ldn, K * ldn} : Planes{Bp, N, K, ldk, N * ldk};
+    TGP_TRY(i8::gemm_i8_mod(PA, PB, q, st));
     return combine(Cp, ldn, Mr * ldn, Mr, (int)N, T, 2 * bits, ea, 0, eb, 1, C, ldc, accumulate, lower_rows, st);
 }
 

@@ -47,6 +47,10 @@ struct CrtTable {                 // passed by value to the kernels (< 1 KiB)
     double frac[MAX_T];           // w_t / P
     double Pw[N_WORDS];           // words of P
     double log2P;
+    // residues of a 56-bit magnitude by byte limbs: u = sum_k a_k 256^k  =>  u mod p = (sum_k a_k (256^k mod p)) mod p;
+    // clo / chi pack (256^k mod p) for k = 0..3 / 4..7 (dp4a operands), magic = ceil(2^32 / p) (exact floor division of
+    // the < 2^19 limb sum by a multiply-high)
+    uint32_t clo[MAX_T], chi[MAX_T], magic[MAX_T];
 };
 
 inline const CrtTable& crt_table(int T) {
@@ -72,6 +76,13 @@ inline const CrtTable& crt_table(int T) {
             const u128 w = q * (u128)inv;
             for (int k = 0; k < N_WORDS; ++k) c.w[t][k] = (double)(unsigned long long)((w >> (WORD_BITS * k)) & mask);
             c.frac[t] = (double)(to_ld(w) / to_ld(P));
+            uint32_t pw = 1 % (uint32_t)p, lo = 0, hi = 0;
+            for (int k = 0; k < 8; ++k) {
+                if (k < 4) lo |= pw << (8 * k); else hi |= pw << (8 * (k - 4));
+                pw = (pw * 256u) % (uint32_t)p;
+            }
+            c.clo[t] = lo; c.chi[t] = hi;
+            c.magic[t] = (uint32_t)((4294967296ull + (unsigned long long)p - 1ull) / (unsigned long long)p);
         }
         for (int k = 0; k < N_WORDS; ++k) c.Pw[k] = (double)(unsigned long long)((P >> (WORD_BITS * k)) & mask);
         c.log2P = (double)log2l(to_ld(P));
@@ -135,78 +146,127 @@ __global__ void k_fill_int(int* __restrict__ p, long n, int v) {
     if (i < n) p[i] = v;
 }
 
-// centred residue of the integer-valued double x (|x| < 2^53) modulo p, as int in [-128, 127]
-__device__ __forceinline__ int residue_of(double x, int p, double invp) {
-    const double q = rint(x * invp);
-    double r = fma(-q, (double)p, x);                 // exact: |r| < 1.5 p
-    const double h = 0.5 * (double)p;
-    if (r >= h) r -= (double)p;
-    if (r < -h) r += (double)p;
-    return (int)r;                                    // [-p/2, p/2): fits int8 for p <= 256
+// centred residue in [-128, 127] of the integer sign * (hi * 2^32 + lo) (magnitude < 2^56) modulo tab.p[t]: two dp4a over
+// the byte limbs, an exact multiply-high division of the < 2^19 limb sum, sign and centring
+__device__ __forceinline__ int residue_of(uint32_t lo, uint32_t hi, bool neg, const CrtTable& tab, int t) {
+    const uint32_t s = __dp4a(lo, tab.clo[t], __dp4a(hi, tab.chi[t], 0u));
+    const int p = tab.p[t];
+    int r = (int)(s - __umulhi(s, tab.magic[t]) * (uint32_t)p);           // [0, p)
+    r = neg ? -r : r;
+    const int h = p >> 1;
+    r = r >= h ? r - p : r;                                               // p = 256: [-128, 127]; odd p: [-(p-1)/2 - 1, (p-1)/2]
+    r = r < -h ? r + p : r;
+    return r;
 }
 
-// src (rows x cols, ld) -> planes[t][r][c] (ldp bytes per row, plane_stride bytes per plane) and / or transposed planes
-// planesT[t][c][r] (ldt, plane_strideT).  Scaling: x * 2^(bits - e) with e = row_exp[r] (scale_mode 0), col_exp[c] (1) or
-// the single exponent exp0[0] (2).  32 x 128 tile per CTA, staged through shared memory for the transposed write.
+// residues of 16 scaled integers (thread-private, consecutive columns of one row) for every modulus -> planes[t][r][c..c+15]
+// (one 16-byte store per modulus).  Tile: RS_TR rows x RS_TC columns per CTA of 256 threads; thread (tr = tid / 8,
+// tcb = 16 * (tid % 8)).
 constexpr int RS_TR = 32, RS_TC = 128;
-__global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ src, long ld, long rows, int cols, int scale_mode,
-                                                     const int* __restrict__ exps, int bits, CrtTable tab,
-                                                     int8_t* __restrict__ planes, long ldp, long plane_stride,
-                                                     int8_t* __restrict__ planesT, long ldt, long plane_strideT) {
-    __shared__ int8_t tile[RS_TR][RS_TC + 4];
-    const long r0 = (long)blockIdx.y * RS_TR;
-    const int c0 = blockIdx.x * RS_TC;
-    const int tid = threadIdx.x;
-    // each thread owns 16 elements of the tile: row tr = tid / 8, columns tc0 + 8 * i + ...; keep them as scaled doubles
-    const int tr = tid >> 3, tcb = (tid & 7) * 16;
-    double x[16];
-    const long r = r0 + tr;
+__device__ __forceinline__ void emit_residues(const long long (&xi)[16], const CrtTable& tab, long r, long rows, int c, int cols,
+                                              int8_t* __restrict__ planes, long ldp, long plane_stride) {
+    uint32_t lo[16], hi[16];
+    uint32_t negmask = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int c = c0 + tcb + i;
-        double v = 0.0;
-        if (r < rows && c < cols) {
-            const int e = scale_mode == 0 ? exps[r] : (scale_mode == 1 ? exps[c] : exps[0]);
-            v = rint(scalbn(src[r * ld + c], bits - e));
-        }
-        x[i] = v;
+        const long long v = xi[i];
+        const unsigned long long u = (unsigned long long)(v < 0 ? -v : v);
+        lo[i] = (uint32_t)u; hi[i] = (uint32_t)(u >> 32);
+        negmask |= (v < 0 ? 1u : 0u) << i;
     }
+    if (!(r < rows && c < cols)) return;
+    int8_t* dst0 = planes + r * ldp + c;
+    const bool vec = c + 16 <= ldp;                  // zero residues pad the row up to ldp
+#pragma unroll 2
     for (int t = 0; t < tab.T; ++t) {
-        const int p = tab.p[t];
-        const double invp = 1.0 / (double)p;
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t word = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) word |= ((uint32_t)(residue_of(x[4 * j + i], p, invp) & 0xff)) << (8 * i);
+            for (int i = 0; i < 4; ++i)
+                word |= ((uint32_t)(residue_of(lo[4 * j + i], hi[4 * j + i], (negmask >> (4 * j + i)) & 1u, tab, t) & 0xff)) << (8 * i);
             w[j] = word;
         }
-        if (planes && r < rows && c0 + tcb < cols) {
-            int8_t* dst = planes + (long)t * plane_stride + r * ldp + c0 + tcb;       // zero residues pad the row up to ldp
-            if (c0 + tcb + 16 <= ldp) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-            else for (int i = 0; i < 16 && c0 + tcb + i < ldp; ++i) dst[i] = (int8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xff);
-        }
-        if (planesT) {
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t*>(&tile[tr][tcb + 4 * j]) = w[j];
-            __syncthreads();
-            // transposed write: thread -> column tcT = tid / 2, 16 consecutive rows
-            const int cT = tid >> 1, rb = (tid & 1) * 16;
-            const int c = c0 + cT;
-            if (c < cols && r0 + rb < ldt) {
-                uint32_t o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    o[j] = ((uint32_t)(uint8_t)tile[rb + 4 * j][cT]) | ((uint32_t)(uint8_t)tile[rb + 4 * j + 1][cT] << 8) |
-                           ((uint32_t)(uint8_t)tile[rb + 4 * j + 2][cT] << 16) | ((uint32_t)(uint8_t)tile[rb + 4 * j + 3][cT] << 24);
-                int8_t* dst = planesT + (long)t * plane_strideT + (long)c * ldt + r0 + rb;
-                if (r0 + rb + 16 <= ldt) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-                else for (int i = 0; i < 16 && r0 + rb + i < ldt; ++i) dst[i] = (int8_t)((o[i >> 2] >> (8 * (i & 3))) & 0xff);
-            }
-        }
+        int8_t* dst = dst0 + (long)t * plane_stride;
+        if (vec) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        else for (int i = 0; i < 16 && c + i < ldp; ++i) dst[i] = (int8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xff);
     }
+}
+
+// src (rows x cols, ld) -> planes[t][r][c] (ldp bytes per row, plane_stride bytes per plane), scaled by 2^(bits - e) with
+// e = exps[r] (scale_mode 0: per row), exps[c] (1: per column) or exps[0] (2).  A second integerisation of the same
+// elements (planes2 != NULL: its own scale mode / exponents / bits / moduli) is produced in the same pass — [Abar | Bbar]
+// feeds one contraction scaled per row and one scaled per column, and is read once.
+__global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ src, long ld, long rows, int cols,
+                                                     int scale_mode, const int* __restrict__ exps, int bits, CrtTable tab,
+                                                     int8_t* __restrict__ planes, long ldp, long plane_stride,
+                                                     int scale_mode2, const int* __restrict__ exps2, int bits2, int T2,
+                                                     int8_t* __restrict__ planes2, long ldp2, long plane_stride2) {
+    const long r = (long)blockIdx.y * RS_TR + (threadIdx.x >> 3);
+    const int c = blockIdx.x * RS_TC + (threadIdx.x & 7) * 16;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (r < rows && c + i < cols) ? src[r * ld + c + i] : 0.0;
+    long long xi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = scale_mode == 0 ? (r < rows ? exps[r] : 0) : (scale_mode == 1 ? (c + i < cols ? exps[c + i] : 0) : exps[0]);
+        xi[i] = __double2ll_rn(scalbn(x[i], bits - e));
+    }
+    emit_residues(xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
+    if (planes2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = scale_mode2 == 0 ? (r < rows ? exps2[r] : 0) : (scale_mode2 == 1 ? (c + i < cols ? exps2[c + i] : 0) : exps2[0]);
+            xi[i] = __double2ll_rn(scalbn(x[i], bits2 - e));
+        }
+        CrtTable tab2 = tab;
+        tab2.T = T2;                                  // the moduli of a shorter table are a prefix of the longer one
+        emit_residues(xi, tab2, r, rows, c, cols, planes2, ldp2, plane_stride2);
+    }
+}
+
+// ARD-RBF K tile generated in registers (same arithmetic as k_rbf_tile_reg: x / ls differences, FMA chain, FP64 exp) and
+// converted on the spot: FP64 K (kept for the kernel gradients) and its residue planes in ONE pass.  The same planes serve
+// the forward (reduction over the inducing index: K-major) and the weight contraction (reduction over the rows: MN-major).
+// One scale for the whole matrix: 0 <= k <= outputscale < 2^kexp.
+template <int MAXD>
+__global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__ X, const double* __restrict__ Zs,
+                                                      const double* __restrict__ ls, const double* __restrict__ os, long R, int M, int D,
+                                                      double* __restrict__ Kout, long ldk_out, const int* __restrict__ kexp, int bits,
+                                                      CrtTable tab, int8_t* __restrict__ planes, long ldp, long plane_stride) {
+    __shared__ __align__(16) double zs[RS_TC][MAXD];
+    const long r0 = (long)blockIdx.y * RS_TR;
+    const int c0 = blockIdx.x * RS_TC;
+    const int tid = threadIdx.x;
+    const int tr = tid >> 3, tcb = (tid & 7) * 16;
+    for (int i = tid; i < RS_TC * MAXD; i += 256) {
+        const int c = i / MAXD, d = i % MAXD, j = c0 + c;
+        zs[c][d] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
+    }
+    const long r = r0 + tr;
+    double xr[MAXD];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) xr[d] = (r < R && d < D) ? X[r * D + d] / ls[d] : 0.0;
+    __syncthreads();
+    const double s = os[0];
+    const int sh = bits - kexp[0];
+    long long xi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = c0 + tcb + i;
+        double val = 0.0;
+        if (r < R && c < M) {
+            double acc = 0.0;
+#pragma unroll
+            for (int d = 0; d < MAXD; ++d) { const double df = xr[d] - zs[tcb + i][d]; acc = fma(df, df, acc); }
+            val = s * exp(-0.5 * acc);
+            if (Kout) Kout[r * ldk_out + c] = val;
+        }
+        xi[i] = __double2ll_rn(scalbn(val, sh));
+    }
+    emit_residues(xi, tab, r, R, c0 + tcb, M, planes, ldp, plane_stride);
 }
 
 // ---- step 3: the int8 GEMMs ------------------------------------------------------------------------------------------
@@ -214,8 +274,11 @@ struct Params {
     int Mrows, Ncols, K, T;
     int tri_mode, tri_rows;          // as gemm_tc.cuh: 1: B rows n < tri_rows are lower triangular (k <= n);  2: k < tri_rows needs k >= n
     int lower_rows;                  // > 0: for output rows m < lower_rows tiles strictly above the diagonal are skipped
+    int mn_major;                    // bit 0: A planes, bit 1: B planes are stored [t][k][m] (MN-major) instead of [t][m][k] (K-major):
+                                     // the tensor core reads the transposed tile straight from shared memory, so a contraction
+                                     // over the ROWS of row-major planes needs no transposed copy
     int8_t* C; long ldc, plane_stride_c;       // residue planes of the result [t][m][n]
-    int p[MAX_T]; float invp[MAX_T];
+    int p[MAX_T]; uint32_t magic[MAX_T];
 };
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -226,9 +289,16 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-// kind::i8: signed 8-bit A and B, S32 accumulate, both K-major, M = 128, N = BN
-__device__ __forceinline__ uint32_t make_idesc_i8() {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::i8: signed 8-bit A and B, S32 accumulate, M = 128, N = BN; bits 15 / 16: A / B operand is MN-major
+__device__ __forceinline__ uint32_t make_idesc_i8(int mn_major) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+           ((mn_major & 1) ? (1u << 15) : 0u) | ((mn_major & 2) ? (1u << 16) : 0u);
+}
+// MN-major, 128-byte swizzle: a tile is BK k-rows of 128 bytes (128 consecutive m); 8 k-rows = 1024 B apart (SBO); for the
+// 256-wide B operand the second 128-column atom sits one A-sized tile further (LBO = BK * 128 B)
+__device__ __forceinline__ uint64_t make_desc_mn(const void* smem_tile) {
+    const uint64_t addr = (uint64_t)((tc::smem_u32(smem_tile) & 0x3FFFF) >> 4);
+    return addr | ((uint64_t)((BK * 128) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
@@ -236,15 +306,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(tc::smem_u32(dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-__device__ __forceinline__ int mod_centered(int acc, int p, float invp) {
-    // q within +-1 of acc / p (the float rounding of acc costs < 64 / 193 of a quotient step); r exact in integers
-    const int q = __float2int_rn((float)acc * invp);
+// acc mod p as a value in [-128, 127] congruent to acc: Barrett with magic = ceil(2^32 / p) = (2^32 + d) / p, 0 <= d < p.
+// __mulhi floors acc / p + acc d / (p 2^32), whose second term is below |acc| / 2^32 in magnitude:
+//   SMALL (|acc| <= 2^24, reductions up to 1024): the term is below 1 / p, q is exact for acc >= 0 and at most one too small for
+//         acc < 0 when p | acc  =>  r = acc - q p in [0, p], and the centring step maps r = p to 0;
+//   otherwise (|acc| < 2^31): q is off by at most one either way  =>  r in [-p, 2p), two more conditional corrections.
+template <bool SMALL>
+__device__ __forceinline__ int mod_centered(int acc, int p, uint32_t magic) {
+    const int q = __mulhi(acc, (int)magic);
     int r = acc - q * p;
-    const int h = p >> 1;
-    r = r >= h ? r - p : r;
-    r = r < -h ? r + p : r;
-    r = r >= h ? r - p : r;
-    r = r < -h ? r + p : r;
+    if (!SMALL) {
+        r = r < 0 ? r + p : r;
+        r = r >= p ? r - p : r;
+    }
+    r = r > 127 ? r - p : r;
     return r;
 }
 
@@ -301,15 +376,22 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    tma_load_3d(st, &mapA, &full[stage], k, m0, t);
-                    tma_load_3d(st + A_BYTES, &mapB, &full[stage], k, n0, t);
+                    // MN-major planes [t][k][m]: boxes of 128 m-bytes x BK k-rows; K-major [t][m][k]: BK k-bytes x rows
+                    if (p.mn_major & 1) tma_load_3d(st, &mapA, &full[stage], m0, k, t);
+                    else tma_load_3d(st, &mapA, &full[stage], k, m0, t);
+                    if (p.mn_major & 2) {
+                        tma_load_3d(st + A_BYTES, &mapB, &full[stage], n0, k, t);
+                        tma_load_3d(st + 2 * A_BYTES, &mapB, &full[stage], n0 + 128, k, t);
+                    } else {
+                        tma_load_3d(st + A_BYTES, &mapB, &full[stage], k, n0, t);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_i8();
+            const uint32_t idesc = make_idesc_i8(p.mn_major);
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t bphase = 0;
             for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -323,11 +405,14 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     uint8_t* st = smem + stage * STAGE_BYTES;
-                    const uint64_t dA = make_desc(st), dB = make_desc(st + A_BYTES);
+                    // per 32-deep MMA the descriptor advances 32 B inside the swizzle row (K-major) or 32 k-rows of 128 B (MN-major)
+                    const uint64_t dA = (p.mn_major & 1) ? make_desc_mn(st) : make_desc(st);
+                    const uint64_t dB = (p.mn_major & 2) ? make_desc_mn(st + A_BYTES) : make_desc(st + A_BYTES);
+                    const uint64_t sA = (uint64_t)(((p.mn_major & 1) ? UMMA_K * 128 : UMMA_K) >> 4);
+                    const uint64_t sB = (uint64_t)(((p.mn_major & 2) ? UMMA_K * 128 : UMMA_K) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * UMMA_K) >> 4);
-                        umma_i8(tmem_d, dA + adv, dB + adv, idesc, accum);
+                        umma_i8(tmem_d, dA + kk * sA, dB + kk * sB, idesc, accum);
                         accum = 1;
                     }
                     umma_commit(&empty[stage]);
@@ -340,12 +425,13 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     } else {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
+        const bool small_acc = (long)p.K * 16384 <= 16777216;        // |acc| <= K * 2^14 <= 2^24
         int buf = 0; uint32_t bphase = 0;
         for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
             int t, m0, n0, kb, ke;
             if (!decode(w, t, m0, n0, kb, ke)) continue;
             const int pm = p.p[t];
-            const float ip = p.invp[t];
+            const uint32_t ip = p.magic[t];
             mbar_wait(&tfull[buf], bphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
@@ -366,12 +452,22 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     : "r"(taddr + (uint32_t)c));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 uint32_t packed[8];
+                if (small_acc) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint32_t word = 0;
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t word = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) word |= ((uint32_t)(mod_centered((int)r[4 * i + j], pm, ip) & 0xff)) << (8 * j);
-                    packed[i] = word;
+                        for (int j = 0; j < 4; ++j) word |= ((uint32_t)(mod_centered<true>((int)r[4 * i + j], pm, ip) & 0xff)) << (8 * j);
+                        packed[i] = word;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) word |= ((uint32_t)(mod_centered<false>((int)r[4 * i + j], pm, ip) & 0xff)) << (8 * j);
+                        packed[i] = word;
+                    }
                 }
                 if (row < p.Mrows) {
                     if (nbase + c + 32 <= p.ldc) {
@@ -403,11 +499,13 @@ struct PlaneMapCache {
     static constexpr int N = 32;
     PlaneMapKey key[N]; CUtensorMap map[N]; int used = 0, next = 0;
 };
-inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long cols, long ld, long plane_stride, int T, int box_rows) {
+inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long cols, long ld, long plane_stride, int T, int box_rows,
+                          int box_cols = BK) {
     static PlaneMapCache cache;
     for (int i = 0; i < cache.used; ++i) {
         const PlaneMapKey& k = cache.key[i];
-        if (k.base == base && k.rows == rows && k.cols == cols && k.ld == ld && k.plane_stride == plane_stride && k.T == T && k.box_rows == box_rows) {
+        if (k.base == base && k.rows == rows && k.cols == cols && k.ld == ld && k.plane_stride == plane_stride && k.T == T &&
+            k.box_rows == box_rows + 1000 * box_cols) {
             *map = cache.map[i];
             return 0;
         }
@@ -418,28 +516,33 @@ inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long 
         return set_error(-2, "residue planes must be 16-byte aligned with 16-byte multiples as strides");
     cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)T};
     cuuint64_t gstr[2] = {(cuuint64_t)ld, (cuuint64_t)plane_stride};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(-102, "cuTensorMapEncodeTiled (residue planes) failed");
     const int i = cache.used < PlaneMapCache::N ? cache.used++ : (cache.next = (cache.next + 1) % PlaneMapCache::N);
-    cache.key[i] = PlaneMapKey{base, rows, cols, ld, plane_stride, T, box_rows};
+    cache.key[i] = PlaneMapKey{base, rows, cols, ld, plane_stride, T, box_rows + 1000 * box_cols};
     cache.map[i] = *map;
     return 0;
 }
 
-struct Planes { const int8_t* base; long rows, cols, ld, plane_stride; };       // cols = reduction length (bytes)
+// K-major: rows = operand rows (m or n), cols = reduction length.  MN-major (Params.mn_major): the planes are stored
+// [t][k][m]: rows = reduction length, cols = operand rows.
+struct Planes { const int8_t* base; long rows, cols, ld, plane_stride; };
 
 inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t st) {
     if (p.Mrows <= 0 || p.Ncols <= 0 || p.K <= 0) return 0;
     if ((long)p.K * 16384 >= 2147483648L) return set_error(-3, "int8 reduction too long for exact s32 accumulation (K < 131072)");
     CUtensorMap mA, mB;
-    TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BM));
-    TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BN));
+    // MN-major boxes: 128 operand rows (contiguous bytes) x BK reduction rows
+    if (p.mn_major & 1) TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BK, 128));
+    else TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BM));
+    if (p.mn_major & 2) TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BK, 128));
+    else TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BN));
     const CrtTable& tab = crt_table(p.T);
-    for (int t = 0; t < p.T; ++t) { p.p[t] = tab.p[t]; p.invp[t] = tab.invp[t]; }
+    for (int t = 0; t < p.T; ++t) { p.p[t] = tab.p[t]; p.magic[t] = tab.magic[t]; }
     static PerDeviceOnce attr_once;
     if (attr_once.first()) cudaFuncSetAttribute(gemm_i8_mod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     const long tiles = (long)cdiv(p.Mrows, BM) * cdiv(p.Ncols, BN) * p.T;
@@ -479,14 +582,18 @@ __device__ __forceinline__ double crt_value(const int* r, const CrtTable& tab) {
 //   ea: row exponents (ea_mode 0) / one exponent ea[0] (ea_mode 2);  eb: per-column exponents (eb_mode 1) / eb[0] (2)
 //   accumulate = 1: FP64 atomicAdd (weight gradients summed over row chunks); lower_rows > 0: rows r < lower_rows only c <= r
 // one warp per row, four consecutive columns per lane per step
+// stats (forward only; cols = 2 * stat_M, row = [a | b]): mu[r] = sum_{c < M} out * m[c], v[r] = os - sum_{c<M} out^2 +
+// sum_{c>=M} out^2 — the q(f) marginals come out of the reconstruction pass, [A | B] is not re-read for them
+struct RowStats { const double* m; const double* os; double* mu; double* v; int M; };
 __global__ void __launch_bounds__(256) k_crt_combine(const int8_t* __restrict__ R, long ldr, long plane_stride, long rows, int cols,
                                                      CrtTable tab, int bits2, const int* __restrict__ ea, int ea_mode,
                                                      const int* __restrict__ eb, int eb_mode, double* __restrict__ out, long ldo,
-                                                     int accumulate, int lower_rows) {
+                                                     int accumulate, int lower_rows, RowStats st) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (long r = (long)blockIdx.x * wpb + wid; r < rows; r += (long)gridDim.x * wpb) {
         const int era = ea_mode == 0 ? ea[r] : ea[0];
         const int climit = (lower_rows > 0 && r < lower_rows) ? (int)min((long)cols, r + 1) : cols;
+        double sm = 0.0, sa = 0.0, sb = 0.0;
         for (int c0 = lane * 4; c0 < climit; c0 += 128) {
             uint32_t w[MAX_T];
 #pragma unroll
@@ -502,7 +609,15 @@ __global__ void __launch_bounds__(256) k_crt_combine(const int8_t* __restrict__ 
                 const double v = scalbn(crt_value(res, tab), era + (eb_mode == 1 ? eb[c] : eb[0]) - bits2);
                 if (accumulate) atomicAdd(out + r * ldo + c, v);
                 else out[r * ldo + c] = v;
+                if (st.mu) {
+                    if (c < st.M) { sm = fma(v, __ldg(st.m + c), sm); sa = fma(v, v, sa); }
+                    else sb = fma(v, v, sb);
+                }
             }
+        }
+        if (st.mu) {
+            sm = warp_sum(sm); sa = warp_sum(sa); sb = warp_sum(sb);
+            if (lane == 0) { st.mu[r] = sm; st.v[r] = st.os[0] - sa + sb; }
         }
     }
 }

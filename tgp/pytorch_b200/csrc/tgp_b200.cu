@@ -636,10 +636,10 @@ int tgp_debug_gemm_tf32x3(int Mrows, int Ncols, int K, const float* Ahi, const f
 size_t tgp_debug_gemm_crt_bytes(long M, long N, long K, int T) { return crt::debug_bytes(M, N, K, T); }
 
 int tgp_debug_gemm_crt(long M, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc, int T,
-                       int tri_mode, int tri_rows, int lower_rows, int accumulate, void* scratch, void* stream) {
+                       int tri_mode, int tri_rows, int lower_rows, int accumulate, int mn_major, void* scratch, void* stream) {
     if (T < 1 || T > i8::MAX_T) return set_error(-1, "T must be in 1..16");
     if (!A || !B || !C || !scratch) return set_error(-1, "NULL argument to tgp_debug_gemm_crt");
-    return crt::debug_matmul(M, N, K, A, lda, B, ldb, C, ldc, T, tri_mode, tri_rows, lower_rows, accumulate, scratch,
+    return crt::debug_matmul(M, N, K, A, lda, B, ldb, C, ldc, T, tri_mode, tri_rows, lower_rows, accumulate, mn_major, scratch,
                              (cudaStream_t)stream);
 }
 

@@ -326,12 +326,14 @@ def debug_gemm_tf32x3(A, B, out, out_mode=0, tri_mode=0, tri_rows=0, lower_rows=
     return Ah, Al, Bh, Bl
 
 
-def debug_gemm_crt(A, B, out, T=16, tri_mode=0, tri_rows=0, lower_rows=0, accumulate=False):
-    """out (+)= A @ B.T through the integer-residue (CRT) pipeline of compute mode 'i8crt'; A (M, K), B (N, K), out (M, N) FP64."""
+def debug_gemm_crt(A, B, out, T=16, tri_mode=0, tri_rows=0, lower_rows=0, accumulate=False, mn_major=0):
+    """out (+)= A @ B.T through the integer-residue (CRT) pipeline of compute mode 'i8crt'; A (M, K), B (N, K), out (M, N) FP64.
+    mn_major bit 0 / 1: A / B is given transposed ((K, M) / (K, N)) and read MN-major by the tensor core."""
     lib = _lib.load()
-    Mr, K = A.shape
-    N = B.shape[0]
+    Mr, K = (A.shape[1], A.shape[0]) if mn_major & 1 else A.shape
+    N = B.shape[1] if mn_major & 2 else B.shape[0]
     scratch = torch.empty(lib.tgp_debug_gemm_crt_bytes(Mr, N, K, T), dtype=torch.uint8, device=A.device)
     _lib.check(lib.tgp_debug_gemm_crt(Mr, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), T, tri_mode,
-                                      tri_rows, lower_rows, 1 if accumulate else 0, _ptr(scratch), _stream()), 'tgp_debug_gemm_crt')
+                                      tri_rows, lower_rows, 1 if accumulate else 0, mn_major, _ptr(scratch), _stream()),
+               'tgp_debug_gemm_crt')
     return out
