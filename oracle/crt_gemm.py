@@ -5,7 +5,7 @@ C = A B^T for FP64 A (m x k), B (n x k), evaluated as the tcgen05 kind::i8 path 
   2. residues: A_t = A' mod p_t (centred, int8) for T pairwise coprime moduli p_t <= 256;
   3. T independent int8 GEMMs with exact int32 accumulation, reduced mod p_t: R_t = (A_t B_t^T) mod p_t (int8 again);
   4. CRT: C' = sum_t R_t w_t mod P  (w_t = (P/p_t) * ((P/p_t)^-1 mod p_t)) in 40-bit words whose partial sums are exact in
-     FP64 (|R_t| <= 128, 16 terms, words < 2^40: sums < 2^51); the multiple of P is rint(sum_t R_t w_t / P);
+     FP64 (|R_t| <= 128, 16 terms, words < 2^40: sums < 2^51); the multiple of P is rint(total / P) evaluated in FP64;
   5. C = C' * 2^(eA_i + eB_j - 2b).
 The integer product is EXACT; the only error is the truncation of the operands to b bits below their row maximum.
 This file mirrors the device arithmetic step by step (same words, same order) with numpy int64 / float64, and offers the
@@ -86,12 +86,13 @@ def combine(R, eA, eB, bA, bB, T):
     _, words, frac, Pw = crt_constants(T)
     r = R.astype(np.float64)
     S = [np.zeros(R.shape[1:]) for _ in range(N_WORDS)]
-    mf = np.zeros(R.shape[1:])
     for t in range(T):
         for k in range(N_WORDS):
             S[k] = S[k] + r[t] * words[t, k]           # exact (< 2^51)
-        mf = mf + r[t] * frac[t]
-    m = np.rint(mf)
+    # the multiple of P: total / P in FP64 (|m| <= 2^11, error ~2^-42; the bit budget keeps |C'| / P away from 1/2)
+    P = crt_constants(T)[0]
+    tw = float(1 << WORD_BITS)
+    m = np.rint((((S[3] * tw + S[2]) * tw + S[1]) * tw + S[0]) * (1.0 / P))
     D = [S[k] - m * Pw[k] for k in range(N_WORDS)]     # exact (< 2^52)
     two = float(1 << WORD_BITS)
     for k in range(N_WORDS - 1):                        # carry normalisation: |D_k| <= 2^39 for k < top

@@ -47,6 +47,7 @@ struct CrtTable {                 // passed by value to the kernels (< 1 KiB)
     double frac[MAX_T];           // w_t / P
     double Pw[N_WORDS];           // words of P
     double log2P;
+    double invP;                  // 1 / P
     // residues of a 56-bit magnitude by byte limbs: u = sum_k a_k 256^k  =>  u mod p = (sum_k a_k (256^k mod p)) mod p;
     // clo / chi pack (256^k mod p) for k = 0..3 / 4..7 (dp4a operands), magic = ceil(2^32 / p) (exact floor division of
     // the < 2^19 limb sum by a multiply-high)
@@ -86,6 +87,7 @@ inline const CrtTable& crt_table(int T) {
         }
         for (int k = 0; k < N_WORDS; ++k) c.Pw[k] = (double)(unsigned long long)((P >> (WORD_BITS * k)) & mask);
         c.log2P = (double)log2l(to_ld(P));
+        c.invP = (double)(1.0L / to_ld(P));
         have[T] = true;
     }
     return tabs[T];
@@ -96,6 +98,12 @@ inline int crt_bits(int T, long k_red) {
     const double room = crt_table(T).log2P - 1.0 - log2((double)(k_red > 1 ? k_red : 1)) - 1e-6;
     int b = (int)floor(room / 2.0);
     return b > 53 ? 53 : (b < 1 ? 1 : b);
+}
+
+// x * 2^n, exact: one multiply by a constructed power of two when n is an ordinary exponent
+__device__ __forceinline__ double mul_pow2(double x, int n) {
+    if (n > -1000 && n < 1000) return x * __hiloint2double((1023 + n) << 20, 0);
+    return scalbn(x, n);
 }
 
 // ---- step 1 + 2: FP64 -> residue planes -----------------------------------------------------------------------------
@@ -148,15 +156,15 @@ __global__ void k_fill_int(int* __restrict__ p, long n, int v) {
 
 // centred residue in [-128, 127] of the integer sign * (hi * 2^32 + lo) (magnitude < 2^56) modulo tab.p[t]: two dp4a over
 // the byte limbs, an exact multiply-high division of the < 2^19 limb sum, sign and centring
-__device__ __forceinline__ int residue_of(uint32_t lo, uint32_t hi, bool neg, const CrtTable& tab, int t) {
-    const uint32_t s = __dp4a(lo, tab.clo[t], __dp4a(hi, tab.chi[t], 0u));
-    const int p = tab.p[t];
-    int r = (int)(s - __umulhi(s, tab.magic[t]) * (uint32_t)p);           // [0, p)
-    r = neg ? -r : r;
-    const int h = p >> 1;
-    r = r >= h ? r - p : r;                                               // p = 256: [-128, 127]; odd p: [-(p-1)/2 - 1, (p-1)/2]
-    r = r < -h ? r + p : r;
-    return r;
+__device__ __forceinline__ int residue_of(uint32_t lo, uint32_t hi, bool neg, uint32_t clo, uint32_t chi, uint32_t magic, int p) {
+    const uint32_t s = __dp4a(lo, clo, __dp4a(hi, chi, 0u));
+    int r = (int)(s - __umulhi(s, magic) * (uint32_t)p);                  // |x| mod p in [0, p)
+    r = neg ? p - r : r;                                                  // -|x| mod p in (0, p]
+    return r > 127 ? r - p : r;                                           // centred representative (p -> 0, 128 -> -128 mod 256)
+}
+// the low bytes of four ints as one word
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
 }
 
 // residues of 16 scaled integers (thread-private, consecutive columns of one row) for every modulus -> planes[t][r][c..c+15]
@@ -179,14 +187,15 @@ __device__ __forceinline__ void emit_residues(const long long (&xi)[16], const C
     const bool vec = c + 16 <= ldp;                  // zero residues pad the row up to ldp
 #pragma unroll 2
     for (int t = 0; t < tab.T; ++t) {
+        const uint32_t clo = tab.clo[t], chi = tab.chi[t], magic = tab.magic[t];
+        const int p = tab.p[t];
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint32_t word = 0;
+            int q[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                word |= ((uint32_t)(residue_of(lo[4 * j + i], hi[4 * j + i], (negmask >> (4 * j + i)) & 1u, tab, t) & 0xff)) << (8 * i);
-            w[j] = word;
+            for (int i = 0; i < 4; ++i) q[i] = residue_of(lo[4 * j + i], hi[4 * j + i], (negmask >> (4 * j + i)) & 1u, clo, chi, magic, p);
+            w[j] = pack4(q[0], q[1], q[2], q[3]);
         }
         int8_t* dst = dst0 + (long)t * plane_stride;
         if (vec) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -212,14 +221,14 @@ __global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int e = scale_mode == 0 ? (r < rows ? exps[r] : 0) : (scale_mode == 1 ? (c + i < cols ? exps[c + i] : 0) : exps[0]);
-        xi[i] = __double2ll_rn(scalbn(x[i], bits - e));
+        xi[i] = __double2ll_rn(mul_pow2(x[i], bits - e));
     }
     emit_residues(xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
     if (planes2) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = scale_mode2 == 0 ? (r < rows ? exps2[r] : 0) : (scale_mode2 == 1 ? (c + i < cols ? exps2[c + i] : 0) : exps2[0]);
-            xi[i] = __double2ll_rn(scalbn(x[i], bits2 - e));
+            xi[i] = __double2ll_rn(mul_pow2(x[i], bits2 - e));
         }
         CrtTable tab2 = tab;
         tab2.T = T2;                                  // the moduli of a shorter table are a prefix of the longer one
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
             val = s * exp(-0.5 * acc);
             if (Kout) Kout[r * ldk_out + c] = val;
         }
-        xi[i] = __double2ll_rn(scalbn(val, sh));
+        xi[i] = __double2ll_rn(mul_pow2(val, sh));
     }
     emit_residues(xi, tab, r, R, c0 + tcb, M, planes, ldp, plane_stride);
 }
@@ -454,20 +463,14 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 uint32_t packed[8];
                 if (small_acc) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint32_t word = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) word |= ((uint32_t)(mod_centered<true>((int)r[4 * i + j], pm, ip) & 0xff)) << (8 * j);
-                        packed[i] = word;
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        packed[i] = pack4(mod_centered<true>((int)r[4 * i], pm, ip), mod_centered<true>((int)r[4 * i + 1], pm, ip),
+                                          mod_centered<true>((int)r[4 * i + 2], pm, ip), mod_centered<true>((int)r[4 * i + 3], pm, ip));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint32_t word = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) word |= ((uint32_t)(mod_centered<false>((int)r[4 * i + j], pm, ip) & 0xff)) << (8 * j);
-                        packed[i] = word;
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        packed[i] = pack4(mod_centered<false>((int)r[4 * i], pm, ip), mod_centered<false>((int)r[4 * i + 1], pm, ip),
+                                          mod_centered<false>((int)r[4 * i + 2], pm, ip), mod_centered<false>((int)r[4 * i + 3], pm, ip));
                 }
                 if (row < p.Mrows) {
                     if (nbase + c + 32 <= p.ldc) {
@@ -555,33 +558,34 @@ inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t 
 }
 
 // ---- step 4 + 5: CRT reconstruction -----------------------------------------------------------------------------------
-// value of sum_t r_t w_t mod P (centred) for one output element, as a double (relative error <= 3 * 2^-53)
-__device__ __forceinline__ double crt_value(const int* r, const CrtTable& tab) {
-    double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0, mf = 0.0;
+// value of sum_t r_t w_t mod P (centred) for the residues packed in byte `i` of w[t], as a double (relative error <= 3 * 2^-53).
+// The multiple of P is m = rint(total / P) with total = ((S3 2^40 + S2) 2^40 + S1) 2^40 + S0 evaluated in FP64: |m| <= 2^11, so
+// its rounding error is ~2^-42, far inside the margin the bit budget leaves between |C'| / P and 1/2.
+__device__ __forceinline__ double crt_value(const uint32_t* w, int i, const CrtTable& tab) {
+    double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0;
+    const uint32_t sel = (uint32_t)i | ((8u | (uint32_t)i) << 4) | ((8u | (uint32_t)i) << 8) | ((8u | (uint32_t)i) << 12);
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t) {
         if (t < tab.T) {
-            const double rt = (double)r[t];
+            int r;                                                                     // sign-extended byte i (prmt: selector
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w[t]), "r"(0u), "r"(sel));   // msb = replicate the byte's sign)
+            // int -> double without a conversion instruction: (2^52 + 2^31 + r) - (2^52 + 2^31)
+            const double rt = __hiloint2double(0x43300000, r ^ 0x80000000) - 4503601774854144.0;
             S0 = fma(rt, tab.w[t][0], S0);
             S1 = fma(rt, tab.w[t][1], S1);
             S2 = fma(rt, tab.w[t][2], S2);
             S3 = fma(rt, tab.w[t][3], S3);
-            mf = fma(rt, tab.frac[t], mf);
         }
     }
-    const double m = rint(mf);
-    double D0 = fma(-m, tab.Pw[0], S0), D1 = fma(-m, tab.Pw[1], S1), D2 = fma(-m, tab.Pw[2], S2), D3 = fma(-m, tab.Pw[3], S3);
     const double two = 1099511627776.0, inv = 9.094947017729282e-13;       // 2^40, 2^-40
+    const double m = rint(fma(fma(fma(S3, two, S2), two, S1), two, S0) * tab.invP);
+    double D0 = fma(-m, tab.Pw[0], S0), D1 = fma(-m, tab.Pw[1], S1), D2 = fma(-m, tab.Pw[2], S2), D3 = fma(-m, tab.Pw[3], S3);
     double c = rint(D0 * inv); D0 = fma(-c, two, D0); D1 += c;
     c = rint(D1 * inv); D1 = fma(-c, two, D1); D2 += c;
     c = rint(D2 * inv); D2 = fma(-c, two, D2); D3 += c;
     return fma(fma(fma(D3, two, D2), two, D1), two, D0);
 }
 
-// R planes [t][rows][ldr] -> out[r * ldo + c] = (or +=) crt * 2^(ea + eb - bits2)
-//   ea: row exponents (ea_mode 0) / one exponent ea[0] (ea_mode 2);  eb: per-column exponents (eb_mode 1) / eb[0] (2)
-//   accumulate = 1: FP64 atomicAdd (weight gradients summed over row chunks); lower_rows > 0: rows r < lower_rows only c <= r
-// one warp per row, four consecutive columns per lane per step
 // stats (forward only; cols = 2 * stat_M, row = [a | b]): mu[r] = sum_{c < M} out * m[c], v[r] = os - sum_{c<M} out^2 +
 // sum_{c>=M} out^2 — the q(f) marginals come out of the reconstruction pass, [A | B] is not re-read for them
 struct RowStats { const double* m; const double* os; double* mu; double* v; int M; };
@@ -603,10 +607,7 @@ __global__ void __launch_bounds__(256) k_crt_combine(const int8_t* __restrict__ 
             for (int i = 0; i < 4; ++i) {
                 const int c = c0 + i;
                 if (c >= climit) break;
-                int res[MAX_T];
-#pragma unroll
-                for (int t = 0; t < MAX_T; ++t) res[t] = (int)(int8_t)((w[t] >> (8 * i)) & 0xff);
-                const double v = scalbn(crt_value(res, tab), era + (eb_mode == 1 ? eb[c] : eb[0]) - bits2);
+                const double v = mul_pow2(crt_value(w, i, tab), era + (eb_mode == 1 ? eb[c] : eb[0]) - bits2);
                 if (accumulate) atomicAdd(out + r * ldo + c, v);
                 else out[r * ldo + c] = v;
                 if (st.mu) {
