@@ -226,7 +226,7 @@ int tgp_debug_gemm_tf32x3(int Mrows, int Ncols, int K, const float* Ahi, const f
                           const float* Blo, long ldb, float* Cf, double* Cd, long ldc, int out_mode, int tri_mode,
                           int tri_rows, int lower_rows, int splitk, void* stream);
 /* Test hook: C (+)= A B^T (A: M x K, B: N x K, row-major FP64) through the integer-residue pipeline of TGP_F64_I8 with T
- * moduli; tri_mode / tri_rows / lower_rows as in the tf32x3 hook; mn_major bit 0 / 1: A / B is passed transposed ((K x M) /
+ * moduli (9, 12, 15 or 16); tri_mode / tri_rows / lower_rows as in the tf32x3 hook; mn_major bit 0 / 1: A / B is passed transposed ((K x M) /
  * (K x N)) and the tensor core reads it MN-major; scratch: tgp_debug_gemm_crt_bytes() device bytes. */
 size_t tgp_debug_gemm_crt_bytes(long M, long N, long K, int T);
 int tgp_debug_gemm_crt(long M, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc,

@@ -2,10 +2,10 @@
 
 C = A B^T for FP64 A (m x k), B (n x k), evaluated as the tcgen05 kind::i8 path does it ("Ozaki scheme II"):
   1. integerise: A'[i,:] = rint(A[i,:] * 2^(b - eA_i)), 2^eA_i > max_j |A_ij| (per row; likewise B), |A'| <= 2^b;
-  2. residues: A_t = A' mod p_t (centred, int8) for T pairwise coprime moduli p_t <= 256;
-  3. T independent int8 GEMMs with exact int32 accumulation, reduced mod p_t: R_t = (A_t B_t^T) mod p_t (int8 again);
+  2. residues: A_t = A' mod p_t in [0, p_t) (uint8) for T pairwise coprime moduli p_t <= 256;
+  3. T independent u8 GEMMs with exact 32-bit accumulation, reduced mod p_t: R_t = (A_t B_t^T) mod p_t (uint8 again);
   4. CRT: C' = sum_t R_t w_t mod P  (w_t = (P/p_t) * ((P/p_t)^-1 mod p_t)) in 40-bit words whose partial sums are exact in
-     FP64 (|R_t| <= 128, 16 terms, words < 2^40: sums < 2^51); the multiple of P is rint(total / P) evaluated in FP64;
+     FP64 (R_t <= 255, 16 terms, words < 2^40: sums < 2^52); the multiple of P is rint(total / P) evaluated in FP64;
   5. C = C' * 2^(eA_i + eB_j - 2b).
 The integer product is EXACT; the only error is the truncation of the operands to b bits below their row maximum.
 This file mirrors the device arithmetic step by step (same words, same order) with numpy int64 / float64, and offers the
@@ -53,31 +53,20 @@ def integerise(A, b):
 
 
 def residues(Ai, T):
-    """(T, rows, cols) int8 centred residues, with the device's arithmetic: q = rint(x / p), r = x - q p, one fix-up."""
-    out = np.empty((T,) + Ai.shape, dtype=np.int8)
-    x = Ai.astype(np.float64)
+    """(T, rows, cols) uint8 residues in [0, p) — what the device's byte-limb / multiply-high arithmetic yields."""
+    out = np.empty((T,) + Ai.shape, dtype=np.uint8)
     for t, p in enumerate(MODULI[:T]):
-        q = np.rint(x * (1.0 / p))
-        r = x - q * p                                  # exact: fma on the device
-        r = np.where(r > p / 2 - 0.25, r - p, r)
-        r = np.where(r < -p / 2 - 0.25, r + p, r)
-        assert np.all(np.abs(r) <= 128)
-        out[t] = np.where(r == 128, -128, r).astype(np.int8) if p == 256 else r.astype(np.int8)
+        out[t] = np.mod(Ai, p).astype(np.uint8)          # numpy's mod is non-negative for a positive modulus
     return out
 
 
 def gemm_mod(Ar, Br, T):
-    """R_t = (A_t B_t^T) mod p_t, centred int8 (exact integer accumulation)."""
-    out = np.empty((T, Ar.shape[1], Br.shape[1]), dtype=np.int8)
+    """R_t = (A_t B_t^T) mod p_t in [0, p) (exact integer accumulation: u8 x u8 products, K * 255^2 < 2^31)."""
+    out = np.empty((T, Ar.shape[1], Br.shape[1]), dtype=np.uint8)
     for t, p in enumerate(MODULI[:T]):
         acc = Ar[t].astype(np.int64) @ Br[t].astype(np.int64).T
-        assert np.abs(acc).max() < 2 ** 31
-        q = np.rint(acc.astype(np.float64) * (1.0 / p)).astype(np.int64)
-        r = acc - q * p
-        r = np.where(r > p // 2, r - p, r)
-        r = np.where(r < -(p // 2) - (1 if p == 256 else 0), r + p, r)
-        r = np.where(r == 128, -128, r)
-        out[t] = r.astype(np.int8)
+        assert 0 <= acc.min() and acc.max() < 2 ** 31
+        out[t] = np.mod(acc, p).astype(np.uint8)
     return out
 
 

@@ -34,8 +34,8 @@ inline int wgt_bits(long rc) { return bits_other(T_ALL, rc, 53); }
 
 struct StepPlanes {               // per step: residues of W = [Linv; C] (2M x M), scaled per row and scaled per column
     double* Wst;                  // FP64 stacked operand (2M x M, ld M)
-    int8_t *W;                    // planes [T][2M][ldk], per-row scale: forward operand (reduction over its columns, K-major)
-    int8_t *Wc;                   // planes [T][2M][ldk], per-column scale: backward-data operand Kbar = ABbar W (reduction over
+    uint8_t *W;                    // planes [T][2M][ldk], per-row scale: forward operand (reduction over its columns, K-major)
+    uint8_t *Wc;                   // planes [T][2M][ldk], per-column scale: backward-data operand Kbar = ABbar W (reduction over
                                   // its ROWS: the tensor core reads it MN-major, no transposed copy)
     int *w_row_exp, *w_col_exp, *k_exp;
     long ldk;
@@ -51,8 +51,8 @@ inline StepPlanes carve_step(void* region, int M) {
     s.ldk = pad16(M);
     char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(region) + 255) & ~uintptr_t(255));
     s.Wst = reinterpret_cast<double*>(p); p += (size_t)2 * M * M * sizeof(double);
-    s.W = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
-    s.Wc = reinterpret_cast<int8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
+    s.W = reinterpret_cast<uint8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
+    s.Wc = reinterpret_cast<uint8_t*>(p); p += (size_t)T_ALL * 2L * M * s.ldk;
     p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
     s.w_row_exp = reinterpret_cast<int*>(p); p += (size_t)2 * M * sizeof(int);
     s.w_col_exp = reinterpret_cast<int*>(p); p += (size_t)M * sizeof(int);
@@ -64,11 +64,11 @@ struct BatchView {
     double *AB;                   // (R x 2M) FP64, forward -> backward ([A | B], turned into [Abar | Bbar] in place)
     double *Kbuf;                 // (R x M) FP64 K_xz (kernel gradients read it)
     double *Kbar;                 // (Rc x M)
-    int8_t *Kp;                   // planes [T_ALL][R][ldk]   K_xz residues: forward operand AND weight-contraction operand
-    int8_t *Op;                   // planes [T][Rc][ld2m]     result residues of the forward; then ABbar scaled per row
-    int8_t *Pc;                   // planes [T_ALL][Rc][ld2m] ABbar scaled per column (weight-contraction operand, MN-major)
-    int8_t *Kbp;                  // planes [T][Rc][ldk]      Kbar result residues
-    int8_t *Gp;                   // planes [T_ALL][2M][ldk]  weight-contraction result residues
+    uint8_t *Kp;                   // planes [T_ALL][R][ldk]   K_xz residues: forward operand AND weight-contraction operand
+    uint8_t *Op;                   // planes [T][Rc][ld2m]     result residues of the forward; then ABbar scaled per row
+    uint8_t *Pc;                   // planes [T_ALL][Rc][ld2m] ABbar scaled per column (weight-contraction operand, MN-major)
+    uint8_t *Kbp;                  // planes [T][Rc][ldk]      Kbar result residues
+    uint8_t *Gp;                   // planes [T_ALL][2M][ldk]  weight-contraction result residues
     int *row_exp, *col_exp;       // (Rc), (2M)
     long Rc, ldk, ld2m;
 };
@@ -91,11 +91,11 @@ inline BatchView carve_batch(void* ws, int M, long R) {
     b.AB = reinterpret_cast<double*>(take((size_t)R * 2 * M * 8));
     b.Kbuf = reinterpret_cast<double*>(take((size_t)R * M * 8));
     b.Kbar = reinterpret_cast<double*>(take((size_t)b.Rc * M * 8));
-    b.Kp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * R * b.ldk));
-    b.Op = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
-    b.Pc = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
-    b.Kbp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * b.Rc * b.ldk));
-    b.Gp = reinterpret_cast<int8_t*>(take((size_t)T_ALL * 2 * M * b.ldk));
+    b.Kp = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * R * b.ldk));
+    b.Op = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
+    b.Pc = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
+    b.Kbp = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * b.Rc * b.ldk));
+    b.Gp = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * 2 * M * b.ldk));
     b.row_exp = reinterpret_cast<int*>(take((size_t)b.Rc * sizeof(int)));
     b.col_exp = reinterpret_cast<int*>(take((size_t)2 * M * sizeof(int)));
     return b;
@@ -123,8 +123,8 @@ inline int exponents(const double* src, long ld, long rows, int cols, int* row_e
 }
 
 inline int to_residues(const double* src, long ld, long rows, int cols, int scale_mode, const int* exps, int bits, int T,
-                       int8_t* planes, long ldp, long plane_stride, cudaStream_t st, int scale_mode2 = 0, const int* exps2 = nullptr,
-                       int bits2 = 0, int T2 = 0, int8_t* planes2 = nullptr, long ldp2 = 0, long plane_stride2 = 0) {
+                       uint8_t* planes, long ldp, long plane_stride, cudaStream_t st, int scale_mode2 = 0, const int* exps2 = nullptr,
+                       int bits2 = 0, int T2 = 0, uint8_t* planes2 = nullptr, long ldp2 = 0, long plane_stride2 = 0) {
     dim3 grid((unsigned)cdiv(cols, i8::RS_TC), (unsigned)cdiv(rows, i8::RS_TR));
     // the second set may use more moduli than the first: pass the longer table, the first set's count travels in tab.T
     i8::CrtTable tab = i8::crt_table(T > T2 ? T : T2);
@@ -134,17 +134,27 @@ inline int to_residues(const double* src, long ld, long rows, int cols, int scal
     return check_launch("k_to_residues");
 }
 
-inline int combine(const int8_t* R, long ldr, long plane_stride, long rows, int cols, int T, int bits2, const int* ea, int ea_mode,
+inline int combine(const uint8_t* R, long ldr, long plane_stride, long rows, int cols, int T, int bits2, const int* ea, int ea_mode,
                    const int* eb, int eb_mode, double* out, long ldo, int accumulate, int lower_rows, cudaStream_t st,
                    i8::RowStats stats = i8::RowStats{nullptr, nullptr, nullptr, nullptr, 0}) {
-    i8::k_crt_combine<<<i8::crt_grid(rows), 256, 0, st>>>(R, ldr, plane_stride, rows, cols, i8::crt_table(T), bits2, ea, ea_mode, eb,
-                                                         eb_mode, out, ldo, accumulate, lower_rows, stats);
+    const i8::CrtTable& tab = i8::crt_table(T);
+    const int grid = i8::crt_grid(rows);
+#define TGP_CC(TT) i8::k_crt_combine<TT><<<grid, 256, 0, st>>>(R, ldr, plane_stride, rows, cols, tab, bits2, ea, ea_mode, eb, eb_mode, out, \
+                                                             ldo, accumulate, lower_rows, stats)
+    switch (T) {          // the modulus count is a compile-time constant of the kernel (immediate constant-bank operands)
+        case 16: TGP_CC(16); break;
+        case 15: TGP_CC(15); break;
+        case 12: TGP_CC(12); break;
+        case 9: TGP_CC(9); break;
+        default: return set_error(-1, "CRT reconstruction is instantiated for 9, 12, 15 and 16 moduli");
+    }
+#undef TGP_CC
     return check_launch("k_crt_combine");
 }
 
 // K_xz of a row chunk in one pass: FP64 values and residue planes (i8::k_rbf_residues)
 inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
-                        const int* kexp, int T, int8_t* planes, long ldp, long plane_stride, cudaStream_t st) {
+                        const int* kexp, int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st) {
     dim3 grid((unsigned)cdiv(M, i8::RS_TC), (unsigned)cdiv(R, i8::RS_TR));
     const i8::CrtTable& tab = i8::crt_table(T);
 #define TGP_RR(MD) i8::k_rbf_residues<MD><<<grid, 256, 0, st>>>(X, Zs, ls, os, R, M, D, Kout, M, kexp, 53, tab, planes, ldp, plane_stride)
@@ -299,9 +309,9 @@ inline int debug_matmul(long Mr, long N, long K, const double* A, long lda, cons
     const bool at = mn_major & 1, bt = mn_major & 2;
     char* p = reinterpret_cast<char*>(scratch);
     auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
-    int8_t* Ap = reinterpret_cast<int8_t*>(take((size_t)T * (at ? K * ldm : Mr * ldk)));
-    int8_t* Bp = reinterpret_cast<int8_t*>(take((size_t)T * (bt ? K * ldn : N * ldk)));
-    int8_t* Cp = reinterpret_cast<int8_t*>(take((size_t)T * Mr * ldn));
+    uint8_t* Ap = reinterpret_cast<uint8_t*>(take((size_t)T * (at ? K * ldm : Mr * ldk)));
+    uint8_t* Bp = reinterpret_cast<uint8_t*>(take((size_t)T * (bt ? K * ldn : N * ldk)));
+    uint8_t* Cp = reinterpret_cast<uint8_t*>(take((size_t)T * Mr * ldn));
     int* ea = reinterpret_cast<int*>(take((size_t)Mr * sizeof(int)));
     int* eb = reinterpret_cast<int*>(take((size_t)N * sizeof(int)));
     const int bits = i8::crt_bits(T, K);

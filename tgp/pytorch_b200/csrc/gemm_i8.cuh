@@ -52,6 +52,7 @@ struct CrtTable {                 // passed by value to the kernels (< 1 KiB)
     // clo / chi pack (256^k mod p) for k = 0..3 / 4..7 (dp4a operands), magic = ceil(2^32 / p) (exact floor division of
     // the < 2^19 limb sum by a multiply-high)
     uint32_t clo[MAX_T], chi[MAX_T], magic[MAX_T];
+    uint32_t init[MAX_T];         // (p - 2^54 mod p) mod p: signed integers are shifted by 2^54 before the limbs are taken
 };
 
 inline const CrtTable& crt_table(int T) {
@@ -84,6 +85,7 @@ inline const CrtTable& crt_table(int T) {
             }
             c.clo[t] = lo; c.chi[t] = hi;
             c.magic[t] = (uint32_t)((4294967296ull + (unsigned long long)p - 1ull) / (unsigned long long)p);
+            c.init[t] = (uint32_t)(((unsigned long long)p - (18014398509481984ull % (unsigned long long)p)) % (unsigned long long)p);
         }
         for (int k = 0; k < N_WORDS; ++k) c.Pw[k] = (double)(unsigned long long)((P >> (WORD_BITS * k)) & mask);
         c.log2P = (double)log2l(to_ld(P));
@@ -154,52 +156,61 @@ __global__ void k_fill_int(int* __restrict__ p, long n, int v) {
     if (i < n) p[i] = v;
 }
 
-// centred residue in [-128, 127] of the integer sign * (hi * 2^32 + lo) (magnitude < 2^56) modulo tab.p[t]: two dp4a over
-// the byte limbs, an exact multiply-high division of the < 2^19 limb sum, sign and centring
-__device__ __forceinline__ int residue_of(uint32_t lo, uint32_t hi, bool neg, uint32_t clo, uint32_t chi, uint32_t magic, int p) {
-    const uint32_t s = __dp4a(lo, clo, __dp4a(hi, chi, 0u));
-    int r = (int)(s - __umulhi(s, magic) * (uint32_t)p);                  // |x| mod p in [0, p)
-    r = neg ? p - r : r;                                                  // -|x| mod p in (0, p]
-    return r > 127 ? r - p : r;                                           // centred representative (p -> 0, 128 -> -128 mod 256)
+// residue in [0, p) of the signed integer x (|x| <= 2^53) handed over as u = x + 2^54 (lo / hi words): two dp4a over the byte
+// limbs of u (u = sum_k a_k 256^k  =>  u mod p = sum_k a_k (256^k mod p) mod p) started from init = -2^54 mod p, then an exact
+// multiply-high division of the < 2^19 limb sum.  Residues are UNSIGNED bytes: the tensor core takes u8 operands
+// (K * 255^2 < 2^31 for reductions up to 33025), and no centring is needed anywhere.
+__device__ __forceinline__ uint32_t residue_of(uint32_t lo, uint32_t hi, uint32_t clo, uint32_t chi, uint32_t init, uint32_t magic, uint32_t p) {
+    const uint32_t s = __dp4a(lo, clo, __dp4a(hi, chi, init));
+    return s - __umulhi(s, magic) * p;
 }
-// the low bytes of four ints as one word
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-    return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
+// the low bytes of four words as one word
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
-// residues of 16 scaled integers (thread-private, consecutive columns of one row) for every modulus -> planes[t][r][c..c+15]
+// residues of 16 scaled integers (thread-private, consecutive columns of one row) for the first T moduli -> planes[t][r][c..c+15]
 // (one 16-byte store per modulus).  Tile: RS_TR rows x RS_TC columns per CTA of 256 threads; thread (tr = tid / 8,
-// tcb = 16 * (tid % 8)).
+// tcb = 16 * (tid % 8)).  T is a compile-time constant: the table entries become immediate constant-bank operands.
 constexpr int RS_TR = 32, RS_TC = 128;
+template <int T>
 __device__ __forceinline__ void emit_residues(const long long (&xi)[16], const CrtTable& tab, long r, long rows, int c, int cols,
-                                              int8_t* __restrict__ planes, long ldp, long plane_stride) {
+                                              uint8_t* __restrict__ planes, long ldp, long plane_stride) {
     uint32_t lo[16], hi[16];
-    uint32_t negmask = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const long long v = xi[i];
-        const unsigned long long u = (unsigned long long)(v < 0 ? -v : v);
+        const unsigned long long u = (unsigned long long)(xi[i] + 18014398509481984ll);       // + 2^54 > 0
         lo[i] = (uint32_t)u; hi[i] = (uint32_t)(u >> 32);
-        negmask |= (v < 0 ? 1u : 0u) << i;
     }
     if (!(r < rows && c < cols)) return;
-    int8_t* dst0 = planes + r * ldp + c;
+    uint8_t* dst0 = planes + r * ldp + c;
     const bool vec = c + 16 <= ldp;                  // zero residues pad the row up to ldp
-#pragma unroll 2
-    for (int t = 0; t < tab.T; ++t) {
-        const uint32_t clo = tab.clo[t], chi = tab.chi[t], magic = tab.magic[t];
-        const int p = tab.p[t];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const uint32_t clo = tab.clo[t], chi = tab.chi[t], magic = tab.magic[t], init = tab.init[t], p = (uint32_t)tab.p[t];
         uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int q[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = residue_of(lo[4 * j + i], hi[4 * j + i], (negmask >> (4 * j + i)) & 1u, clo, chi, magic, p);
-            w[j] = pack4(q[0], q[1], q[2], q[3]);
-        }
-        int8_t* dst = dst0 + (long)t * plane_stride;
+        for (int j = 0; j < 4; ++j)
+            w[j] = pack4(residue_of(lo[4 * j], hi[4 * j], clo, chi, init, magic, p), residue_of(lo[4 * j + 1], hi[4 * j + 1], clo, chi, init, magic, p),
+                         residue_of(lo[4 * j + 2], hi[4 * j + 2], clo, chi, init, magic, p), residue_of(lo[4 * j + 3], hi[4 * j + 3], clo, chi, init, magic, p));
+        uint8_t* dst = dst0 + (long)t * plane_stride;
         if (vec) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        else for (int i = 0; i < 16 && c + i < ldp; ++i) dst[i] = (int8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xff);
+        else for (int i = 0; i < 16 && c + i < ldp; ++i) dst[i] = (uint8_t)((w[i >> 2] >> (8 * (i & 3))) & 0xff);
+    }
+}
+template <int DUMMY = 0>
+__device__ __forceinline__ void emit_residues_rt(int T, const long long (&xi)[16], const CrtTable& tab, long r, long rows, int c, int cols,
+                                                 uint8_t* __restrict__ planes, long ldp, long plane_stride) {
+    if (T == 15) emit_residues<15>(xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
+    else if (T == 16) emit_residues<16>(xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
+    else {                                           // any other count (tests): emit in two compile-time chunks
+        if (T >= 8) emit_residues<8>(xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
+        CrtTable rest = tab;
+        const int base = T >= 8 ? 8 : 0;
+        for (int t = base; t < T; ++t) {
+            rest.clo[0] = tab.clo[t]; rest.chi[0] = tab.chi[t]; rest.magic[0] = tab.magic[t]; rest.init[0] = tab.init[t]; rest.p[0] = tab.p[t];
+            emit_residues<1>(xi, rest, r, rows, c, cols, planes + (long)t * plane_stride, ldp, plane_stride);
+        }
     }
 }
 
@@ -209,9 +220,9 @@ __device__ __forceinline__ void emit_residues(const long long (&xi)[16], const C
 // feeds one contraction scaled per row and one scaled per column, and is read once.
 __global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ src, long ld, long rows, int cols,
                                                      int scale_mode, const int* __restrict__ exps, int bits, CrtTable tab,
-                                                     int8_t* __restrict__ planes, long ldp, long plane_stride,
+                                                     uint8_t* __restrict__ planes, long ldp, long plane_stride,
                                                      int scale_mode2, const int* __restrict__ exps2, int bits2, int T2,
-                                                     int8_t* __restrict__ planes2, long ldp2, long plane_stride2) {
+                                                     uint8_t* __restrict__ planes2, long ldp2, long plane_stride2) {
     const long r = (long)blockIdx.y * RS_TR + (threadIdx.x >> 3);
     const int c = blockIdx.x * RS_TC + (threadIdx.x & 7) * 16;
     double x[16];
@@ -223,16 +234,14 @@ __global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ 
         const int e = scale_mode == 0 ? (r < rows ? exps[r] : 0) : (scale_mode == 1 ? (c + i < cols ? exps[c + i] : 0) : exps[0]);
         xi[i] = __double2ll_rn(mul_pow2(x[i], bits - e));
     }
-    emit_residues(xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
+    emit_residues_rt(tab.T, xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
     if (planes2) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = scale_mode2 == 0 ? (r < rows ? exps2[r] : 0) : (scale_mode2 == 1 ? (c + i < cols ? exps2[c + i] : 0) : exps2[0]);
             xi[i] = __double2ll_rn(mul_pow2(x[i], bits2 - e));
         }
-        CrtTable tab2 = tab;
-        tab2.T = T2;                                  // the moduli of a shorter table are a prefix of the longer one
-        emit_residues(xi, tab2, r, rows, c, cols, planes2, ldp2, plane_stride2);
+        emit_residues_rt(T2, xi, tab, r, rows, c, cols, planes2, ldp2, plane_stride2);      // moduli of a shorter table: a prefix
     }
 }
 
@@ -244,7 +253,7 @@ template <int MAXD>
 __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__ X, const double* __restrict__ Zs,
                                                       const double* __restrict__ ls, const double* __restrict__ os, long R, int M, int D,
                                                       double* __restrict__ Kout, long ldk_out, const int* __restrict__ kexp, int bits,
-                                                      CrtTable tab, int8_t* __restrict__ planes, long ldp, long plane_stride) {
+                                                      CrtTable tab, uint8_t* __restrict__ planes, long ldp, long plane_stride) {
     __shared__ __align__(16) double zs[RS_TC][MAXD];
     const long r0 = (long)blockIdx.y * RS_TR;
     const int c0 = blockIdx.x * RS_TC;
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
         }
         xi[i] = __double2ll_rn(mul_pow2(val, sh));
     }
-    emit_residues(xi, tab, r, R, c0 + tcb, M, planes, ldp, plane_stride);
+    emit_residues_rt(tab.T, xi, tab, r, R, c0 + tcb, M, planes, ldp, plane_stride);
 }
 
 // ---- step 3: the int8 GEMMs ------------------------------------------------------------------------------------------
@@ -286,7 +295,7 @@ struct Params {
     int mn_major;                    // bit 0: A planes, bit 1: B planes are stored [t][k][m] (MN-major) instead of [t][m][k] (K-major):
                                      // the tensor core reads the transposed tile straight from shared memory, so a contraction
                                      // over the ROWS of row-major planes needs no transposed copy
-    int8_t* C; long ldc, plane_stride_c;       // residue planes of the result [t][m][n]
+    uint8_t* C; long ldc, plane_stride_c;       // residue planes of the result [t][m][n]
     int p[MAX_T]; uint32_t magic[MAX_T];
 };
 
@@ -298,9 +307,9 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-// kind::i8: signed 8-bit A and B, S32 accumulate, M = 128, N = BN; bits 15 / 16: A / B operand is MN-major
+// kind::i8: UNSIGNED 8-bit A and B (format 0), S32 accumulate, M = 128, N = BN; bits 15 / 16: A / B operand is MN-major
 __device__ __forceinline__ uint32_t make_idesc_i8(int mn_major) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
            ((mn_major & 1) ? (1u << 15) : 0u) | ((mn_major & 2) ? (1u << 16) : 0u);
 }
 // MN-major, 128-byte swizzle: a tile is BK k-rows of 128 bytes (128 consecutive m); 8 k-rows = 1024 B apart (SBO); for the
@@ -315,21 +324,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(tc::smem_u32(dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-// acc mod p as a value in [-128, 127] congruent to acc: Barrett with magic = ceil(2^32 / p) = (2^32 + d) / p, 0 <= d < p.
-// __mulhi floors acc / p + acc d / (p 2^32), whose second term is below |acc| / 2^32 in magnitude:
-//   SMALL (|acc| <= 2^24, reductions up to 1024): the term is below 1 / p, q is exact for acc >= 0 and at most one too small for
-//         acc < 0 when p | acc  =>  r = acc - q p in [0, p], and the centring step maps r = p to 0;
-//   otherwise (|acc| < 2^31): q is off by at most one either way  =>  r in [-p, 2p), two more conditional corrections.
-template <bool SMALL>
-__device__ __forceinline__ int mod_centered(int acc, int p, uint32_t magic) {
-    const int q = __mulhi(acc, (int)magic);
-    int r = acc - q * p;
-    if (!SMALL) {
-        r = r < 0 ? r + p : r;
-        r = r >= p ? r - p : r;
-    }
-    r = r > 127 ? r - p : r;
-    return r;
+// acc mod p in [0, p) for a non-negative accumulator (u8 x u8 products): Barrett with magic = ceil(2^32 / p) = (2^32 + d) / p,
+// 0 <= d < p.  umulhi floors acc / p + acc d / (p 2^32), whose second term is in [0, 1/2) for acc < 2^31: the quotient is exact or
+// one too large, r = acc - q p lands in [-p, p), one conditional addition fixes it.
+__device__ __forceinline__ uint32_t mod_p(uint32_t acc, uint32_t p, uint32_t magic) {
+    const int r = (int)(acc - __umulhi(acc, magic) * p);
+    return (uint32_t)(r < 0 ? r + (int)p : r);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -434,19 +434,17 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     } else {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        const bool small_acc = (long)p.K * 16384 <= 16777216;        // |acc| <= K * 2^14 <= 2^24
         int buf = 0; uint32_t bphase = 0;
         for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
             int t, m0, n0, kb, ke;
             if (!decode(w, t, m0, n0, kb, ke)) continue;
-            const int pm = p.p[t];
-            const uint32_t ip = p.magic[t];
+            const uint32_t pm = (uint32_t)p.p[t], ip = p.magic[t];
             mbar_wait(&tfull[buf], bphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
             const int row = m0 + q * 32 + lane;
             const int nbase = n0 + half * 128;
-            int8_t* dst = p.C + (long)t * p.plane_stride_c + (long)row * p.ldc + nbase;
+            uint8_t* dst = p.C + (long)t * p.plane_stride_c + (long)row * p.ldc + nbase;
 #pragma unroll
             for (int c = 0; c < 128; c += 32) {
                 uint32_t r[32];
@@ -461,23 +459,15 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     : "r"(taddr + (uint32_t)c));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 uint32_t packed[8];
-                if (small_acc) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        packed[i] = pack4(mod_centered<true>((int)r[4 * i], pm, ip), mod_centered<true>((int)r[4 * i + 1], pm, ip),
-                                          mod_centered<true>((int)r[4 * i + 2], pm, ip), mod_centered<true>((int)r[4 * i + 3], pm, ip));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        packed[i] = pack4(mod_centered<false>((int)r[4 * i], pm, ip), mod_centered<false>((int)r[4 * i + 1], pm, ip),
-                                          mod_centered<false>((int)r[4 * i + 2], pm, ip), mod_centered<false>((int)r[4 * i + 3], pm, ip));
-                }
+                for (int i = 0; i < 8; ++i)
+                    packed[i] = pack4(mod_p(r[4 * i], pm, ip), mod_p(r[4 * i + 1], pm, ip), mod_p(r[4 * i + 2], pm, ip), mod_p(r[4 * i + 3], pm, ip));
                 if (row < p.Mrows) {
                     if (nbase + c + 32 <= p.ldc) {
                         *reinterpret_cast<uint4*>(dst + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                         *reinterpret_cast<uint4*>(dst + c + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                     } else {
-                        for (int i = 0; i < 32 && nbase + c + i < p.ldc; ++i) dst[c + i] = (int8_t)((packed[i >> 2] >> (8 * (i & 3))) & 0xff);
+                        for (int i = 0; i < 32 && nbase + c + i < p.ldc; ++i) dst[c + i] = (uint8_t)((packed[i >> 2] >> (8 * (i & 3))) & 0xff);
                     }
                 }
             }
@@ -502,7 +492,7 @@ struct PlaneMapCache {
     static constexpr int N = 32;
     PlaneMapKey key[N]; CUtensorMap map[N]; int used = 0, next = 0;
 };
-inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long cols, long ld, long plane_stride, int T, int box_rows,
+inline int make_plane_map(CUtensorMap* map, const uint8_t* base, long rows, long cols, long ld, long plane_stride, int T, int box_rows,
                           int box_cols = BK) {
     static PlaneMapCache cache;
     for (int i = 0; i < cache.used; ++i) {
@@ -521,7 +511,7 @@ inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long 
     cuuint64_t gstr[2] = {(cuuint64_t)ld, (cuuint64_t)plane_stride};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(-102, "cuTensorMapEncodeTiled (residue planes) failed");
@@ -533,11 +523,11 @@ inline int make_plane_map(CUtensorMap* map, const int8_t* base, long rows, long 
 
 // K-major: rows = operand rows (m or n), cols = reduction length.  MN-major (Params.mn_major): the planes are stored
 // [t][k][m]: rows = reduction length, cols = operand rows.
-struct Planes { const int8_t* base; long rows, cols, ld, plane_stride; };
+struct Planes { const uint8_t* base; long rows, cols, ld, plane_stride; };
 
 inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t st) {
     if (p.Mrows <= 0 || p.Ncols <= 0 || p.K <= 0) return 0;
-    if ((long)p.K * 16384 >= 2147483648L) return set_error(-3, "int8 reduction too long for exact s32 accumulation (K < 131072)");
+    if ((long)p.K * 65025 >= 2147483648L) return set_error(-3, "u8 reduction too long for exact s32 accumulation (K <= 33025)");
     CUtensorMap mA, mB;
     // MN-major boxes: 128 operand rows (contiguous bytes) x BK reduction rows
     if (p.mn_major & 1) TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BK, 128));
@@ -559,23 +549,21 @@ inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t 
 
 // ---- step 4 + 5: CRT reconstruction -----------------------------------------------------------------------------------
 // value of sum_t r_t w_t mod P (centred) for the residues packed in byte `i` of w[t], as a double (relative error <= 3 * 2^-53).
-// The multiple of P is m = rint(total / P) with total = ((S3 2^40 + S2) 2^40 + S1) 2^40 + S0 evaluated in FP64: |m| <= 2^11, so
-// its rounding error is ~2^-42, far inside the margin the bit budget leaves between |C'| / P and 1/2.
+// r_t in [0, 255], T <= 16 terms, words < 2^40: every partial sum stays below 2^52 and is exact.  The multiple of P is
+// m = rint(total / P) with total = ((S3 2^40 + S2) 2^40 + S1) 2^40 + S0 evaluated in FP64: m <= 2^12, so its rounding error is
+// ~2^-41, far inside the margin the bit budget leaves between |C'| / P and 1/2.
+template <int T>
 __device__ __forceinline__ double crt_value(const uint32_t* w, int i, const CrtTable& tab) {
     double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0;
-    const uint32_t sel = (uint32_t)i | ((8u | (uint32_t)i) << 4) | ((8u | (uint32_t)i) << 8) | ((8u | (uint32_t)i) << 12);
+    const uint32_t sel = 0x4440u | (uint32_t)i;                                        // byte i, zero-extended
 #pragma unroll
-    for (int t = 0; t < MAX_T; ++t) {
-        if (t < tab.T) {
-            int r;                                                                     // sign-extended byte i (prmt: selector
-            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w[t]), "r"(0u), "r"(sel));   // msb = replicate the byte's sign)
-            // int -> double without a conversion instruction: (2^52 + 2^31 + r) - (2^52 + 2^31)
-            const double rt = __hiloint2double(0x43300000, r ^ 0x80000000) - 4503601774854144.0;
-            S0 = fma(rt, tab.w[t][0], S0);
-            S1 = fma(rt, tab.w[t][1], S1);
-            S2 = fma(rt, tab.w[t][2], S2);
-            S3 = fma(rt, tab.w[t][3], S3);
-        }
+    for (int t = 0; t < T; ++t) {
+        const uint32_t r = __byte_perm(w[t], 0u, sel);
+        const double rt = __hiloint2double(0x43300000, (int)r) - 4503599627370496.0;   // (2^52 + r) - 2^52: no conversion instruction
+        S0 = fma(rt, tab.w[t][0], S0);
+        S1 = fma(rt, tab.w[t][1], S1);
+        S2 = fma(rt, tab.w[t][2], S2);
+        S3 = fma(rt, tab.w[t][3], S3);
     }
     const double two = 1099511627776.0, inv = 9.094947017729282e-13;       // 2^40, 2^-40
     const double m = rint(fma(fma(fma(S3, two, S2), two, S1), two, S0) * tab.invP);
@@ -589,30 +577,57 @@ __device__ __forceinline__ double crt_value(const uint32_t* w, int i, const CrtT
 // stats (forward only; cols = 2 * stat_M, row = [a | b]): mu[r] = sum_{c < M} out * m[c], v[r] = os - sum_{c<M} out^2 +
 // sum_{c>=M} out^2 — the q(f) marginals come out of the reconstruction pass, [A | B] is not re-read for them
 struct RowStats { const double* m; const double* os; double* mu; double* v; int M; };
-__global__ void __launch_bounds__(256) k_crt_combine(const int8_t* __restrict__ R, long ldr, long plane_stride, long rows, int cols,
-                                                     CrtTable tab, int bits2, const int* __restrict__ ea, int ea_mode,
+
+// R planes [t][rows][ldr] -> out[r * ldo + c] = (or +=) crt * 2^(ea + eb - bits2)
+//   ea: row exponents (ea_mode 0) / one exponent ea[0] (ea_mode 2);  eb: per-column exponents (eb_mode 1) / eb[0] (2)
+//   accumulate = 1: FP64 atomicAdd (weight gradients summed over row chunks); lower_rows > 0: rows r < lower_rows only c <= r
+// one warp per row, four consecutive columns per lane per step
+template <int T>
+__global__ void __launch_bounds__(256) k_crt_combine(const uint8_t* __restrict__ R, long ldr, long plane_stride, long rows, int cols,
+                                                     const __grid_constant__ CrtTable tab, int bits2, const int* __restrict__ ea, int ea_mode,
                                                      const int* __restrict__ eb, int eb_mode, double* __restrict__ out, long ldo,
                                                      int accumulate, int lower_rows, RowStats st) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (long r = (long)blockIdx.x * wpb + wid; r < rows; r += (long)gridDim.x * wpb) {
-        const int era = ea_mode == 0 ? ea[r] : ea[0];
+        const int era = (ea_mode == 0 ? ea[r] : ea[0]) - bits2;
         const int climit = (lower_rows > 0 && r < lower_rows) ? (int)min((long)cols, r + 1) : cols;
         double sm = 0.0, sa = 0.0, sb = 0.0;
         for (int c0 = lane * 4; c0 < climit; c0 += 128) {
-            uint32_t w[MAX_T];
+            uint32_t w[T];
 #pragma unroll
-            for (int t = 0; t < MAX_T; ++t)
-                w[t] = t < tab.T ? *reinterpret_cast<const uint32_t*>(R + (long)t * plane_stride + r * ldr + c0) : 0u;
+            for (int t = 0; t < T; ++t) w[t] = *reinterpret_cast<const uint32_t*>(R + (long)t * plane_stride + r * ldr + c0);
+            int e4[4];
+            if (eb_mode == 1) {
+                if (c0 + 4 <= cols && ((reinterpret_cast<uintptr_t>(eb + c0) & 15) == 0)) {
+                    const int4 e = *reinterpret_cast<const int4*>(eb + c0);
+                    e4[0] = e.x; e4[1] = e.y; e4[2] = e.z; e4[3] = e.w;
+                } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = c0 + i;
-                if (c >= climit) break;
-                const double v = mul_pow2(crt_value(w, i, tab), era + (eb_mode == 1 ? eb[c] : eb[0]) - bits2);
-                if (accumulate) atomicAdd(out + r * ldo + c, v);
-                else out[r * ldo + c] = v;
-                if (st.mu) {
-                    if (c < st.M) { sm = fma(v, __ldg(st.m + c), sm); sa = fma(v, v, sa); }
-                    else sb = fma(v, v, sb);
+                    for (int i = 0; i < 4; ++i) e4[i] = c0 + i < cols ? eb[c0 + i] : 0;
+                }
+            } else {
+                e4[0] = e4[1] = e4[2] = e4[3] = eb[0];
+            }
+            double v4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v4[i] = mul_pow2(crt_value<T>(w, i, tab), era + e4[i]);
+            double* o = out + r * ldo + c0;
+            if (!accumulate && c0 + 4 <= climit && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                *reinterpret_cast<double2*>(o) = make_double2(v4[0], v4[1]);
+                *reinterpret_cast<double2*>(o + 2) = make_double2(v4[2], v4[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c0 + i < climit) { if (accumulate) atomicAdd(o + i, v4[i]); else o[i] = v4[i]; }
+            }
+            if (st.mu) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = c0 + i;
+                    if (c < climit) {
+                        if (c < st.M) { sm = fma(v4[i], __ldg(st.m + c), sm); sa = fma(v4[i], v4[i], sa); }
+                        else sb = fma(v4[i], v4[i], sb);
+                    }
                 }
             }
         }

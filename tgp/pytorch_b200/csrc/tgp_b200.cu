@@ -637,7 +637,7 @@ size_t tgp_debug_gemm_crt_bytes(long M, long N, long K, int T) { return crt::deb
 
 int tgp_debug_gemm_crt(long M, long N, long K, const double* A, long lda, const double* B, long ldb, double* C, long ldc, int T,
                        int tri_mode, int tri_rows, int lower_rows, int accumulate, int mn_major, void* scratch, void* stream) {
-    if (T < 1 || T > i8::MAX_T) return set_error(-1, "T must be in 1..16");
+    if (T != 9 && T != 12 && T != 15 && T != 16) return set_error(-1, "T must be 9, 12, 15 or 16");
     if (!A || !B || !C || !scratch) return set_error(-1, "NULL argument to tgp_debug_gemm_crt");
     return crt::debug_matmul(M, N, K, A, lda, B, ldb, C, ldc, T, tri_mode, tri_rows, lower_rows, accumulate, mn_major, scratch,
                              (cudaStream_t)stream);
