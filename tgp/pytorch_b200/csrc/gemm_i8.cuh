@@ -324,6 +324,27 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(tc::smem_u32(dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// multicast variants: the tile lands at the same shared-memory offset of every CTA in `mask`, and completes tx bytes on the
+// mbarrier at the same offset of each of them
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(tc::smem_u32(dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // acc mod p in [0, p) for a non-negative accumulator (u8 x u8 products): Barrett with magic = ceil(2^32 / p) = (2^32 + d) / p,
 // 0 <= d < p.  umulhi floors acc / p + acc d / (p 2^32), whose second term is in [0, 1/2) for acc < 2^31: the quotient is exact or
 // one too large, r = acc - q p lands in [-p, p), one conditional addition fixes it.
@@ -332,7 +353,12 @@ __device__ __forceinline__ uint32_t mod_p(uint32_t acc, uint32_t p, uint32_t mag
     return (uint32_t)(r < 0 ? r + (int)p : r);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// Launched as clusters of TWO CTAs that own vertically adjacent 128-row tiles of the same (modulus, n-tile): the B tile is the
+// same for both, so each CTA fetches one 128-row half of it and MULTICASTS it into both shared memories (L2 -> SM traffic per
+// CTA and k-block: 16 KiB of A + 16 KiB of B instead of 16 + 32; the single-CTA version was L2-bound at ~10 TB/s).  A stage
+// may be refilled only when BOTH consumers have released it: the MMA issuer's tcgen05.commit arrives on the `empty` barrier of
+// both CTAs (count 2).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
@@ -344,11 +370,14 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
     const int tiles_m = (p.Mrows + BM - 1) / BM, tiles_n = (p.Ncols + BN - 1) / BN;
-    const long n_work = (long)p.T * tiles_m * tiles_n;
+    const int pairs_m = (tiles_m + 1) >> 1;
+    const long n_work = (long)p.T * pairs_m * tiles_n;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -358,17 +387,21 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();              // the peer's barriers are initialised before anything is multicast into this CTA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // work item -> (modulus t, m-tile, n-tile, k-range); n fastest (the A row block is shared by consecutive CTAs),
-    // modulus slowest (one modulus' planes of both operands fit the L2)
+    // work item (cluster-wide) -> (modulus t, pair of m-tiles, n-tile, k-range); this CTA's m-tile is 2 * pair + rank.  n fastest
+    // (the A row blocks are shared by consecutive clusters), modulus slowest (one modulus' planes of both operands fit the L2).
+    // Both CTAs of a cluster run the same sequence with the same k-range, so their pipelines stay in step.
     auto decode = [&](long w, int& t, int& m0, int& n0, int& kb, int& ke) -> bool {
         n0 = (int)(w % tiles_n) * BN;
         const long r = w / tiles_n;
-        m0 = (int)(r % tiles_m) * BM;
-        t = (int)(r / tiles_m);
-        if (p.lower_rows > 0 && m0 < p.lower_rows && n0 > m0 + BM - 1) return false;
+        const int mp = (int)(r % pairs_m);
+        m0 = (2 * mp + rank) * BM;
+        t = (int)(r / pairs_m);
+        const int m_hi = (2 * mp + 1) * BM;                    // the lower tile of the pair
+        if (p.lower_rows > 0 && m_hi < p.lower_rows && n0 > m_hi + BM - 1) return false;       // both tiles strictly above the diagonal
         kb = 0; ke = p.K;
         if (p.tri_mode == 1 && n0 < p.tri_rows) ke = min(p.K, n0 + BN);
         if (p.tri_mode == 2 && n0 < p.tri_rows) kb = (n0 / BK) * BK;
@@ -378,22 +411,20 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            uint8_t* const bhalf_off = reinterpret_cast<uint8_t*>((uintptr_t)(A_BYTES + rank * (B_BYTES / 2)));
+            for (long w = cluster_id; w < n_work; w += n_clusters) {
                 int t, m0, n0, kb, ke;
                 if (!decode(w, t, m0, n0, kb, ke)) continue;
                 for (int k = kb; k < ke; k += BK) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);          // own A + both halves of B
                     // MN-major planes [t][k][m]: boxes of 128 m-bytes x BK k-rows; K-major [t][m][k]: BK k-bytes x rows
                     if (p.mn_major & 1) tma_load_3d(st, &mapA, &full[stage], m0, k, t);
                     else tma_load_3d(st, &mapA, &full[stage], k, m0, t);
-                    if (p.mn_major & 2) {
-                        tma_load_3d(st + A_BYTES, &mapB, &full[stage], n0, k, t);
-                        tma_load_3d(st + 2 * A_BYTES, &mapB, &full[stage], n0 + 128, k, t);
-                    } else {
-                        tma_load_3d(st + A_BYTES, &mapB, &full[stage], k, n0, t);
-                    }
+                    uint8_t* bdst = st + (uintptr_t)bhalf_off;           // this CTA's 128-row half of the B tile, for both CTAs
+                    if (p.mn_major & 2) tma_load_3d_mc(bdst, &mapB, &full[stage], n0 + 128 * rank, k, t, (uint16_t)3);
+                    else tma_load_3d_mc(bdst, &mapB, &full[stage], k, n0 + 128 * rank, t, (uint16_t)3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -403,7 +434,7 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             const uint32_t idesc = make_idesc_i8(p.mn_major);
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t bphase = 0;
-            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            for (long w = cluster_id; w < n_work; w += n_clusters) {
                 int t, m0, n0, kb, ke;
                 if (!decode(w, t, m0, n0, kb, ke)) continue;
                 mbar_wait(&tempty[buf], bphase ^ 1);
@@ -424,7 +455,7 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                         umma_i8(tmem_d, dA + kk * sA, dB + kk * sB, idesc, accum);
                         accum = 1;
                     }
-                    umma_commit(&empty[stage]);
+                    umma_commit_mc(&empty[stage], (uint16_t)3);       // releases the stage in BOTH CTAs when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[buf]);
@@ -435,7 +466,7 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         int buf = 0; uint32_t bphase = 0;
-        for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+        for (long w = cluster_id; w < n_work; w += n_clusters) {
             int t, m0, n0, kb, ke;
             if (!decode(w, t, m0, n0, kb, ke)) continue;
             const uint32_t pm = (uint32_t)p.p[t], ip = p.magic[t];
@@ -444,6 +475,8 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             const uint32_t taddr = tmem_base + (uint32_t)buf * BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
             const int row = m0 + q * 32 + lane;
             const int nbase = n0 + half * 128;
+            // this CTA's tile may lie strictly above the diagonal (its pair partner does not) or below the last row: nothing to store
+            const bool store = row < p.Mrows && !(p.lower_rows > 0 && m0 < p.lower_rows && n0 > m0 + BM - 1);
             uint8_t* dst = p.C + (long)t * p.plane_stride_c + (long)row * p.ldc + nbase;
 #pragma unroll
             for (int c = 0; c < 128; c += 32) {
@@ -458,11 +491,11 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr + (uint32_t)c));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint32_t packed[8];
+                if (store) {
+                    uint32_t packed[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    packed[i] = pack4(mod_p(r[4 * i], pm, ip), mod_p(r[4 * i + 1], pm, ip), mod_p(r[4 * i + 2], pm, ip), mod_p(r[4 * i + 3], pm, ip));
-                if (row < p.Mrows) {
+                    for (int i = 0; i < 8; ++i)
+                        packed[i] = pack4(mod_p(r[4 * i], pm, ip), mod_p(r[4 * i + 1], pm, ip), mod_p(r[4 * i + 2], pm, ip), mod_p(r[4 * i + 3], pm, ip));
                     if (nbase + c + 32 <= p.ldc) {
                         *reinterpret_cast<uint4*>(dst + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                         *reinterpret_cast<uint4*>(dst + c + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
@@ -480,6 +513,7 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();              // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -533,13 +567,13 @@ inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t 
     if (p.mn_major & 1) TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BK, 128));
     else TGP_TRY(make_plane_map(&mA, A.base, A.rows, A.cols, A.ld, A.plane_stride, p.T, BM));
     if (p.mn_major & 2) TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BK, 128));
-    else TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BN));
+    else TGP_TRY(make_plane_map(&mB, B.base, B.rows, B.cols, B.ld, B.plane_stride, p.T, BN / 2));      // each CTA loads one half
     const CrtTable& tab = crt_table(p.T);
     for (int t = 0; t < p.T; ++t) { p.p[t] = tab.p[t]; p.magic[t] = tab.magic[t]; }
     static PerDeviceOnce attr_once;
     if (attr_once.first()) cudaFuncSetAttribute(gemm_i8_mod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    const long tiles = (long)cdiv(p.Mrows, BM) * cdiv(p.Ncols, BN) * p.T;
-    const int grid = (int)(tiles < 148 ? tiles : 148);
+    const long pairs = (long)((cdiv(p.Mrows, BM) + 1) / 2) * cdiv(p.Ncols, BN) * p.T;        // cluster-wide work items
+    const int grid = 2 * (int)(pairs < 74 ? pairs : 74);
     const bool timed = g_gemm_timer.enabled;
     if (timed) g_gemm_timer.begin(2, st);
     gemm_i8_mod_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB, p);
