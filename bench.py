@@ -265,6 +265,8 @@ def run_ours(args):
     from tgp.pytorch_b200 import _lib, functional as Fn
     from tgp.pytorch_b200.dist import local_slice
     lib = _lib.load()
+    if args.no_overlap:
+        lib.tgp_set_option(_lib.OPT_OVERLAP_KGEN, 0)
     wl = WORKLOADS[args.workload]
     N_DATA, D, M = wl['N'], wl['D'], wl['M']
     BATCH = wl['batch'] if args.scaling == 'weak' else wl['batch'] // world      # rows per GPU per step
@@ -507,6 +509,7 @@ def run_e2e(args, wl, p, X, Y, perm, rank, world, dev, BATCH):
     cg.set_maximum_precission()
     cg.device = str(dev)
     cg.sync_elbo_in_forward = False            # one collective per step; the global ELBO is read after backward
+    cg.compute = args.compute                  # the class API runs the headline compute mode
     from tgp.pytorch_b200.dsp.models import instance_kernel, sparse_MF_SP
     from tgp.pytorch_b200.dsp.models.flow import instance_flow
     from tgp.pytorch_b200.dsp.likelihoods import GaussianNonLinearMean, Bernoulli
@@ -596,6 +599,7 @@ def main():
     ap.add_argument('--no-other-mode', action='store_true', help='measure only the headline compute mode')
     ap.add_argument('--no-gemm-timing', action='store_true', help='(diagnostic) do not instrument GEMM launches with events')
     ap.add_argument('--no-clocks', action='store_true', help='(diagnostic) do not sample nvidia-smi during the timed region')
+    ap.add_argument('--no-overlap', action='store_true', help='(diagnostic) K_xz generation on the main stream (TGP_OPT_OVERLAP_KGEN = 0)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -205,7 +205,10 @@ int tgp_test_nll_fwd(TgpHandle* h, const TgpParams* params, const TgpBatch* batc
  * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels.
  * TGP_OPT_ROW_CHUNK (FP64 mode): rows per launch of the batch contractions (default 32768; a tuning knob — it changes the
  * workspace size, so set it before asking for tgp_batch_workspace_bytes). */
-enum { TGP_OPT_FUSED_FORWARD = 1, TGP_OPT_ROW_CHUNK = 2 };
+enum { TGP_OPT_FUSED_FORWARD = 1, TGP_OPT_ROW_CHUNK = 2,
+       TGP_OPT_OVERLAP_KGEN = 3 };   /* 1 (default): K_xz generation runs on a library-owned side stream concurrently with the
+                                      * factorisation of tgp_prepare (fork at its parameter transforms, join before the first
+                                      * contraction); 0: everything on the caller's stream */
 int tgp_set_option(int key, int value);
 
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */

@@ -15,6 +15,7 @@ FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
 MAX_LAYERS = 64
 OPT_FUSED_FORWARD = 1
 OPT_ROW_CHUNK = 2
+OPT_OVERLAP_KGEN = 3
 
 
 class TgpFlowLayer(C.Structure):

@@ -31,6 +31,38 @@ inline int check_launch(const char* what) {
 
 #define TGP_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
 
+// A library-owned side stream per device, used to run K_xz generation concurrently with the (single-SM-bound) factorisation:
+// tgp_prepare records `params_ready` right after the parameter transforms; tgp_qf_forward generates K_xz on the side stream
+// as soon as that event fires and joins back with `k_ready`.  Host objects only (no device memory).  `capturing` remembers
+// whether the prepare was enqueued under CUDA-graph capture: fork and join must belong to the same capture.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t params_ready = nullptr, k_ready = nullptr;
+    bool have_params = false, capturing = false;
+    bool fresh = false;          // set by tgp_prepare, consumed by the FIRST forward after it: a later forward on the same
+                                 // factorisation may follow work that still reads the batch workspace, and stays on the main stream
+};
+inline SideStream& side_stream() {
+    static SideStream s[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream& x = s[dev >= 0 && dev < 64 ? dev : 0];
+    if (!x.stream) {
+        int lo = 0, hi = 0;          // lowest priority: the factorisation's small kernels are never queued behind K_xz tiles
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&x.stream, cudaStreamNonBlocking, lo);
+        cudaEventCreateWithFlags(&x.params_ready, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&x.k_ready, cudaEventDisableTiming);
+    }
+    return x;
+}
+inline bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs != cudaStreamCaptureStatusNone;
+}
+extern int g_overlap_kgen;       // TGP_OPT_OVERLAP_KGEN
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

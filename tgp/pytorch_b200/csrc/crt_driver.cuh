@@ -154,10 +154,10 @@ inline int combine(const uint8_t* R, long ldr, long plane_stride, long rows, int
 
 // K_xz of a row chunk in one pass: FP64 values and residue planes (i8::k_rbf_residues)
 inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
-                        const int* kexp, int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st) {
+                        int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st) {
     dim3 grid((unsigned)cdiv(M, i8::RS_TC), (unsigned)cdiv(R, i8::RS_TR));
     const i8::CrtTable& tab = i8::crt_table(T);
-#define TGP_RR(MD) i8::k_rbf_residues<MD><<<grid, 256, 0, st>>>(X, Zs, ls, os, R, M, D, Kout, M, kexp, 53, tab, planes, ldp, plane_stride)
+#define TGP_RR(MD) i8::k_rbf_residues<MD><<<grid, 256, 0, st>>>(X, Zs, ls, os, R, M, D, Kout, M, 53, tab, planes, ldp, plane_stride)
     if (D <= 4) TGP_RR(4);
     else if (D <= 8) TGP_RR(8);
     else if (D <= 16) TGP_RR(16);
@@ -226,15 +226,33 @@ inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, cons
     StepPlanes sp = carve_step(step_region, M);
     BatchView b = carve_batch(batch_ws, M, R);
     const int Tf = fwd_T(M), bits = fwd_bits_w(M);
+    // K_xz (FP64 values + residue planes) of every chunk.  It depends on Zs / ls / os only, not on the factorisation, so it is
+    // enqueued on the library's side stream behind tgp_prepare's `params_ready` event and runs UNDER the factorisation (which
+    // keeps a single SM busy for ~1 ms); the main stream joins before the first contraction.
+    SideStream& ss = side_stream();
+    const bool overlap = g_overlap_kgen && ss.have_params && ss.fresh && D <= 32 && ss.capturing == stream_is_capturing(st);
+    ss.fresh = false;
+    cudaStream_t kst = st;
+    if (overlap) {
+        if (cudaStreamWaitEvent(ss.stream, ss.params_ready, 0) == cudaSuccess) kst = ss.stream;
+        else cudaGetLastError();
+    }
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         double* Kc = b.Kbuf + r0 * M;
         // K residues: one scale for the whole matrix (0 <= k <= outputscale), shared by the forward and the weight contraction
-        const int rr = rbf_residues(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, Kc, sp.k_exp, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, st);
+        const int rr = rbf_residues(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, Kc, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, kst);
         if (rr == -7) {
             TGP_TRY(launch_rbf(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
             TGP_TRY(to_residues(Kc, M, rc, M, 2, sp.k_exp, 53, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, st));
         } else if (rr != 0) return rr;
+    }
+    if (kst != st) {
+        if (cudaEventRecord(ss.k_ready, kst) != cudaSuccess || cudaStreamWaitEvent(st, ss.k_ready, 0) != cudaSuccess)
+            return set_error(-100, "side-stream join failed");
+    }
+    for (long r0 = 0; r0 < R; r0 += b.Rc) {
+        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         i8::Params p{};
         p.Mrows = rc; p.Ncols = 2 * M; p.K = M; p.T = Tf; p.tri_mode = 1; p.tri_rows = M; p.lower_rows = 0; p.mn_major = 0;
         p.C = b.Op; p.ldc = b.ld2m; p.plane_stride_c = (long)b.Rc * b.ld2m;

@@ -248,11 +248,12 @@ __global__ void __launch_bounds__(256) k_to_residues(const double* __restrict__ 
 // ARD-RBF K tile generated in registers (same arithmetic as k_rbf_tile_reg: x / ls differences, FMA chain, FP64 exp) and
 // converted on the spot: FP64 K (kept for the kernel gradients) and its residue planes in ONE pass.  The same planes serve
 // the forward (reduction over the inducing index: K-major) and the weight contraction (reduction over the rows: MN-major).
-// One scale for the whole matrix: 0 <= k <= outputscale < 2^kexp.
+// One scale for the whole matrix: 0 <= k <= outputscale < 2^kexp, kexp derived from the outputscale in-kernel (the kernel
+// depends on nothing the factorisation produces, so it can run on a side stream under it).
 template <int MAXD>
 __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__ X, const double* __restrict__ Zs,
                                                       const double* __restrict__ ls, const double* __restrict__ os, long R, int M, int D,
-                                                      double* __restrict__ Kout, long ldk_out, const int* __restrict__ kexp, int bits,
+                                                      double* __restrict__ Kout, long ldk_out, int bits,
                                                       CrtTable tab, uint8_t* __restrict__ planes, long ldp, long plane_stride) {
     __shared__ __align__(16) double zs[RS_TC][MAXD];
     const long r0 = (long)blockIdx.y * RS_TR;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
     for (int d = 0; d < MAXD; ++d) xr[d] = (r < R && d < D) ? X[r * D + d] / ls[d] : 0.0;
     __syncthreads();
     const double s = os[0];
-    const int sh = bits - kexp[0];
+    const int sh = bits - exp_above(s);            // the same exponent tgp_prepare stores for the reconstruction (k_exp)
     long long xi[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {

@@ -327,6 +327,13 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
         const int n = max(M * D, D);
         k_transform_params<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(Z, raw_ls, raw_os, M, D, v.ls, v.os, v.Zs);
         TGP_TRY(check_launch("k_transform_params"));
+        if (g_overlap_kgen) {          // K_xz generation of the coming forward may start from here (it needs Zs, ls, os only)
+            SideStream& ss = side_stream();
+            ss.capturing = stream_is_capturing(st);
+            ss.have_params = cudaEventRecord(ss.params_ready, st) == cudaSuccess;
+            if (!ss.have_params) cudaGetLastError();
+            ss.fresh = ss.have_params;
+        }
     }
     TGP_TRY(launch_rbf(v.Zs, v.Zs, v.ls, v.os, M, M, D, 1, v.Kzz, Mp, Mp, Mp, jitter, st));
     k_tril_kl<<<Mp, 256, 0, st>>>(Lraw, m, M, v.LS, Mp, Mp, v.kl3);

@@ -15,6 +15,7 @@ char g_last_error[512] = "";
 long g_launch_count = 0;
 GemmTimer g_gemm_timer;
 namespace tc { int g_fused_forward = 0; }
+int g_overlap_kgen = 1;
 
 long g_row_chunk = 32768;             // rows per launch of the batch contractions (Kbar / Abar staging); measured at cfg4:
                                       // 8192 -> 20.3 ms/step, 16384 -> 20.0, 32768 -> 19.6, 65536 -> 19.5
@@ -200,10 +201,25 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
                                R, (double*)mu, (double*)v, st);
     BatchView b = carve_batch(batch_ws, M, R);
     const double* Xd = (const double*)X;
+    {   // K_xz of every chunk: independent of the factorisation, generated on the side stream under it (TGP_OPT_OVERLAP_KGEN)
+        SideStream& ss = side_stream();
+        cudaStream_t kst = st;
+        const bool overlap = g_overlap_kgen && ss.have_params && ss.fresh && ss.capturing == stream_is_capturing(st);
+        ss.fresh = false;
+        if (overlap) {
+            if (cudaStreamWaitEvent(ss.stream, ss.params_ready, 0) == cudaSuccess) kst = ss.stream;
+            else cudaGetLastError();
+        }
+        for (long r0 = 0; r0 < R; r0 += b.Rc) {
+            const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
+            TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf + r0 * M, M, rc, M, 0.0, kst));
+        }
+        if (kst != st && (cudaEventRecord(ss.k_ready, kst) != cudaSuccess || cudaStreamWaitEvent(st, ss.k_ready, 0) != cudaSuccess))
+            return set_error(-100, "side-stream join failed");
+    }
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         double* Kc = b.Kbuf + r0 * M;
-        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
         // A = K L^-T   (Bop[n,k] = Linv[n,k], nonzero k <= n)
         GemmArgs ga = make_gemm(rc, M, M, Kc, M, 0, s.Linv, s.Mp, 0, b.AB + r0 * 2 * M, 2 * M);
         ga.b_tri = 1;
@@ -593,6 +609,7 @@ long tgp_launch_count(void) { return g_launch_count; }
 
 int tgp_set_option(int key, int value) {
     if (key == TGP_OPT_FUSED_FORWARD) { tc::g_fused_forward = value != 0; return 0; }
+    if (key == TGP_OPT_OVERLAP_KGEN) { g_overlap_kgen = value != 0; return 0; }
     if (key == TGP_OPT_ROW_CHUNK) {
         if (value < 128) return set_error(-1, "row chunk must be >= 128");
         g_row_chunk = value;
