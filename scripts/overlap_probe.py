@@ -24,3 +24,14 @@ for ov in (1, 0, 1, 0):
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print(mode, 'overlap', ov, 'prepare+qf_forward median %.3f ms' % sorted(ts)[len(ts) // 2])
+
+# the same without a host synchronisation between iterations (the host runs ahead of the device, as in a training loop)
+for ov in (1, 0, 1, 0):
+    lib.tgp_set_option(_lib.OPT_OVERLAP_KGEN, ov)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(20):
+        eng.prepare(0.0); eng.qf_forward(xb)
+    e1.record(); torch.cuda.synchronize()
+    print(mode, 'overlap', ov, 'async loop: %.3f ms per (prepare + qf_forward)' % (e0.elapsed_time(e1) / 20))

@@ -154,8 +154,9 @@ inline int combine(const uint8_t* R, long ldr, long plane_stride, long rows, int
 
 // K_xz of a row chunk in one pass: FP64 values and residue planes (i8::k_rbf_residues)
 inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
-                        int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st) {
-    dim3 grid((unsigned)cdiv(M, i8::RS_TC), (unsigned)cdiv(R, i8::RS_TR));
+                        int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st, int ctas_per_sm = 3) {
+    const long n_tiles = cdiv(M, i8::RS_TC) * cdiv(R, i8::RS_TR);
+    const unsigned grid = (unsigned)(n_tiles < 148L * ctas_per_sm ? n_tiles : 148L * ctas_per_sm);
     const i8::CrtTable& tab = i8::crt_table(T);
 #define TGP_RR(MD) i8::k_rbf_residues<MD><<<grid, 256, 0, st>>>(X, Zs, ls, os, R, M, D, Kout, M, 53, tab, planes, ldp, plane_stride)
     if (D <= 4) TGP_RR(4);
@@ -237,14 +238,13 @@ inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, cons
         if (cudaStreamWaitEvent(ss.stream, ss.params_ready, 0) == cudaSuccess) kst = ss.stream;
         else cudaGetLastError();
     }
-    for (long r0 = 0; r0 < R; r0 += b.Rc) {
-        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
-        double* Kc = b.Kbuf + r0 * M;
-        // K residues: one scale for the whole matrix (0 <= k <= outputscale), shared by the forward and the weight contraction
-        const int rr = rbf_residues(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, Kc, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, kst);
+    {   // one launch for all rows.  K residues: one scale for the whole matrix (0 <= k <= outputscale), shared by the forward and
+        // the weight contraction
+        const int rr = rbf_residues(X, s.Zs, s.ls, s.os, R, M, D, b.Kbuf, T_ALL, b.Kp, b.ldk, R * b.ldk, kst, kst != st ? 2 : 3);
         if (rr == -7) {
-            TGP_TRY(launch_rbf(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, Kc, M, rc, M, 0.0, st));
-            TGP_TRY(to_residues(Kc, M, rc, M, 2, sp.k_exp, 53, T_ALL, b.Kp + r0 * b.ldk, b.ldk, R * b.ldk, st));
+            kst = st;
+            TGP_TRY(launch_rbf(X, s.Zs, s.ls, s.os, (int)R, M, D, 0, b.Kbuf, M, (int)R, M, 0.0, st));
+            TGP_TRY(to_residues(b.Kbuf, M, R, M, 2, sp.k_exp, 53, T_ALL, b.Kp, b.ldk, R * b.ldk, st));
         } else if (rr != 0) return rr;
     }
     if (kst != st) {

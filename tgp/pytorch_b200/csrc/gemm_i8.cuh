@@ -256,36 +256,48 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
                                                       double* __restrict__ Kout, long ldk_out, int bits,
                                                       CrtTable tab, uint8_t* __restrict__ planes, long ldp, long plane_stride) {
     __shared__ __align__(16) double zs[RS_TC][MAXD];
-    const long r0 = (long)blockIdx.y * RS_TR;
-    const int c0 = blockIdx.x * RS_TC;
     const int tid = threadIdx.x;
     const int tr = tid >> 3, tcb = (tid & 7) * 16;
-    for (int i = tid; i < RS_TC * MAXD; i += 256) {
-        const int c = i / MAXD, d = i % MAXD, j = c0 + c;
-        zs[c][d] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
-    }
-    const long r = r0 + tr;
-    double xr[MAXD];
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) xr[d] = (r < R && d < D) ? X[r * D + d] / ls[d] : 0.0;
-    __syncthreads();
     const double s = os[0];
     const int sh = bits - exp_above(s);            // the same exponent tgp_prepare stores for the reconstruction (k_exp)
-    long long xi[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int c = c0 + tcb + i;
-        double val = 0.0;
-        if (r < R && c < M) {
-            double acc = 0.0;
-#pragma unroll
-            for (int d = 0; d < MAXD; ++d) { const double df = xr[d] - zs[tcb + i][d]; acc = fma(df, df, acc); }
-            val = s * exp(-0.5 * acc);
-            if (Kout) Kout[r * ldk_out + c] = val;
+    // A bounded, persistent grid (the launcher caps it at a few CTAs per SM): when this kernel runs on the side stream under the
+    // factorisation it must leave CTA slots free, or the factorisation's small kernels would queue behind thousands of tiles.
+    // Tiles are walked column-block-major so that a CTA reloads its inducing rows rarely.
+    const long row_tiles = cdiv(R, RS_TR);
+    const long n_tiles = row_tiles * cdiv(M, RS_TC);
+    int c0_loaded = -1;
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int c0 = (int)(tile / row_tiles) * RS_TC;
+        const long r0 = (tile % row_tiles) * RS_TR;
+        if (c0 != c0_loaded) {
+            __syncthreads();
+            for (int i = tid; i < RS_TC * MAXD; i += 256) {
+                const int c = i / MAXD, d = i % MAXD, j = c0 + c;
+                zs[c][d] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
+            }
+            __syncthreads();
+            c0_loaded = c0;
         }
-        xi[i] = __double2ll_rn(mul_pow2(val, sh));
+        const long r = r0 + tr;
+        double xr[MAXD];
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) xr[d] = (r < R && d < D) ? X[r * D + d] / ls[d] : 0.0;
+        long long xi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int c = c0 + tcb + i;
+            double val = 0.0;
+            if (r < R && c < M) {
+                double acc = 0.0;
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) { const double df = xr[d] - zs[tcb + i][d]; acc = fma(df, df, acc); }
+                val = s * exp(-0.5 * acc);
+                if (Kout) Kout[r * ldk_out + c] = val;
+            }
+            xi[i] = __double2ll_rn(mul_pow2(val, sh));
+        }
+        emit_residues_rt(tab.T, xi, tab, r, R, c0 + tcb, M, planes, ldp, plane_stride);
     }
-    emit_residues_rt(tab.T, xi, tab, r, R, c0 + tcb, M, planes, ldp, plane_stride);
 }
 
 // ---- step 3: the int8 GEMMs ------------------------------------------------------------------------------------------
