@@ -3,13 +3,14 @@
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path, one process per GPU under torchrun
   python bench.py --impl reference --gpus N ...            # the reference's algorithm on the host CPU cores (oracle port)
-  options: --workload cfg4|cfg5   --scaling weak|strong   --compute f64|tf32x3
+  options: --workload cfg4|cfg5   --scaling weak|strong   --compute i8crt|f64|tf32x3
 
 Workloads:
   cfg4 (default; BASELINE.json configs[3], the configuration the metric is quoted on): TGP regression, synthetic
        N = 5 M rows, D = 8, M = 1024 inducing points, StepTanhL(1,3) flow, Gaussian likelihood, 100 Gauss-Hermite points;
   cfg5 (configs[4]): TGP binary classification, N = 1 M, D = 16, M = 2048, SAL(1) flow, Bernoulli likelihood, 100 points.
-Both FP64 (what the reference's main.py runs).  One step = ELBO forward + backward over one minibatch:
+Both with FP64 results (what the reference's main.py runs): the default compute mode `i8crt` evaluates the batch contractions on
+the tcgen05 integer tensor pipe through CRT residues (FP64-accurate, parity-tested at 1e-10 like `f64`, the DMMA mode).  One step = ELBO forward + backward over one minibatch:
   weak scaling  (default): 65536 rows PER GPU, global minibatch 65536 * N;
   strong scaling          : 65536 rows in total, 65536 / N per GPU.
 The N/MB scale uses the global size; ranks exchange ONE all-reduce of the tril-packed pre-chain gradient buffer per step.
@@ -179,6 +180,49 @@ def measure_gemm_peak(dev, dtype, tf32=False, n=8192, reps=5):
     del a, b
     torch.backends.cuda.matmul.allow_tf32 = old
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def measure_int8_peak(dev, n=8192, reps=5):
+    """cuBLASLt INT8 GEMM n^3 via torch._int_mm (s8 x s8 -> s32), best of `reps`, in TOP/s."""
+    try:
+        a = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+        torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record()  # noqa: E702
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:          # noqa: BLE001
+        return None
+
+
+def i8crt_executed_ops(M, rows, chunk=16384):
+    """Integer operations (2 x MAC) the three residue GEMMs of compute mode i8crt EXECUTE per step: 128 x 256 tiles over their
+    clipped k-ranges (csrc/gemm_i8.cuh decode), times the modulus count of each contraction (csrc/crt_driver.cuh)."""
+    log2P = {15: 117.82, 16: 125.41}
+    bits_other = lambda T, k, fixed: min(53, int(math.floor(log2P[T] - 1.0 - math.log2(max(k, 1)) - fixed - 1e-6)))  # noqa: E731
+    Tf = 15 if bits_other(15, M, 53) >= 52 else 16
+    Tb = 15 if min(53, int(math.floor((log2P[15] - 1.0 - math.log2(2 * M)) / 2.0))) >= 52 else 16
+    cdiv = lambda a, b: (a + b - 1) // b  # noqa: E731
+    total = 0.0
+    for r0 in range(0, rows, chunk):
+        rc = min(chunk, rows - r0)
+        mt = cdiv(rc, 128) * 128
+        fwd = sum(min(M, n0 + 256) if n0 < M else M for n0 in range(0, 2 * M, 256))                   # k-length per n-tile
+        bwd = sum(2 * M - (n0 // 128) * 128 for n0 in range(0, M, 256))
+        wgt = 0
+        for mp in range(cdiv(cdiv(2 * M, 128), 2)):
+            for n0 in range(0, M, 256):
+                m_hi = (2 * mp + 1) * 128
+                if m_hi < M and n0 > m_hi + 127:
+                    continue
+                wgt += 2 * 128 * 256 * cdiv(rc, 128) * 128
+        total += 2.0 * (Tf * mt * 256 * fwd + Tb * mt * 256 * bwd + 16 * wgt)
+    return total
 
 
 def load_json(path):
@@ -415,7 +459,7 @@ def run_ours(args):
     parity = dist_parity() if world > 1 else None
     # the secondary mode runs first: on a fresh box the first seconds of a process are not steady (cold clocks, lazy
     # module loads), and the headline should not absorb that
-    second = args.other or ('tf32x3' if args.compute == 'f64' else 'f64')
+    second = args.other or ('f64' if args.compute != 'f64' else 'tf32x3')
     other = None
     if not args.no_other_mode:
         measure(second, False)                      # discarded: absorbs the cold start of a fresh box
@@ -437,12 +481,31 @@ def run_ours(args):
     extra = load_json(os.path.join(ROOT, 'profiles', 'r02_measured_peaks_extra.json'))     # scripts/measure_peaks.py on this pool
     peak64 = measure_gemm_peak(dev, torch.float64)
     peak_tf32 = measure_gemm_peak(dev, torch.float32, tf32=True)
+    peak_i8 = measure_int8_peak(dev)
     alg_flop_step = 6.0 * M * M * BATCH                         # 6*M^2 FLOP per row, fwd+bwd (per GPU)
 
     def roofline_of(mode, g_ms, g_n, step_ms):
         tag = 1 if mode == 'f64' else 2
         k_ms, k_n = g_ms[tag] / args.steps, g_n[tag] / args.steps
         ach = alg_flop_step / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        if mode == 'i8crt':
+            # the bounding pipe is the INTEGER tensor pipe: executed u8 x u8 operations against the measured INT8 GEMM rate;
+            # the algorithmic FP64 rate (6 M^2 FLOP per row) is reported beside it, with the cuBLAS DGEMM rate for scale
+            ops = i8crt_executed_ops(M, BATCH)
+            ex = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+            return {'bound': 'tensor', 'kernel': 'gemm_i8_mod_kernel (tcgen05 kind::i8, u8 x u8 -> s32 in TMEM, 15-16 residue planes, '
+                                                 '2-CTA clusters with TMA multicast), the three batch contractions',
+                    'achieved': ex, 'peak': peak_i8, 'unit': 'TOP/s', 'frac': ex / peak_i8 if peak_i8 else None,
+                    'peak_source': 'cuBLASLt INT8 GEMM 8192^3 via torch._int_mm, best of 5, measured in this run (tcgen05 kind::i8 issue '
+                                   'rate measured by scripts/microbench/mma_rate.cu: 4556 TOP/s); MEASURED_PEAKS.json holds bf16 %.0f TF/s '
+                                   'and HBM %.0f GB/s only' % (peaks.get('bf16_tflops', 0.0), peaks.get('hbm_gbs', 0.0)),
+                    'executed_int8_ops_per_step': ops, 'algorithmic_fp64_tflops': ach, 'cublas_dgemm_tflops': peak64,
+                    'algorithmic_vs_cublas_dgemm': ach / peak64 if peak64 else None,
+                    'algorithmic_flop_per_launch': alg_flop_step / max(k_n, 1), 'avg_launch_ms': k_ms / max(k_n, 1),
+                    'launches_per_step': k_n, 'kernel_share_of_step': k_ms / step_ms, 'traffic': None,
+                    'per_step_o_m3_gemm_ms': g_ms[0] / args.steps,
+                    'note': 'FP64-accurate results (operands truncated at 52-53 bits below their row maximum, integer product exact); '
+                            'the residue conversion and CRT reconstruction kernels around the GEMMs are counted in ms_per_step, not here'}
         if mode == 'f64':
             peak, src, kern = peak64, 'cuBLAS DGEMM 8192^3 via torch.matmul, best of 5, measured in this run', \
                 'gemm_f64_kernel (FP64 DMMA mma.sync.m8n8k4), the six batch contractions'
@@ -494,8 +557,9 @@ def run_ours(args):
                               'loss_rel_diff_vs_headline': abs(other['loss'] - final_loss) / abs(final_loss),
                               'test_nll_rows_per_s': other['test_nll_rows_per_s'],
                               'roofline': roofline_of(second, other['gemm_ms'], other['gemm_n'], other['ms_total'] / args.steps),
-                              'note': 'tf32x3 = batch contractions on tcgen05 (3xTF32 split, FP32 TMEM accumulation); per-step '
-                                      'factorisation, backward chain and the row epilogue stay FP64 in both modes'}
+                              'note': 'f64 = every contraction on the FP64 DMMA pipe (mma.sync.m8n8k4.f64); i8crt = batch contractions on '
+                                      'the tcgen05 integer pipe through CRT residues (FP64-accurate); tf32x3 = tcgen05 3xTF32 (FP32 '
+                                      'accuracy); per-step factorisation, backward chain and the row epilogue are FP64 in every mode'}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -593,7 +657,7 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: 65536 rows per GPU per step; strong: 65536 rows per step in total')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
-    ap.add_argument('--compute', default='f64', choices=['f64', 'tf32x3', 'i8crt'],
+    ap.add_argument('--compute', default='i8crt', choices=['f64', 'tf32x3', 'i8crt'],
                     help='f64: FP64 DMMA; i8crt: FP64-accurate on the tcgen05 integer path (CRT residues); tf32x3: tcgen05 3xTF32')
     ap.add_argument('--other', default=None, choices=['f64', 'tf32x3', 'i8crt'], help='secondary mode reported as other_mode')
     ap.add_argument('--no-other-mode', action='store_true', help='measure only the headline compute mode')

@@ -118,3 +118,47 @@ def test_i8crt_mode_reproduces_the_reference_at_fp64_tolerances(name):
     assert vals['ELBO'] < 1e-10 and vals['mu'] < 1e-10 and vals['v'] < 1e-9, vals
     bad = {k: e for k, e in errs.items() if not e < 1e-10}
     assert not bad, (bad, errs)
+
+
+@pytest.mark.parametrize('name', ['boston_tgp_steptanh13_p1', 'synth_clf_d16_m48_p1', 'boston_idtgp_drop_p1', 'synth_reg_d8_m1024_p1',
+                                  'boston_svgp_jitter'])
+def test_class_api_in_i8crt_mode(name):
+    """cg.compute = 'i8crt' through sparse_MF_SP.ELBO + backward + test_log_likelihood: same tolerances as the FP64 DMMA mode."""
+    from tests.model_util import build_from_golden, set_dropout_mode
+    from tests.test_gpu_parity import BERNOULLI_TOL
+    from tgp.pytorch_b200.dsp import config as cg
+    g = Golden(name)
+    old = cg.compute
+    try:
+        model = build_from_golden(g, DEV)
+        cg.compute = 'i8crt'
+        set_dropout_mode(model, g)
+        X, Y = g.t('X').to(DEV), g.t('Y').to(DEV)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ELBO, ELL, KLD = model.ELBO(X, Y)
+            (-ELBO).backward()
+        bern = g.meta['likelihood'] == 'bernoulli'
+        vtol = BERNOULLI_TOL['ELBO'] if bern else (1e-7 if 'jitter' in name else 1e-10)
+        gtol = BERNOULLI_TOL['grads'] if bern else 1e-10
+        assert rel_err(ELBO.detach().cpu(), g.t('ELBO')) < vtol
+        assert any(e.compute == 'i8crt' for e in model._engines.values())
+        if 'jitter' not in name:
+            worst = {}
+            for n, prm in model.named_parameters():
+                if 'grad:' + n not in g.z.files:
+                    worst.update({k: e for k, e in g.grad_errors({'L_raw': -prm.grad.detach()[0]}).items() if k.startswith('L_raw.')})
+                    continue
+                ref = -g.t('grad:' + n)
+                if float(ref.norm()) > 0:
+                    worst[n] = rel_err(prm.grad.detach().cpu().reshape(ref.shape), ref)
+            bad = {k: e for k, e in worst.items() if not e < gtol}
+            assert not bad, bad
+        model.set_is_training(False)
+        Xt, Yt = g.t('Xte').to(DEV), g.t('Yte').to(DEV)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            lp, _ = model.test_log_likelihood(Xt, Yt.long() if bern else Yt, return_moments=True, Y_std=torch.ones(1, device=DEV) * g.meta['y_std'])
+        assert rel_err(lp.double().sum().cpu(), g.t('test_logp')) < (1e-5 if bern else 1e-10)
+    finally:
+        cg.compute = old

@@ -36,8 +36,13 @@ positive_transform = 'exp'
 strict_flag = True
 constant_jitter = None
 global_jitter = None
-compute = 'f64'                # 'f64': FP64 DMMA path (parity mode, what main.py's set_maximum_precission runs);
-                               # 'tf32x3': batch contractions on tcgen05 (3xTF32, FP32 accumulate), rest FP64
+compute = 'f64'                # how the O(rows * M^2) batch contractions are evaluated (results are FP64 tensors in every mode):
+                               # 'f64':    FP64 DMMA tensor path (mma.sync.m8n8k4.f64);
+                               # 'i8crt':  tcgen05 integer tensor path (kind::i8, exact s32 accumulation in TMEM) over 15-16 residue
+                               #           planes + CRT reconstruction: FP64-ACCURATE (same 1e-10 parity tests as 'f64'), 1.2-1.6x
+                               #           faster at the BASELINE sizes; small problems gain nothing from it;
+                               # 'tf32x3': tcgen05 3xTF32 with FP32 TMEM accumulation (FP32 accuracy; chosen automatically for
+                               #           float32 models)
 cache_factorisation_in_eval = True   # consecutive no-grad evaluations with unchanged parameters reuse L, L^-1 (the cache
                                      # is keyed on tensor identity + in-place version; mutate parameters through
                                      # `.data` in-place only after set_is_training() / ELBO(), which drop it)
