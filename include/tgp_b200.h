@@ -87,6 +87,11 @@ int tgp_reduce_layout(const TgpModel* model, TgpReduceLayout* out);
 int tgp_prepare(const TgpModel* model, const TgpParams* params, double jitter, void* step_ws, double* kl_out,
                 int* status, void* stream);
 
+/* Blocks the HOST until the factorisation enqueued by the last tgp_prepare on the current device has finished (and only that:
+ * kernels enqueued after it keep running) and returns its pivot status in *status_out — what the jitter ladder of
+ * psd_safe_cholesky (utils.py:241-270) needs to decide.  Not available for a tgp_prepare recorded under graph capture. */
+int tgp_factor_status(int* status_out);
+
 /* q(f) marginals of R rows: mu, v (device, length R).  Saves A = K L^-T and B = K C^T in batch_ws for the backward.
  * Replaces sparse_MF_SP.marginal_variational_qf_parameters (sparse_MF_SP.py:274-396, whitened diagonal branch). */
 int tgp_qf_forward(const TgpModel* model, const void* step_ws, void* batch_ws, const void* X, long R, void* mu,
@@ -206,9 +211,12 @@ int tgp_test_nll_fwd(TgpHandle* h, const TgpParams* params, const TgpBatch* batc
  * TGP_OPT_ROW_CHUNK (FP64 mode): rows per launch of the batch contractions (default 32768; a tuning knob — it changes the
  * workspace size, so set it before asking for tgp_batch_workspace_bytes). */
 enum { TGP_OPT_FUSED_FORWARD = 1, TGP_OPT_ROW_CHUNK = 2,
-       TGP_OPT_OVERLAP_KGEN = 3 };   /* 1 (default): K_xz generation runs on a library-owned side stream concurrently with the
-                                      * factorisation of tgp_prepare (fork at its parameter transforms, join before the first
-                                      * contraction); 0: everything on the caller's stream */
+       TGP_OPT_OVERLAP_KGEN = 3 };   /* 1 (default): tgp_prepare forks the factorisation onto a library-owned high-priority stream;
+                                      * tgp_qf_forward enqueues K_xz generation on the caller's stream and joins afterwards, every
+                                      * other consumer of the step workspace joins first; 0: everything on the caller's stream.
+                                      * Either way the outputs of each entry point are ready in the order of the caller's stream
+                                      * once a consuming entry point has been enqueued on it; kl_out is always in stream order,
+                                      * status is read with tgp_factor_status() */
 int tgp_set_option(int key, int value);
 
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */

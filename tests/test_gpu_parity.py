@@ -83,8 +83,9 @@ def test_prepare_cholesky_inverse_kl(M, D):
     eng.set_params(ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'],
                    torch.zeros(0, dtype=torch.float64, device=DEV))
     kl, status = eng.prepare(0.0)
-    assert int(status.item()) == 0
+    assert eng.status_reader()() == 0            # host-blocking read of the pivot status (the factorisation may run on its own stream)
     L, Linv, Cm = (t.cpu() for t in eng.export_step())
+    assert int(status.item()) == 0               # ... and the device word, in stream order after a consumer has joined
     Kzz = O.rbf_ard(p['Z'], p['Z'], p['raw_lengthscale'], p['raw_outputscale'])
     Lref = torch.linalg.cholesky(Kzz)
     assert rel_err(L, Lref) < 1e-11

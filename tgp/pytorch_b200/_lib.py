@@ -70,6 +70,7 @@ SIGNATURES = {
     'tgp_batch_workspace_bytes': (C.c_size_t, [C.POINTER(TgpModel), _L]),
     'tgp_reduce_layout': (_I, [C.POINTER(TgpModel), C.POINTER(TgpReduceLayout)]),
     'tgp_prepare': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _D, _P, _P, _P, _P]),
+    'tgp_factor_status': (_I, [C.POINTER(C.c_int)]),
     'tgp_qf_forward': (_I, [C.POINTER(TgpModel), _P, _P, _P, _L, _P, _P, _P]),
     'tgp_ell_forward': (_I, [C.POINTER(TgpModel), C.POINTER(TgpParams), _P, _P, _P, _P, _L, _D, _P, _P, _I, _P, _P, _P,
                              _P, _P, _P]),

@@ -31,28 +31,33 @@ inline int check_launch(const char* what) {
 
 #define TGP_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
 
-// A library-owned side stream per device, used to run K_xz generation concurrently with the (single-SM-bound) factorisation:
-// tgp_prepare records `params_ready` right after the parameter transforms; tgp_qf_forward generates K_xz on the side stream
-// as soon as that event fires and joins back with `k_ready`.  Host objects only (no device memory).  `capturing` remembers
-// whether the prepare was enqueued under CUDA-graph capture: fork and join must belong to the same capture.
+// Concurrency of the per-step factorisation with K_xz generation.  tgp_prepare is a chain of ~80 small, mostly single-CTA
+// kernels (1.2-1.4 ms at M = 1024) that leaves the GPU almost idle; K_xz generation of the coming forward needs only the
+// transformed parameters.  With TGP_OPT_OVERLAP_KGEN (default) tgp_prepare forks: the factorisation runs on a library-owned
+// HIGHEST-priority stream (its short kernels are dispatched ahead of the K_xz tiles), the caller's stream continues;
+// tgp_qf_forward enqueues K_xz generation on the caller's stream and only then joins.  Every other consumer of the step
+// workspace joins first (join_factor).  The 4-byte pivot status is copied to pinned host memory on the factorisation's
+// stream; tgp_factor_status() blocks the host on that copy alone.  Host objects only — no device memory is allocated.
 struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t params_ready = nullptr, k_ready = nullptr;
-    bool have_params = false, capturing = false;
-    bool fresh = false;          // set by tgp_prepare, consumed by the FIRST forward after it: a later forward on the same
-                                 // factorisation may follow work that still reads the batch workspace, and stays on the main stream
+    cudaStream_t hp = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_status = nullptr;
+    int* status_host = nullptr;
+    bool pending = false;        // a factorisation is in flight on `hp` and the consumer stream has not joined yet
+    bool status_valid = false;   // ev_status was recorded outside graph capture
 };
 inline SideStream& side_stream() {
     static SideStream s[64];
     int dev = 0;
     cudaGetDevice(&dev);
     SideStream& x = s[dev >= 0 && dev < 64 ? dev : 0];
-    if (!x.stream) {
-        int lo = 0, hi = 0;          // lowest priority: the factorisation's small kernels are never queued behind K_xz tiles
+    if (!x.hp) {
+        int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaStreamCreateWithPriority(&x.stream, cudaStreamNonBlocking, lo);
-        cudaEventCreateWithFlags(&x.params_ready, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&x.k_ready, cudaEventDisableTiming);
+        cudaStreamCreateWithPriority(&x.hp, cudaStreamNonBlocking, hi);
+        cudaEventCreateWithFlags(&x.ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&x.ev_factor, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&x.ev_status, cudaEventDisableTiming);
+        cudaHostAlloc(reinterpret_cast<void**>(&x.status_host), sizeof(int), cudaHostAllocDefault);
     }
     return x;
 }
@@ -60,6 +65,15 @@ inline bool stream_is_capturing(cudaStream_t st) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
     return cs != cudaStreamCaptureStatusNone;
+}
+// the consumer stream waits for the factorisation in flight (no-op when there is none)
+inline int join_factor(cudaStream_t st) {
+    SideStream& ss = side_stream();
+    if (ss.pending) {
+        ss.pending = false;
+        if (cudaStreamWaitEvent(st, ss.ev_factor, 0) != cudaSuccess) return -100;
+    }
+    return 0;
 }
 extern int g_overlap_kgen;       // TGP_OPT_OVERLAP_KGEN
 

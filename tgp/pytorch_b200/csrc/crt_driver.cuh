@@ -156,7 +156,8 @@ inline int combine(const uint8_t* R, long ldr, long plane_stride, long rows, int
 inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
                         int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st, int ctas_per_sm = 3) {
     const long n_tiles = cdiv(M, i8::RS_TC) * cdiv(R, i8::RS_TR);
-    const unsigned grid = (unsigned)(n_tiles < 148L * ctas_per_sm ? n_tiles : 148L * ctas_per_sm);
+    // ctas_per_sm = 0: one CTA per tile (short CTAs: a concurrent high-priority stream gets slots every few microseconds)
+    const unsigned grid = (unsigned)((ctas_per_sm <= 0 || n_tiles < 148L * ctas_per_sm) ? n_tiles : 148L * ctas_per_sm);
     const i8::CrtTable& tab = i8::crt_table(T);
 #define TGP_RR(MD) i8::k_rbf_residues<MD><<<grid, 256, 0, st>>>(X, Zs, ls, os, R, M, D, Kout, M, 53, tab, planes, ldp, plane_stride)
     if (D <= 4) TGP_RR(4);
@@ -227,29 +228,18 @@ inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, cons
     StepPlanes sp = carve_step(step_region, M);
     BatchView b = carve_batch(batch_ws, M, R);
     const int Tf = fwd_T(M), bits = fwd_bits_w(M);
-    // K_xz (FP64 values + residue planes) of every chunk.  It depends on Zs / ls / os only, not on the factorisation, so it is
-    // enqueued on the library's side stream behind tgp_prepare's `params_ready` event and runs UNDER the factorisation (which
-    // keeps a single SM busy for ~1 ms); the main stream joins before the first contraction.
-    SideStream& ss = side_stream();
-    const bool overlap = g_overlap_kgen && ss.have_params && ss.fresh && D <= 32 && ss.capturing == stream_is_capturing(st);
-    ss.fresh = false;
-    cudaStream_t kst = st;
-    if (overlap) {
-        if (cudaStreamWaitEvent(ss.stream, ss.params_ready, 0) == cudaSuccess) kst = ss.stream;
-        else cudaGetLastError();
-    }
-    {   // one launch for all rows.  K residues: one scale for the whole matrix (0 <= k <= outputscale), shared by the forward and
-        // the weight contraction
-        const int rr = rbf_residues(X, s.Zs, s.ls, s.os, R, M, D, b.Kbuf, T_ALL, b.Kp, b.ldk, R * b.ldk, kst, kst != st ? 2 : 3);
+    // K_xz (FP64 values + residue planes) of all rows in one launch.  It depends on Zs / ls / os only, not on the factorisation:
+    // it is enqueued BEFORE the join with the factorisation, which may still be running on the library's high-priority stream
+    // (TGP_OPT_OVERLAP_KGEN, common.cuh), and runs under it.  K residues: one scale for the whole matrix (0 <= k <= outputscale),
+    // shared by the forward and the weight contraction.
+    {
+        const int rr = rbf_residues(X, s.Zs, s.ls, s.os, R, M, D, b.Kbuf, T_ALL, b.Kp, b.ldk, R * b.ldk, st, 0);
+        if (rr != 0 && rr != -7) return rr;
+        if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
         if (rr == -7) {
-            kst = st;
             TGP_TRY(launch_rbf(X, s.Zs, s.ls, s.os, (int)R, M, D, 0, b.Kbuf, M, (int)R, M, 0.0, st));
             TGP_TRY(to_residues(b.Kbuf, M, R, M, 2, sp.k_exp, 53, T_ALL, b.Kp, b.ldk, R * b.ldk, st));
-        } else if (rr != 0) return rr;
-    }
-    if (kst != st) {
-        if (cudaEventRecord(ss.k_ready, kst) != cudaSuccess || cudaStreamWaitEvent(st, ss.k_ready, 0) != cudaSuccess)
-            return set_error(-100, "side-stream join failed");
+        }
     }
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
@@ -271,6 +261,7 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
     const int M = s.M, D = s.D;
     StepPlanes sp = carve_step(step_region, M);
     BatchView b = carve_batch(batch_ws, M, R);
+    if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
     const int Tb = bwd_T(M), bits_b = bwd_bits(M);
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);

@@ -314,7 +314,7 @@ inline StepView carve_step(void* ws, int M, int D) {
 // K_zz (+jitter) -> L, L^-1 (explicit), C = L_S^T L^-1, KL.  Everything stays on `st`; no host sync.
 inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls, const double* raw_os,
                        const double* m, const double* Lraw, double jitter, double* kl_out, int* status,
-                       bool need_C, cudaStream_t st) {
+                       bool need_C, cudaStream_t st, cudaStream_t (*fork)(cudaStream_t) = nullptr) {
     const int M = v.M, Mp = v.Mp, D = v.D, NB = POTRF_NB, nb = Mp / NB;
     const size_t mm = (size_t)Mp * Mp;
     static PerDeviceOnce potrf_once;
@@ -327,18 +327,15 @@ inline int run_prepare(const StepView& v, const double* Z, const double* raw_ls,
         const int n = max(M * D, D);
         k_transform_params<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(Z, raw_ls, raw_os, M, D, v.ls, v.os, v.Zs);
         TGP_TRY(check_launch("k_transform_params"));
-        if (g_overlap_kgen) {          // K_xz generation of the coming forward may start from here (it needs Zs, ls, os only)
-            SideStream& ss = side_stream();
-            ss.capturing = stream_is_capturing(st);
-            ss.have_params = cudaEventRecord(ss.params_ready, st) == cudaSuccess;
-            if (!ss.have_params) cudaGetLastError();
-            ss.fresh = ss.have_params;
-        }
     }
-    TGP_TRY(launch_rbf(v.Zs, v.Zs, v.ls, v.os, M, M, D, 1, v.Kzz, Mp, Mp, Mp, jitter, st));
     k_tril_kl<<<Mp, 256, 0, st>>>(Lraw, m, M, v.LS, Mp, Mp, v.kl3);
     TGP_TRY(check_launch("k_tril_kl"));
     k_kl_finish<<<1, 1, 0, st>>>(v.kl3, M, kl_out);
+    cudaStream_t fst = fork ? fork(st) : nullptr;
+    // everything above stays on the caller's stream (kl_out is an output in stream order); the factorisation proper forks
+    // onto the high-priority stream `fst` when the caller passed one (tgp_prepare), see common.cuh
+    st = fst ? fst : st;
+    TGP_TRY(launch_rbf(v.Zs, v.Zs, v.ls, v.os, M, M, D, 1, v.Kzz, Mp, Mp, Mp, jitter, st));
 
     // right-looking blocked Cholesky; the panel solve is a GEMM with the inverted diagonal block
     for (int kb = 0; kb < nb; ++kb) {

@@ -172,17 +172,52 @@ int tgp_reduce_layout(const TgpModel* md, TgpReduceLayout* out) {
     return 0;
 }
 
+// fork of tgp_prepare: the factorisation's stream (the library's high-priority stream, ordered after everything enqueued on
+// `st` so far), or `st` itself when the overlap is off / the fork fails
+static cudaStream_t g_factor_stream = nullptr;
+static cudaStream_t fork_factor(cudaStream_t st) {
+    g_factor_stream = st;
+    if (!g_overlap_kgen) return st;
+    SideStream& ss = side_stream();
+    if (cudaEventRecord(ss.ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(ss.hp, ss.ev_fork, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return st;
+    }
+    g_factor_stream = ss.hp;
+    return ss.hp;
+}
+
 int tgp_prepare(const TgpModel* md, const TgpParams* p, double jitter, void* step_ws, double* kl_out, int* status,
                 void* stream) {
     TGP_TRY(validate(md));
     if (!p || !step_ws || !kl_out || !status) return set_error(-1, "NULL argument to tgp_prepare");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (join_factor(st)) return set_error(-100, "join with the previous factorisation failed");      // it may still use this workspace
     StepView v = carve_step(step_ws, md->M, md->D);
     TGP_TRY(run_prepare(v, (const double*)p->Z, (const double*)p->raw_lengthscale, (const double*)p->raw_outputscale,
-                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, md->dtype != TGP_F64,
-                        (cudaStream_t)stream));
-    if (md->dtype == TGP_F32) TGP_TRY(tc::make_step_planes(v, step_ws, (cudaStream_t)stream));
-    if (md->dtype == TGP_F64_I8)
-        TGP_TRY(crt::make_step_planes(v, reinterpret_cast<char*>(step_ws) + crt_step_offset(md), (cudaStream_t)stream));
+                        (const double*)p->m, (const double*)p->L_raw, jitter, kl_out, status, md->dtype != TGP_F64, st, fork_factor));
+    cudaStream_t fst = g_factor_stream;
+    if (md->dtype == TGP_F32) TGP_TRY(tc::make_step_planes(v, step_ws, fst));
+    if (md->dtype == TGP_F64_I8) TGP_TRY(crt::make_step_planes(v, reinterpret_cast<char*>(step_ws) + crt_step_offset(md), fst));
+    SideStream& ss = side_stream();
+    ss.status_valid = false;
+    if (!stream_is_capturing(st)) {          // the pivot status travels to pinned host memory behind the factorisation alone
+        cudaMemcpyAsync(ss.status_host, status, sizeof(int), cudaMemcpyDeviceToHost, fst);
+        ss.status_valid = cudaEventRecord(ss.ev_status, fst) == cudaSuccess;
+    }
+    if (fst != st) {
+        if (cudaEventRecord(ss.ev_factor, fst) != cudaSuccess) return set_error(-100, "recording the factorisation event failed");
+        ss.pending = true;
+    }
+    return 0;
+}
+
+int tgp_factor_status(int* status_out) {
+    SideStream& ss = side_stream();
+    if (!status_out) return set_error(-1, "status_out is NULL");
+    if (!ss.status_valid) return set_error(-1, "no factorisation status in flight (tgp_prepare under graph capture records none)");
+    if (cudaEventSynchronize(ss.ev_status) != cudaSuccess) return set_error(-100, "waiting for the factorisation failed");
+    *status_out = *ss.status_host;
     return 0;
 }
 
@@ -194,6 +229,9 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
     cudaStream_t st = (cudaStream_t)stream;
     const int M = md->M, D = md->D;
     StepView s = carve_step(const_cast<void*>(step_ws), M, D);
+    if (md->dtype == TGP_F32) {
+        if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
+    }
     if (md->dtype == TGP_F32)
         return tc::qf_forward(s, const_cast<void*>(step_ws), batch_ws, (const double*)X, R, (double*)mu, (double*)v, st);
     if (md->dtype == TGP_F64_I8)
@@ -201,22 +239,13 @@ int tgp_qf_forward(const TgpModel* md, const void* step_ws, void* batch_ws, cons
                                R, (double*)mu, (double*)v, st);
     BatchView b = carve_batch(batch_ws, M, R);
     const double* Xd = (const double*)X;
-    {   // K_xz of every chunk: independent of the factorisation, generated on the side stream under it (TGP_OPT_OVERLAP_KGEN)
-        SideStream& ss = side_stream();
-        cudaStream_t kst = st;
-        const bool overlap = g_overlap_kgen && ss.have_params && ss.fresh && ss.capturing == stream_is_capturing(st);
-        ss.fresh = false;
-        if (overlap) {
-            if (cudaStreamWaitEvent(ss.stream, ss.params_ready, 0) == cudaSuccess) kst = ss.stream;
-            else cudaGetLastError();
-        }
-        for (long r0 = 0; r0 < R; r0 += b.Rc) {
-            const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
-            TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf + r0 * M, M, rc, M, 0.0, kst));
-        }
-        if (kst != st && (cudaEventRecord(ss.k_ready, kst) != cudaSuccess || cudaStreamWaitEvent(st, ss.k_ready, 0) != cudaSuccess))
-            return set_error(-100, "side-stream join failed");
+    // K_xz of every chunk depends on the transformed parameters only: it is enqueued BEFORE the join with the factorisation
+    // (which may still be running on the library's high-priority stream, TGP_OPT_OVERLAP_KGEN) and runs under it
+    for (long r0 = 0; r0 < R; r0 += b.Rc) {
+        const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
+        TGP_TRY(launch_rbf(Xd + r0 * D, s.Zs, s.ls, s.os, rc, M, D, 0, b.Kbuf + r0 * M, M, rc, M, 0.0, st));
     }
+    if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         double* Kc = b.Kbuf + r0 * M;
@@ -273,6 +302,7 @@ int tgp_qf_backward(const TgpModel* md, const TgpParams* p, const void* step_ws,
     BatchView b = carve_batch(batch_ws, M, R);
     const TgpReduceLayout l = reduce_layout(md);
     const double* Xd = (const double*)X;
+    if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
     double* Gbar = reduce_buf + l.Gbar;
     double* Cbar = reduce_buf + l.Cbar;
     if (md->dtype == TGP_F32)
@@ -325,6 +355,7 @@ int tgp_chain_backward(const TgpModel* md, const TgpParams* p, void* step_ws, co
         return set_error(-1, "NULL argument to tgp_chain_backward");
     if (md->n_theta > 0 && !dtheta) return set_error(-1, "dtheta required");
     cudaStream_t st = (cudaStream_t)stream;
+    if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
     const int M = md->M, D = md->D, Mp = pad_M(md->M);
     const size_t mm = (size_t)Mp * Mp;
     StepView s = carve_step(step_ws, M, D);
@@ -664,6 +695,7 @@ int tgp_debug_export_step(const TgpModel* md, const void* step_ws, double* L, do
     TGP_TRY(validate(md));
     StepView s = carve_step(const_cast<void*>(step_ws), md->M, md->D);
     cudaStream_t st = (cudaStream_t)stream;
+    if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
     if (L) k_copy_strided<<<md->M, 256, 0, st>>>(s.L, s.Mp, L, md->M, md->M);
     if (Linv) k_copy_strided<<<md->M, 256, 0, st>>>(s.Linv, s.Mp, Linv, md->M, md->M);
     if (C) k_copy_strided<<<md->M, 256, 0, st>>>(s.Cm, s.Mp, C, md->M, md->M);

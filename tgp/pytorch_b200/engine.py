@@ -197,24 +197,17 @@ class Engine:
         return self.kl, self.status
 
     def status_reader(self):
-        """Starts the device->host copy of the 4-byte pivot status on a side stream that waits only for the work enqueued
-        SO FAR (call right after prepare()).  Returns a function that blocks until that copy has landed and yields the
-        status — by then the caller has enqueued the kernels that consume the factorisation, so the check does not
-        drain the compute stream."""
-        if getattr(self, '_status_host', None) is None:
-            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            self._status_stream = torch.cuda.Stream(device=self.device)
-            self._status_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        ready, landed = self._status_ev
-        ready.record(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self._status_stream):
-            self._status_stream.wait_event(ready)
-            self._status_host.copy_(self.status, non_blocking=True)
-            landed.record(self._status_stream)
+        """Returns a function that blocks the host until the factorisation of the last prepare() has finished — and only the
+        factorisation: the library copies the 4-byte pivot status to pinned host memory right behind it (on its own
+        high-priority stream when TGP_OPT_OVERLAP_KGEN forks it there) — and yields the status.  Call it after the kernels
+        that consume the factorisation have been enqueued: the check then costs no pipeline bubble."""
+        dev = self.device
 
         def read():
-            landed.synchronize()
-            return int(self._status_host[0])
+            out = C.c_int(0)
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.tgp_factor_status(C.byref(out)), 'tgp_factor_status')
+            return int(out.value)
         return read
 
     @_on_device

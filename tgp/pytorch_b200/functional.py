@@ -54,8 +54,8 @@ def _jitter_ladder(engine, fail, base_jitter=None, constant_jitter=0.0):
     jitter = 1e-8 if base_jitter is None else base_jitter
     for i in range(3):
         j = jitter * (10 ** i)
-        kl, status = engine.prepare(constant_jitter + j)
-        if int(status.item()) == 0:
+        kl, _ = engine.prepare(constant_jitter + j)
+        if engine.status_reader()() == 0:        # blocks on the factorisation alone (it may run on the library's own stream)
             warnings.warn('A not p.d., added jitter of %g to the diagonal' % j, NumericalWarning)
             return kl, j
     raise RuntimeError('cholesky: matrix not positive definite after 3 jitter escalations (first bad pivot %d)' % fail)
