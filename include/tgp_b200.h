@@ -28,7 +28,12 @@ enum { TGP_LIK_GAUSS_LINEAR = 0,     /* likelihoods/GaussianLinearMean.py:60-87 
 enum { TGP_FLOW_IDENTITY = 0,        /* models/flow.py:296-307                                              */
        TGP_FLOW_AFFINE = 1,          /* models/flow.py:330-340   params [a, b]                              */
        TGP_FLOW_TANH_STEP = 2,       /* models/flow.py:1096-1103 over :755-773   params n_steps x [a,b,c,d] */
-       TGP_FLOW_SAL = 3 };           /* models/flow.py:904-905, 965-977   params [a, b]                     */
+       TGP_FLOW_SAL = 3,             /* models/flow.py:904-905, 965-977   params [a, b]                     */
+       TGP_FLOW_ARCSINH = 4,         /* models/flow.py:495-557  a + b asinh((f - c) / d)   params [a, b, c, d]
+                                      * (RESTRICT: softplus on b and d; asinh(u) = log(u + sqrt(u^2 + 1)))  */
+       TGP_FLOW_BOXCOX = 5,          /* models/flow.py:377-421  (sgn(f)|f|^lam - 1) / lam   params [lam] — the
+                                      * value AFTER the module's constraint (transform_param, :398-409)     */
+       TGP_FLOW_INV_BOXCOX = 6 };    /* models/flow.py:423-446  sgn(lam f + 1)|lam f + 1|^(1/lam)  params [lam] */
 enum { TGP_FLOW_RESTRICT = 1,        /* set_restrictions: softplus on a (affine) / b (sinh-arcsinh)         */
        TGP_FLOW_ADD_F0 = 2,          /* add_init_f0                                                         */
        TGP_FLOW_PER_ROW = 4 };       /* parameters come from the per-row matrix (input-dependent flow)      */

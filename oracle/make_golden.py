@@ -21,9 +21,9 @@ dsp = load_reference()
 import dsp.config as cg  # noqa: E402
 from dsp.models import instance_kernel, sparse_MF_SP, sparse_MF_GP  # noqa: E402
 from dsp.models.flow import (instance_flow, AffineFlow, StepFlow, TanhFlow, Sinh_ArcsinhFlow,  # noqa: E402
-                             IdentityFlow, CompositeFlow)
+                             IdentityFlow, CompositeFlow, ArcsinhFlow, BoxCoxFlow, InverseBoxCoxFlow)
 from dsp.likelihoods import GaussianNonLinearMean, GaussianLinearMean, Bernoulli  # noqa: E402
-from dsp.flows import SAL, StepTanhL  # noqa: E402
+from dsp.flows import SAL, StepTanhL, ArcSL, BoxCoxL, InverseBoxCoxL, build_chain  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 UCI = os.path.join(os.environ.get('TGP_REFERENCE_ROOT', '/root/reference'), 'code', 'datasets', 'regression', 'uci')
@@ -125,6 +125,11 @@ def flow_to_spec(flow, store, X=None, prefix='fl'):
                 assert not sub.add_init_f0 and not sub.input_dependent
                 steps.append([put(sub.a), put(sub.b), put(sub.c), put(sub.d)])
             spec.append(['tanh_step', steps, bool(fl.add_init_f0)])
+        elif isinstance(fl, ArcsinhFlow):
+            spec.append(['arcsinh', put(fl.a), put(fl.b), put(fl.c), put(fl.d), bool(fl.set_restrictions), bool(fl.add_init_f0)])
+        elif isinstance(fl, BoxCoxFlow):             # InverseBoxCoxFlow derives from it
+            kind = 'invboxcox' if isinstance(fl, InverseBoxCoxFlow) else 'boxcox'
+            spec.append([kind, put(fl.transform_param()), bool(fl.add_init_f0)])      # lam AFTER the constraint
         elif isinstance(fl, Sinh_ArcsinhFlow):
             if fl.input_dependent:
                 a = fl.NNets_a(X).squeeze(-1)
@@ -372,6 +377,36 @@ def main_dropout():
             record('%s_idtgp_drop_p1' % tag, m, X, Y, Xt, Yt, ys, 'gauss_nonlinear', id_flow=True, tape=tape)
 
 
+def boxcox_constraint(lam):
+    """The constraint of the reference's own Box-Cox chains (flows.py:542, n = 2): lam in (0.01, 2.01)."""
+    return 2.0 * torch.sigmoid(lam) + 0.01
+
+
+def main_flows():
+    """the remaining flow families of the reference's launch scripts — arcsinh, Box-Cox and inverse
+    Box-Cox layers and the build_chain combinations (flows.py:71-109, 140-214; flow.py:377-446, 495-557)."""
+    Xb, Yb, Xbt, Ybt, ysb = load_uci('boston')
+    Nb = Xb.shape[0]
+    cases = (('boston_tgp_arcsl2_p1', 'ArcSL:2', lambda: ArcSL(2), False, 50),
+             ('boston_tgp_bcl1_p1', 'BoxCoxL:1:random', lambda: BoxCoxL(1, init_random=True), False, 51),
+             ('boston_tgp_bcl_al_p1', 'build_chain:BCL_AL:1', lambda: build_chain('BCL_AL', 1, constraint=boxcox_constraint), True, 52),
+             ('boston_tgp_sal_invbcl_p1', 'build_chain:SAL_InvBCL:1', lambda: build_chain('SAL_InvBCL', 1, constraint=boxcox_constraint), True, 53),
+             ('boston_tgp_sal_al2_p1', 'build_chain:SAL_AL:2', lambda: build_chain('SAL_AL', 2), False, 54))
+    for name, builder, make, constrained, sd in cases:
+        torch.manual_seed(sd); np.random.seed(sd)  # noqa: E702
+        m = build('TGP', Xb, 100, Nb, make(), seed=sd)
+        g = torch.Generator().manual_seed(sd + 100)
+        randomise(m, sd + 10)
+        with torch.no_grad():
+            # keep the Box-Cox exponents in their well-behaved range and the composed map gentle
+            for n, prm in m.named_parameters():
+                if n.endswith('.lam'):
+                    prm.copy_((0.3 * torch.randn((), generator=g)).reshape(prm.shape) if constrained
+                              else (1.0 + 0.15 * torch.randn((), generator=g)).reshape(prm.shape))
+        record(name, m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear',
+               extra={'flow_builder': builder, 'boxcox_constraint': constrained})
+
+
 def main_big():
     """Fixtures at the BASELINE.json sizes (configs[3]: D=8, M=1024, StepTanhL(1,3); configs[4]: Bernoulli, D=16, M=2048,
     SAL(1)); row counts the CPU oracle replays in seconds.  Z = distinct data rows, as in bench.py."""
@@ -390,6 +425,9 @@ if __name__ == '__main__':
     if 'BIG' in ONLY:
         ONLY.discard('BIG')
         main_big()
+    elif 'FLOWS' in ONLY:
+        ONLY.discard('FLOWS')
+        main_flows()
     elif 'DROPOUT' in ONLY:
         ONLY.discard('DROPOUT')
         main_dropout()

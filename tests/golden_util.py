@@ -46,6 +46,10 @@ class Golden:
                 layers.append(('tanh_step', [tuple(get(k) for k in st) for st in lay[1]], lay[2]))
             elif lay[0] == 'sal':
                 layers.append(('sal', get(lay[1]), get(lay[2]), lay[3], lay[4]))
+            elif lay[0] == 'arcsinh':
+                layers.append(('arcsinh', get(lay[1]), get(lay[2]), get(lay[3]), get(lay[4]), lay[5], lay[6]))
+            elif lay[0] in ('boxcox', 'invboxcox'):
+                layers.append((lay[0], get(lay[1]), lay[2]))
         return layers
 
     def oracle_params(self, which='train', dtype=torch.float64):
@@ -103,8 +107,14 @@ class Golden:
                         keys += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
                 elif lay[0] == 'sal':
                     keys += ['flow%d.a' % i, 'flow%d.b' % i]
+                elif lay[0] == 'arcsinh':
+                    keys += ['flow%d.%s' % (i, c) for c in 'abcd']
+                elif lay[0] in ('boxcox', 'invboxcox'):
+                    # the layer's leaf is lam AFTER the module's constraint; the reference's gradient is w.r.t. the raw
+                    # parameter: comparable only when there is no constraint (the class-API tests cover the chain)
+                    keys += ['flow%d.lam' % i if not self.meta.get('boxcox_constraint') else None]
             assert len(keys) == len(vals), (keys, flow_names)
-            g.update(dict(zip(keys, vals)))
+            g.update({k: v for k, v in zip(keys, vals) if k is not None})
         return g
 
 

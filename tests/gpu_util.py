@@ -19,6 +19,14 @@ def flow_layout_and_params(layers, device):
             for j, st in enumerate(lay[1]):
                 theta += [t.reshape(()) for t in st]
                 names += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
+        elif lay[0] == 'arcsinh':
+            desc.append(dict(kind='arcsinh', restrict=lay[5], add_f0=lay[6]))
+            theta += [t.reshape(()) for t in lay[1:5]]
+            names += ['flow%d.%s' % (i, c) for c in 'abcd']
+        elif lay[0] in ('boxcox', 'invboxcox'):
+            desc.append(dict(kind=lay[0], add_f0=lay[2]))
+            theta += [lay[1].reshape(())]
+            names += ['flow%d.lam' % i]
         elif lay[0] == 'sal':
             per_row = lay[1].dim() > 0
             desc.append(dict(kind='sal', restrict=lay[3], add_f0=lay[4], per_row=per_row))

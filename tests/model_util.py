@@ -29,7 +29,17 @@ def build_from_golden(g, device):
         # rebuild the flow architecture from the fixture's layer list
         spec = meta['flow_train']
         names = meta['param_names']
-        if spec[0][0] == 'tanh_step':
+        if meta.get('flow_builder'):
+            from tgp.pytorch_b200.dsp.flows import ArcSL, BoxCoxL, build_chain
+            parts = meta['flow_builder'].split(':')
+            constraint = (lambda lam: 2.0 * torch.sigmoid(lam) + 0.01) if meta.get('boxcox_constraint') else None
+            if parts[0] == 'ArcSL':
+                flow = ArcSL(int(parts[1]))
+            elif parts[0] == 'BoxCoxL':
+                flow = BoxCoxL(int(parts[1]), init_random=True)
+            else:
+                flow = build_chain(parts[1], int(parts[2]), constraint=constraint)
+        elif spec[0][0] == 'tanh_step':
             flow = StepTanhL(len(spec) // 2, len(spec[0][1]), add_f0=True)
         elif meta['id_flow']:
             nb = len(spec) // 2

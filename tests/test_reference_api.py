@@ -34,11 +34,14 @@ def test_public_names_and_signatures_match_the_reference():
              (rm.sparse_MF_GP.__init__, om.sparse_MF_GP.__init__), (rf.instance_flow, of.instance_flow),
              (rl.GaussianNonLinearMean.__init__, ol.GaussianNonLinearMean.__init__),
              (rl.GaussianLinearMean.__init__, ol.GaussianLinearMean.__init__), (rl.Bernoulli.__init__, ol.Bernoulli.__init__),
-             (rfl.SAL, ofl.SAL), (rfl.StepTanhL, ofl.StepTanhL), (ru.KMEANS, ou.KMEANS)]
+             (rfl.SAL, ofl.SAL), (rfl.StepTanhL, ofl.StepTanhL), (ru.KMEANS, ou.KMEANS),
+             (rfl.BoxCoxL, ofl.BoxCoxL), (rfl.InverseBoxCoxL, ofl.InverseBoxCoxL), (rfl.ArcSL, ofl.ArcSL),
+             (rfl.build_chain, ofl.build_chain)]
     for meth in ('ELBO', 'KLD', 'ELL', 'marginal_variational_qf_parameters', 'predictive_distribution', 'test_log_likelihood',
                  'sample_from_predictive_distribution', 'sample_from_variational_marginal', 'be_fully_bayesian', 'set_is_training'):
         pairs.append((getattr(rm.sparse_MF_SP, meth), getattr(om.sparse_MF_SP, meth)))
-    for cls in ('AffineFlow', 'TanhFlow', 'Sinh_ArcsinhFlow', 'StepFlow', 'CompositeFlow', 'IdentityFlow'):
+    for cls in ('AffineFlow', 'TanhFlow', 'Sinh_ArcsinhFlow', 'StepFlow', 'CompositeFlow', 'IdentityFlow', 'ArcsinhFlow', 'BoxCoxFlow',
+                'InverseBoxCoxFlow'):
         pairs.append((getattr(rf, cls).__init__, getattr(of, cls).__init__))
         pairs.append((getattr(rf, cls).forward, getattr(of, cls).forward))
     for lik in ('GaussianNonLinearMean', 'GaussianLinearMean', 'Bernoulli'):

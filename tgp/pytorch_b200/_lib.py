@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get('TGP_B200_LIB', os.path.join(_HERE, 'libtgp_b200.so'))
 
 TGP_F64, TGP_F32, TGP_F64_I8 = 0, 1, 2
 LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
-FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL = 0, 1, 2, 3
+FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL, FLOW_ARCSINH, FLOW_BOXCOX, FLOW_INV_BOXCOX = 0, 1, 2, 3, 4, 5, 6
 FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
 MAX_LAYERS = 64
 OPT_FUSED_FORWARD = 1

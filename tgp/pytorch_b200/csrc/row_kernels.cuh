@@ -79,6 +79,8 @@ __device__ __forceinline__ void flow_prepare(const FlowDesc& fd, const double* _
             else if (w == 3) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
         } else if (L.kind == TGP_FLOW_SAL) {
             if (idx == 1 && res) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
+        } else if (L.kind == TGP_FLOW_ARCSINH) {
+            if ((idx == 1 || idx == 3) && res) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
         }
         prep[3 * s] = v0; prep[3 * s + 1] = v1; prep[3 * s + 2] = 1.0 / v0;
     }
@@ -147,6 +149,39 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
             if (pg) { pg[slot] = -ch; pg[slot + 1] = ch * w * ch1; }
             slot += 2;
             if (L.flags & TGP_FLOW_ADD_F0) { g += f; d += 1.0; }
+        } else if (L.kind == TGP_FLOW_ARCSINH) {
+            double chb, chd;
+            const double a = val(0, false, ch0), b = val(1, res, chb), c = val(2, false, ch0), de = val(3, res, chd);
+            const double u = (f - c) / de;
+            const double r = sqrt(u * u + 1.0);
+            const double w = log(u + r);                 // the reference's asinh (flow.py:521-522)
+            const double dw = (1.0 + u / r) / (u + r);   // its derivative as autograd forms it
+            g = a + b * w;
+            d = b * dw / de;
+            if (pg) { pg[slot] = 1.0; pg[slot + 1] = w * chb; pg[slot + 2] = -d; pg[slot + 3] = -d * u * chd; }
+            slot += 4;
+            if (L.flags & TGP_FLOW_ADD_F0) { g += f; d += 1.0; }
+        } else if (L.kind == TGP_FLOW_BOXCOX) {
+            const double lam = val(0, false, ch0);
+            const double sg = f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0), pos = sg * f;
+            const double pw = pow(pos, lam);
+            g = (sg * pw - 1.0) / lam;
+            d = pos > 0.0 ? pw / pos : (lam == 1.0 ? 1.0 : (lam > 1.0 ? 0.0 : INFINITY));       // |f|^(lam - 1)
+            if (pg) pg[slot] = (pos > 0.0 ? sg * pw * log(pos) : 0.0) / lam - (sg * pw - 1.0) / (lam * lam);
+            slot += 1;
+            if (L.flags & TGP_FLOW_ADD_F0) { g += f; d += 1.0; }
+        } else if (L.kind == TGP_FLOW_INV_BOXCOX) {
+            const double lam = val(0, false, ch0);
+            const double aux = lam * f + 1.0;
+            const double sg = aux > 0.0 ? 1.0 : (aux < 0.0 ? -1.0 : 0.0), pos = sg * aux;
+            const double e = 1.0 / lam;
+            const double pw = pow(pos, e);
+            g = sg * pw;
+            const double pwm1 = pos > 0.0 ? pw / pos : (e == 1.0 ? 1.0 : (e > 1.0 ? 0.0 : INFINITY));   // pos^(1/lam - 1)
+            d = pwm1;                                     // (1/lam) pos^(1/lam - 1) * lam
+            if (pg) pg[slot] = (pos > 0.0 ? -sg * pw * log(pos) * e * e : 0.0) + e * pwm1 * f;
+            slot += 1;
+            if (L.flags & TGP_FLOW_ADD_F0) { g += f; d += 1.0; }
         } else {   // identity
             g = f; d = 1.0;
         }
@@ -159,7 +194,13 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
 }
 
 __device__ __forceinline__ int layer_nparams(const TgpFlowLayer& L) {
-    return L.kind == TGP_FLOW_TANH_STEP ? 4 * L.n_steps : (L.kind == TGP_FLOW_IDENTITY ? 0 : 2);
+    switch (L.kind) {
+        case TGP_FLOW_TANH_STEP: return 4 * L.n_steps;
+        case TGP_FLOW_IDENTITY: return 0;
+        case TGP_FLOW_ARCSINH: return 4;
+        case TGP_FLOW_BOXCOX: case TGP_FLOW_INV_BOXCOX: return 1;
+        default: return 2;
+    }
 }
 
 // torch.distributions.Normal(0,1).cdf: 0.5 * (1 + erf(x / sqrt(2)))

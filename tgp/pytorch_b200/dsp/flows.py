@@ -64,3 +64,70 @@ def StepTanhL(num_blocks, num_steps, **kwargs):
         blocks.append(('step_flow', {'flow_arr': steps, 'add_init_f0': addf0}))
         blocks.append(('affine', {'init_a': a_aff, 'init_b': b_aff, 'set_restrictions': False}))
     return blocks
+
+
+def BoxCoxL(num_blocks, **kwargs):
+    """num_blocks x [boxcox, affine] (reference flows.py:140-163)."""
+    set_res, addf0, init_random, constraint = common_config(kwargs)
+    blocks = []
+    for _ in range(num_blocks):
+        if init_random:
+            a_aff, b_aff = numpy.random.randn(2)
+            init_lam = numpy.random.randn(1) + 1.
+            constraint = None
+        else:
+            a_aff, b_aff, init_lam = 1.0, 0.0, 5.0
+        blocks.append(('boxcox', {'init_lam': init_lam, 'add_init_f0': addf0, 'constraint': constraint}))
+        blocks.append(('affine', {'init_a': a_aff, 'init_b': b_aff, 'set_restrictions': set_res}))
+    return blocks
+
+
+def InverseBoxCoxL(num_blocks, **kwargs):
+    """num_blocks x [inverseboxcox, affine] (reference flows.py:167-189)."""
+    set_res, addf0, init_random, constraint = common_config(kwargs)
+    blocks = []
+    for _ in range(num_blocks):
+        if init_random:
+            a_aff, b_aff = numpy.random.randn(2)
+            init_lam = numpy.random.randn(1) + 1.
+        else:
+            a_aff, b_aff, init_lam = 1.0, 0.0, 5.0
+        blocks.append(('inverseboxcox', {'init_lam': init_lam, 'add_init_f0': addf0, 'constraint': constraint}))
+        blocks.append(('affine', {'init_a': a_aff, 'init_b': b_aff, 'set_restrictions': set_res}))
+    return blocks
+
+
+def ArcSL(num_blocks, **kwargs):
+    """num_blocks x [arcsinh, affine] (reference flows.py:193-214)."""
+    set_res, addf0, init_random, _ = common_config(kwargs)
+    blocks = []
+    for _ in range(num_blocks):
+        if init_random:
+            a_aff, b_aff = numpy.random.randn(2)
+            a_arc, b_arc, c_arc, d_arc = numpy.random.randn(4)
+        else:
+            a_aff, b_aff = 1.0, 0.0
+            a_arc, b_arc, c_arc, d_arc = numpy.random.randn(4)
+            b_arc += 1
+            d_arc += 1
+        blocks.append(('arcsinh', {'init_a': a_arc, 'init_b': b_arc, 'init_c': c_arc, 'init_d': d_arc, 'add_init_f0': addf0,
+                                   'set_restrictions': set_res}))
+        blocks.append(('affine', {'init_a': a_aff, 'init_b': b_aff, 'set_restrictions': set_res}))
+    return blocks
+
+
+def build_chain(flow_combination, num_blocks, **kwargs):
+    """Combined chains of the reference's launch scripts (reference flows.py:71-109)."""
+    blocks = []
+    for _ in range(num_blocks):
+        if flow_combination == 'SAL_BCL':
+            blocks.extend(SAL(1)); blocks.extend(BoxCoxL(1, constraint=kwargs['constraint']))          # noqa: E702
+        elif flow_combination == 'SAL_InvBCL':
+            blocks.extend(SAL(1)); blocks.extend(InverseBoxCoxL(1, constraint=kwargs['constraint']))   # noqa: E702
+        elif flow_combination == 'SAL_AL':
+            blocks.extend(SAL(1)); blocks.extend(ArcSL(1))                                             # noqa: E702
+        elif flow_combination == 'BCL_AL':
+            blocks.extend(BoxCoxL(1, constraint=kwargs['constraint'])); blocks.extend(ArcSL(1))        # noqa: E702
+        elif flow_combination == 'InvBCL_AL':
+            blocks.extend(InverseBoxCoxL(1, constraint=kwargs['constraint'])); blocks.extend(ArcSL(1))  # noqa: E702
+    return blocks

@@ -30,9 +30,15 @@ def instance_flow(flow_list, is_composite=True):
             fl = TanhFlow(**init)
         elif name == 'step_flow':
             fl = StepFlow(**init)
+        elif name == 'arcsinh':
+            fl = ArcsinhFlow(**init)
+        elif name == 'boxcox':
+            fl = BoxCoxFlow(**init)
+        elif name in ('inverseboxcox', 'inverse_boxcox'):
+            fl = InverseBoxCoxFlow(**init)
         else:
-            raise ValueError('flow %r is outside the fused hot-path subset (identity, affine, tanh, sinh_arcsinh, '
-                             'step_flow); see DESIGN.md "out of scope"' % (name,))
+            raise ValueError('flow %r is outside the fused hot-path subset (identity, affine, tanh, sinh_arcsinh, step_flow, '
+                             'arcsinh, boxcox, inverseboxcox); see DESIGN.md "out of scope"' % (name,))
         built.append(fl)
     return CompositeFlow(built) if is_composite else built
 
@@ -148,6 +154,93 @@ class AffineFlow(Flow):
         if self._input_dependent and self.input_dependent:
             raise NotImplementedError()
         return [dict(kind='affine', restrict=bool(self.set_restrictions))], [self.a, self.b], []
+
+
+class ArcsinhFlow(Flow):
+    """fk = a + b*asinh((f0-c)/d) [+ f0]; b, d -> softplus under set_restrictions (reference flow.py:495-557)."""
+
+    def __init__(self, init_a, init_b, init_c, init_d, add_init_f0, set_restrictions):
+        super().__init__()
+        for n, val in zip('abcd', (init_a, init_b, init_c, init_d)):
+            setattr(self, n, nn.Parameter(torch.tensor(val, dtype=cg.dtype)))
+        self.set_restrictions = True if add_init_f0 else set_restrictions
+        self.add_init_f0 = add_init_f0
+
+    def asinh(self, f):
+        return torch.log(f + (f ** 2 + 1) ** 0.5)
+
+    def forward(self, f0, X=None):
+        b, d = (softplus(self.b), softplus(self.d)) if self.set_restrictions else (self.b, self.d)
+        fk = self.a + b * self.asinh((f0 - self.c) / d)
+        return fk + f0 if self.add_init_f0 else fk
+
+    def inverse(self, f):
+        b, d = (softplus(self.b), softplus(self.d)) if self.set_restrictions else (self.b, self.d)
+        return self.c + d * torch.sinh((f - self.a) / b)
+
+    def forward_initializer(self, X):
+        return 0.0
+
+    def turn_off_initializer_parameters(self):
+        pass
+
+    def describe(self, X=None, n_mc=1):
+        return ([dict(kind='arcsinh', restrict=bool(self.set_restrictions), add_f0=bool(self.add_init_f0))],
+                [self.a, self.b, self.c, self.d], [])
+
+
+class BoxCoxFlow(Flow):
+    """fk = (sgn(f0)|f0|^lam - 1)/lam [+ f0]; lam optionally through a user constraint (reference flow.py:377-421)."""
+
+    def __init__(self, init_lam, add_init_f0, constraint=None):
+        super().__init__()
+        self.lam = nn.Parameter(torch.tensor(init_lam, dtype=cg.dtype).reshape(()))
+        self.add_init_f0 = add_init_f0
+        self.constraint = constraint
+
+    def transform_param(self):
+        if self.constraint is None:
+            lam = self.lam
+            if lam == 0:
+                lam = lam + 1e-11
+        else:
+            lam = self.constraint(self.lam)
+        assert lam != 0, 'Invalid value for Box Cox parameter. This flow is not defined for values of lam == 0'
+        return lam
+
+    def forward(self, f0, X=None):
+        lam = self.transform_param()
+        sgn = torch.sign(f0)
+        fk = (sgn * torch.pow(sgn * f0, lam) - 1) / lam
+        return fk + f0 if self.add_init_f0 else fk
+
+    def forward_initializer(self, X):
+        return 0.0
+
+    def turn_off_initializer_parameters(self):
+        pass
+
+    _kind = 'boxcox'
+
+    def describe(self, X=None, n_mc=1):
+        # the kernel receives lam AFTER the constraint; autograd carries the gradient back through the constraint
+        return [dict(kind=self._kind, add_f0=bool(self.add_init_f0))], [self.transform_param()], []
+
+
+class InverseBoxCoxFlow(BoxCoxFlow):
+    """fk = sgn(lam*f0+1)|lam*f0+1|^(1/lam) [+ f0] (reference flow.py:423-446)."""
+
+    _kind = 'invboxcox'
+
+    def __init__(self, init_lam, add_init_f0, constraint=None):
+        super().__init__(init_lam, add_init_f0, constraint)
+
+    def forward(self, f0, X=None):
+        lam = self.transform_param()
+        aux = lam * f0 + 1
+        sgn = torch.sign(aux)
+        fk = sgn * torch.pow(sgn * aux, 1. / lam)
+        return fk + f0 if self.add_init_f0 else fk
 
 
 def _mlp(input_dim, cfg, n_out_nets):

@@ -11,7 +11,8 @@ import torch
 from . import _lib
 
 _KIND = {'identity': _lib.FLOW_IDENTITY, 'affine': _lib.FLOW_AFFINE, 'tanh_step': _lib.FLOW_TANH_STEP,
-         'sal': _lib.FLOW_SAL}
+         'sal': _lib.FLOW_SAL, 'arcsinh': _lib.FLOW_ARCSINH, 'boxcox': _lib.FLOW_BOXCOX, 'invboxcox': _lib.FLOW_INV_BOXCOX}
+_NPAR = {'affine': 2, 'sal': 2, 'arcsinh': 4, 'boxcox': 1, 'invboxcox': 1}
 _LIK = {'gauss_linear': _lib.LIK_GAUSS_LINEAR, 'gauss_nonlinear': _lib.LIK_GAUSS_NONLINEAR,
         'bernoulli': _lib.LIK_BERNOULLI}
 
@@ -21,8 +22,9 @@ class FlowLayout:
 
     `layers`: list of dicts {kind, restrict, add_f0, n_steps, per_row}.  Global parameters of all layers are packed
     in descriptor order into `theta`; per-row (input-dependent) parameters into the columns of a (R, n_rowparams)
-    matrix.  Parameter order inside a layer: affine [a, b]; tanh_step n_steps x [a, b, c, d]; sal [a, b]
-    (reference code/dsp/models/flow.py:330-340, 755-773, 965-977).
+    matrix.  Parameter order inside a layer: affine [a, b]; tanh_step n_steps x [a, b, c, d]; sal [a, b]; arcsinh
+    [a, b, c, d]; boxcox / invboxcox [lam after the module's constraint]
+    (reference code/dsp/models/flow.py:330-340, 377-446, 495-557, 755-773, 965-977).
     """
 
     def __init__(self, layers):
@@ -33,7 +35,7 @@ class FlowLayout:
             kind = lay['kind']
             if kind == 'identity':
                 continue
-            npar = 4 * lay.get('n_steps', 0) if kind == 'tanh_step' else 2
+            npar = 4 * lay.get('n_steps', 0) if kind == 'tanh_step' else _NPAR[kind]
             per_row = bool(lay.get('per_row', False))
             p0 = self.n_rowparams if per_row else self.n_theta
             if per_row:
