@@ -42,6 +42,7 @@ for compute in sys.argv[1:] or ['f64', 'i8crt', 'tf32x3']:
         eng.qf_backward(xb, g_mu, g_v, rb)
     t_fb, _ = timed(bwd)
     t_chain, _ = timed(lambda: eng.chain_backward(rb, 1.0, -1.0))
-    t_test, _ = timed(lambda: eng.test_rows(mu, v, yb, None, 1, 1.0))
+    bstd = v.std().reshape(1) if WL['likelihood'] == 'bernoulli' else None
+    t_test, _ = timed(lambda: eng.test_rows(mu, v, yb, None, 1, 1.0, bstd))
     print('%-13s prepare %.3f  qf_forward %.3f  ell %.3f  qf_backward %.3f  chain %.3f  test_rows %.3f  | sum %.3f ms'
           % (label, t_prep, t_fwd, t_ell, t_fb - t_fwd, t_chain, t_test, t_prep + t_fwd + t_ell + (t_fb - t_fwd) + t_chain))

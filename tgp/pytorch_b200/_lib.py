@@ -16,6 +16,7 @@ MAX_LAYERS = 64
 OPT_FUSED_FORWARD = 1
 OPT_ROW_CHUNK = 2
 OPT_OVERLAP_KGEN = 3
+OPT_FUSED_KBAR_GRADS = 4
 
 
 class TgpFlowLayer(C.Structure):

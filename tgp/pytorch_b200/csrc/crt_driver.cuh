@@ -9,6 +9,7 @@
 #include "gemm_i8.cuh"
 
 namespace tgp {
+extern int g_fused_kbar_grads;
 namespace crt {
 
 using i8::Planes;
@@ -152,6 +153,22 @@ inline int combine(const uint8_t* R, long ldr, long plane_stride, long rows, int
     return check_launch("k_crt_combine");
 }
 
+inline int combine_kgrads(const uint8_t* R, long ldr, long plane_stride, long rows, int M, int T, int bits2, const int* ea, const int* eb,
+                          const double* Kval, long ldk, const double* X, const double* Zs, const double* ls, const double* os, int D,
+                          double* dZ, double* dls, double* dos, cudaStream_t st) {
+    // opt-in (TGP_OPT_FUSED_KBAR_GRADS): measured at cfg4 the fused kernel needs 255 registers (one CTA per SM) and takes 0.45 ms per
+    // 16384-row chunk against 0.20 + 0.15 ms for reconstruction + stand-alone gradient kernel, so the two-kernel form is the default
+    if (!g_fused_kbar_grads || D > 16 || (T != 15 && T != 16)) return -7;
+    const i8::CrtTable& tab = i8::crt_table(T);
+    dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rows, i8::KG_RB));
+#define TGP_CK(TT, MD) i8::k_crt_combine_kgrads<TT, MD><<<grid, 256, 0, st>>>(R, ldr, plane_stride, rows, M, tab, bits2, ea, eb, Kval, ldk, X, \
+                                                                            Zs, ls, os, D, dZ, dls, dos)
+    if (T == 15) { if (D <= 4) TGP_CK(15, 4); else if (D <= 8) TGP_CK(15, 8); else TGP_CK(15, 16); }
+    else { if (D <= 4) TGP_CK(16, 4); else if (D <= 8) TGP_CK(16, 8); else TGP_CK(16, 16); }
+#undef TGP_CK
+    return check_launch("k_crt_combine_kgrads");
+}
+
 // K_xz of a row chunk in one pass: FP64 values and residue planes (i8::k_rbf_residues)
 inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
                         int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st, int ctas_per_sm = 3) {
@@ -285,9 +302,15 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
             Planes A{b.Op, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
             Planes B{sp.Wc, 2L * M, M, sp.ldk, 2L * M * sp.ldk};
             TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
-            TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, 0, sp.w_col_exp, 1, b.Kbar, M, 0, 0, st));
         }
-        TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
+        // reconstruction of Kbar fused with Kbar o K -> dZ, dlengthscale, doutputscale (Kbar is never written); wider inputs
+        // reconstruct into the staging buffer and run the stand-alone gradient kernel
+        const int fr = combine_kgrads(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, sp.w_col_exp, b.Kbuf + r0 * M, M,
+                                      X + r0 * D, s.Zs, s.ls, s.os, D, dZ, dls, dos, st);
+        if (fr == -7) {
+            TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, 0, sp.w_col_exp, 1, b.Kbar, M, 0, 0, st));
+            TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
+        } else if (fr != 0) return fr;
         {   // [Gbar; Cbar] (2M x M) += ABbar^T K: reduction over the chunk rows; both operands are row-major planes read MN-major
             i8::Params p{};
             p.Mrows = 2 * M; p.Ncols = M; p.K = rc; p.T = Tw; p.tri_mode = 0; p.tri_rows = 0; p.lower_rows = M; p.mn_major = 3;
