@@ -211,6 +211,16 @@ int tgp_test_nll_fwd(TgpHandle* h, const TgpParams* params, const TgpBatch* batc
                      const double* bern_std, void* logp_rows, void* m1, void* m2, void* mu, void* v, int* status,
                      void* stream);
 
+/* ---- optimiser step next to the path ---------------------------------------------------------------
+ * Adam / AdamW-style update of ALL parameter tensors in one launch, with torch.optim.Adam's arithmetic (trainer_base.py:342
+ * via optimizers.py:10-22): g += wd p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) /
+ * sqrt(1 - b2^t) + eps).  The step count t lives in DEVICE memory and is incremented by the kernel (graph-replay safe).
+ * Tables (device): per tensor the addresses of param / grad / exp_avg / exp_avg_sq (n_tensors x 4 pointers, row-major), its
+ * element count, learning rate and weight decay; per 4096-element block its tensor index and element offset.  All FP64. */
+int tgp_adam_step(int n_tensors, long n_blocks, const void* const* ptr_table, const long* sizes, const double* lr,
+                  const double* weight_decay, const int* block_tensor, const long* block_offset, double beta1, double beta2,
+                  double eps, long* step_dev, void* stream);
+
 /* Library options.  TGP_OPT_FUSED_FORWARD (tensor-core mode): 1 = tgp_qf_forward is ONE kernel that generates the K_xz
  * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels.
  * TGP_OPT_ROW_CHUNK (FP64 mode): rows per launch of the batch contractions (default 32768; a tuning knob — it changes the

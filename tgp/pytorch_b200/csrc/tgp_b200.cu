@@ -637,6 +637,46 @@ int tgp_test_nll_fwd(TgpHandle* h, const TgpParams* p, const TgpBatch* b, int re
                          m2, stream);
 }
 
+namespace tgp {
+constexpr int ADAM_BLOCK = 4096;
+__global__ void __launch_bounds__(256) k_adam(const void* const* __restrict__ tab, const long* __restrict__ sizes,
+                                              const double* __restrict__ lr, const double* __restrict__ wd,
+                                              const int* __restrict__ block_tensor, const long* __restrict__ block_offset,
+                                              double beta1, double beta2, double eps, const long* __restrict__ step_dev) {
+    const int t = block_tensor[blockIdx.x];
+    const long off = block_offset[blockIdx.x], n = sizes[t];
+    double* p = (double*)tab[4 * t];
+    const double* g = (const double*)tab[4 * t + 1];
+    double* m = (double*)tab[4 * t + 2];
+    double* v = (double*)tab[4 * t + 3];
+    const double step = (double)(step_dev[0] + 1);                 // this update's count; k_adam_count bumps it afterwards
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    const double step_size = lr[t] / bc1, rsq2 = 1.0 / sqrt(bc2), w = wd[t];
+    for (long i = off + threadIdx.x; i < min(off + (long)ADAM_BLOCK, n); i += 256) {
+        const double pi = p[i];
+        const double gi = g[i] + w * pi;
+        const double mi = beta1 * m[i] + (1.0 - beta1) * gi;       // torch: exp_avg.lerp_(grad, 1 - beta1)
+        const double vi = beta2 * v[i] + (1.0 - beta2) * gi * gi;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        m[i] = mi; v[i] = vi;
+        p[i] = pi - step_size * (mi / (sqrt(vi) * rsq2 + eps));    // param.addcdiv_(exp_avg, denom, value=-step_size)
+    }
+}
+__global__ void k_adam_count(long* step_dev) { step_dev[0] += 1; }
+}  // namespace tgp
+
+int tgp_adam_step(int n_tensors, long n_blocks, const void* const* ptr_table, const long* sizes, const double* lr,
+                  const double* weight_decay, const int* block_tensor, const long* block_offset, double beta1, double beta2,
+                  double eps, long* step_dev, void* stream) {
+    if (n_tensors <= 0 || n_blocks <= 0) return 0;
+    if (!ptr_table || !sizes || !lr || !weight_decay || !block_tensor || !block_offset || !step_dev)
+        return set_error(-1, "NULL argument to tgp_adam_step");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_adam<<<(unsigned)n_blocks, 256, 0, st>>>(ptr_table, sizes, lr, weight_decay, block_tensor, block_offset, beta1, beta2, eps, step_dev);
+    TGP_TRY(check_launch("k_adam"));
+    k_adam_count<<<1, 1, 0, st>>>(step_dev);
+    return check_launch("k_adam_count");
+}
+
 long tgp_launch_count(void) { return g_launch_count; }
 
 int tgp_set_option(int key, int value) {
