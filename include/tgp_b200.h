@@ -129,6 +129,16 @@ int tgp_chain_backward(const TgpModel* model, const TgpParams* params, void* ste
                        double gE, double gK, const double* g_dev, void* dZ, void* draw_lengthscale, void* draw_outputscale, void* dm,
                        void* dL_raw, void* dlog_var_noise, void* dtheta, void* stream);
 
+/* Posterior-predictive samples and 95 % interval coverage per row, from the marginals (mu, v) of the test-NLL pass — replaces
+ * sample_from_predictive_distribution (sparse_MF_SP.py:886-992: S x the cost of q(f)) + numpy.quantile + the coverage count of
+ * trainers_regression.py:181-224.  Gaussian likelihoods only.  S <= 128 samples per row (Philox stream: seed, *offset_dev, which
+ * the call advances); q_lo / q_hi: numpy.quantile-interpolated quantiles at q_lo_p / q_hi_p; covered: 1.0 where q_lo <= y <= q_hi;
+ * samples (optional, R x S); count (optional device double): += covered rows.  rowparams: (R, n_mc, n_rowparams), n_mc in {1, S}. */
+int tgp_coverage_rows(const TgpModel* model, const TgpParams* params, const void* mu, const void* v, const void* Y,
+                      const void* rowparams, long R, int n_mc, int S, unsigned long long seed, unsigned long long* offset_dev,
+                      double q_lo_p, double q_hi_p, void* q_lo, void* q_hi, void* covered, void* samples, double* count,
+                      void* stream);
+
 /* The exchange format of the one collective per step.  The reduce buffer holds two (padded) M x M blocks
  * of which only the lower triangles are populated in TGP_F64 mode (Gbar and dL_S; in TGP_F32 mode the second block, Cbar,
  * is dense): tgp_reduce_pack gathers [small vector | tril(Gbar) | tril or full second block] into `packed`

@@ -9,6 +9,7 @@
 #include "tc_driver.cuh"
 #include "flow_mlp.cuh"
 #include "crt_driver.cuh"
+#include "eval_kernels.cuh"
 
 namespace tgp {
 char g_last_error[512] = "";
@@ -447,6 +448,32 @@ int tgp_test_rows(const TgpModel* md, const TgpParams* p, const void* mu, const 
     fill_flow(a.flow, md);
     k_row_test<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(a);
     return check_launch("k_row_test");
+}
+
+int tgp_coverage_rows(const TgpModel* md, const TgpParams* p, const void* mu, const void* v, const void* Y, const void* rowparams,
+                      long R, int n_mc, int S, unsigned long long seed, unsigned long long* offset_dev, double q_lo_p, double q_hi_p,
+                      void* q_lo, void* q_hi, void* covered, void* samples, double* count, void* stream) {
+    TGP_TRY(validate(md));
+    if (R <= 0) return 0;
+    if (md->likelihood == TGP_LIK_BERNOULLI) return set_error(-1, "coverage intervals are defined for the Gaussian likelihoods");
+    if (!p || !mu || !v || !Y || !q_lo || !q_hi || !covered || !p->log_var_noise) return set_error(-1, "NULL argument to tgp_coverage_rows");
+    if (S < 2 || S > 128) return set_error(-1, "S must be in 2..128");
+    if (n_mc != 1 && n_mc != S) return set_error(-1, "n_mc must be 1 or S");
+    if (md->n_rowparams > 0 && !rowparams) return set_error(-1, "rowparams required for input-dependent flows");
+    RowCoverArgs a;
+    a.R = (int)R; a.n_rowp = md->n_rowparams; a.n_mc = n_mc; a.S = S;
+    a.mu = (const double*)mu; a.v = (const double*)v; a.y = (const double*)Y; a.log_var_noise = (const double*)p->log_var_noise;
+    a.theta = (const double*)p->theta; a.rowp = md->n_rowparams > 0 ? (const double*)rowparams : nullptr;
+    a.seed = seed; a.offset_dev = offset_dev; a.q_lo_p = q_lo_p; a.q_hi_p = q_hi_p;
+    a.q_lo = (double*)q_lo; a.q_hi = (double*)q_hi; a.covered = (double*)covered; a.samples = (double*)samples; a.count = count;
+    fill_flow(a.flow, md);
+    k_row_coverage<<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(a);
+    TGP_TRY(check_launch("k_row_coverage"));
+    if (offset_dev) {
+        k_bump_offset<<<1, 1, 0, (cudaStream_t)stream>>>(offset_dev);
+        TGP_TRY(check_launch("k_bump_offset"));
+    }
+    return 0;
 }
 
 int tgp_reduce_pack(const TgpModel* md, const double* reduce_buf, double* packed, void* stream) {

@@ -85,3 +85,19 @@ def test_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X, y_std=1.0, n
             y = torch.zeros(R, dtype=torch.float64, device=dev)
         return eng.test_rows(mu.double().contiguous(), v.double().contiguous(), y.double().contiguous(), rowp, n_mc, y_std,
                              None if bern_std is None else bern_std.double())
+
+
+def coverage_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X, S, n_mc=1, seed=0, want_samples=False):
+    """S posterior-predictive samples per row, their 2.5 % / 97.5 % quantiles and the coverage indicator of y (forward only)."""
+    with torch.no_grad():
+        layout, theta, rowp = flow_pack(flow, X, n_mc) if likelihood != 'gauss_linear' else (FlowLayout([]), None, None)
+        eng = row_engine(likelihood, n_quad, layout, mu.device)
+        dev = mu.device
+        z = torch.zeros(1, dtype=torch.float64, device=dev)
+        eng.set_params(torch.zeros(1, 1, dtype=torch.float64, device=dev), z, z, z, torch.ones(1, 1, dtype=torch.float64, device=dev),
+                       log_var_noise.detach().reshape(1).to(torch.float64).contiguous(), None if theta is None else theta.detach().contiguous())
+        R = mu.shape[0]
+        if rowp is not None:
+            rowp = rowp.reshape(n_mc, R, -1).permute(1, 0, 2).contiguous()
+        return eng.coverage_rows(mu.double().contiguous(), v.double().contiguous(), y.double().contiguous(), rowp, n_mc, S, seed,
+                                 want_samples=want_samples)

@@ -371,6 +371,40 @@ class sparse_MF_SP(nn.Module):
         self.train()
         return log_p_y, predictive_params
 
+    def evaluation_bundle(self, X, Y, Y_std, S=100, S_MC_NNet=None, seed=None, want_samples=False):
+        """Everything `Trainer_GP_regression.performance_metrics` (reference trainers_regression.py:317-338, 181-224) derives from a
+        test batch, from ONE q(f) evaluation: test log-likelihood and predictive moments (`test_log_likelihood`), plus the
+        posterior-predictive 95 % interval coverage for which the reference re-runs q(f) on a 100x-repeated X
+        (`sample_from_predictive_distribution`, sparse_MF_SP.py:939-992) and calls numpy.quantile on the host.
+
+        Returns a dict: log_p_y (Dy,), m1 / m2 (Dy, MB), sq_err (Dy,) = sum_n (m1 - y)^2, coverage (Dy,) = number of rows whose y
+        lies in the [2.5 %, 97.5 %] interval of S predictive samples, q_lo / q_hi (Dy, MB) and optionally samples (Dy, MB, S).
+        Gaussian likelihoods; input-dependent flows draw one dropout mask per sample when the model is fully Bayesian."""
+        assert not self.is_training, 'This method only works in eval mode'
+        lik = self.likelihood
+        if isinstance(lik, Bernoulli):
+            raise NotImplementedError('interval coverage is defined for the Gaussian likelihoods (regression)')
+        kind = _LIK_KIND[type(lik)]
+        log_p_y, (m1, m2) = self.test_log_likelihood(X, Y, return_moments=True, Y_std=Y_std, S_MC_NNet=S_MC_NNet)
+        X_run = self._rows3(X)
+        self._eval_mode()
+        out = dict(log_p_y=log_p_y, m1=m1, m2=m2, sq_err=((m1.reshape(self.out_dim, -1) - Y.t()) ** 2).sum(1))
+        cov, qlo, qhi, smp = [], [], [], []
+        with torch.no_grad():
+            mean_q_f, cov_q_f = self.marginal_variational_qf_parameters(X_run, diagonal=True, is_duvenaud=False)   # cached factorisation
+            n_mc = S if (self.fully_bayesian and kind == 'gauss_nonlinear') else 1
+            for dy in range(self.out_dim):
+                Xr = X_run[dy].repeat(n_mc, 1) if n_mc > 1 else X_run[dy]
+                a, b, c, s = _rows.coverage_rows(kind, self.quad_points, Y[:, dy].to(torch.float64), mean_q_f[dy, :, 0], cov_q_f[dy, :, 0],
+                                                 self._noise(dy), None if kind == 'gauss_linear' else self.G_matrix[dy], Xr, S, n_mc=n_mc,
+                                                 seed=cg.config_seed if seed is None else seed, want_samples=want_samples)
+                qlo.append(a); qhi.append(b); cov.append(c.sum()); smp.append(s)     # noqa: E702
+        self.train()
+        out.update(coverage=torch.stack(cov), q_lo=torch.stack(qlo), q_hi=torch.stack(qhi))
+        if want_samples:
+            out['samples'] = torch.stack(smp)
+        return out
+
     # ---- sampling (caller-side utilities; element-wise torch ops on the kernel outputs) --------------------------
     def sample_from_variational_marginal_base(self, X, diagonal, is_duvenaud, init_Z=None):
         if not diagonal:

@@ -280,6 +280,25 @@ class Engine:
         return logp, m1, m2
 
     @_on_device
+    def coverage_rows(self, mu, v, Y, rowparams, n_mc, S, seed=0, q=(0.025, 0.975), want_samples=False):
+        """Posterior-predictive samples + interval coverage from given marginals (tgp_coverage_rows).
+        -> (q_lo, q_hi, covered, samples or None)."""
+        R = mu.shape[0]
+        _chk(mu, 'mu', (R,)); _chk(v, 'v', (R,)); _chk(Y, 'Y', (R,))
+        nrp = self.flow.n_rowparams
+        if nrp:
+            _chk(rowparams, 'rowparams', (R, n_mc, nrp))
+        f64 = torch.float64
+        qlo, qhi, cov = (torch.empty(R, dtype=f64, device=self.device) for _ in range(3))
+        smp = torch.empty(R, S, dtype=f64, device=self.device) if want_samples else None
+        if getattr(self, '_cov_offset', None) is None:
+            self._cov_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.tgp_coverage_rows(self.model, self._params, _ptr(mu), _ptr(v), _ptr(Y), _ptr(rowparams) if nrp else None, R,
+                                              int(n_mc), int(S), int(seed) % (1 << 64), _ptr(self._cov_offset), float(q[0]), float(q[1]),
+                                              _ptr(qlo), _ptr(qhi), _ptr(cov), _ptr(smp), None, _stream(self.device)), 'tgp_coverage_rows')
+        return qlo, qhi, cov, smp
+
+    @_on_device
     def export_step(self):
         M = self.M
         L, Li, Cm = (torch.empty(M, M, dtype=torch.float64, device=self.device) for _ in range(3))
