@@ -231,6 +231,13 @@ int tgp_adam_step(int n_tensors, long n_blocks, const void* const* ptr_table, co
                   const double* weight_decay, const int* block_tensor, const long* block_offset, double beta1, double beta2,
                   double eps, long* step_dev, void* stream);
 
+/* ---- inducing-point initialisation next to the path -------------------------------------------------
+ * One Lloyd iteration of k-means on the device (reference: Z = KMEANS(X_tr, M), utils.py:143-159 / main.py:145, sklearn on the
+ * host).  X (N, D) FP64, centroids C (M, D) updated in place when update != 0; assign (N) int32 or NULL; scratch: sums (M, D),
+ * counts (M), inertia (1) — zeroed by the call; inertia[0] = sum of squared distances to the nearest OLD centroid.  D <= 32. */
+int tgp_kmeans_iteration(const void* X, long N, int D, void* C, int M, int* assign, double* sums, double* counts,
+                         double* inertia, int update, void* stream);
+
 /* Library options.  TGP_OPT_FUSED_FORWARD (tensor-core mode): 1 = tgp_qf_forward is ONE kernel that generates the K_xz
  * tiles inside the tcgen05 contraction and emits mu, v from the TMEM accumulators; 0 = staged planes + separate kernels.
  * TGP_OPT_ROW_CHUNK (FP64 mode): rows per launch of the batch contractions (default 32768; a tuning knob — it changes the

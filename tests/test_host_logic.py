@@ -132,3 +132,29 @@ def test_library_options_and_workspace_sizing_without_a_gpu():
         assert lib.tgp_set_option(99, 1) != 0
     finally:
         assert lib.tgp_set_option(_lib.OPT_ROW_CHUNK, 32768) == 0
+
+
+def test_split_csv_reader_standardises_like_the_reference(tmp_path):
+    """data.load_split_csv: the airline-style on-disk format (header-less CSV + splits_idx pickle,
+    regression_datasets.py:95-192) with the training-statistics standardisation of data.py:260-299."""
+    import pickle
+    import numpy as np
+    from tgp.pytorch_b200.data import load_split_csv
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(200, 6)) * np.array([1, 10, 0.1, 5, 2, 3]) + np.array([0, 5, -1, 2, 0, 7])
+    csv = tmp_path / 'airline.csv'
+    np.savetxt(csv, data, delimiter=',')
+    perm = rng.permutation(200)
+    with open(tmp_path / 'splits_idx_airline.pkl', 'wb') as fh:
+        pickle.dump({'seed_3': {'train': perm[:150], 'test': perm[150:]}}, fh)
+    X_tr, Y_tr, X_te, Y_te, Y_std = load_split_csv(str(csv), str(tmp_path / 'splits_idx_airline.pkl'), 3)
+    raw = np.loadtxt(csv, delimiter=',')
+    tr, te = raw[perm[:150]], raw[perm[150:]]
+    xm, xs = tr[:, :-1].mean(0), tr[:, :-1].std(0) + 1e-15
+    ym, ys = tr[:, -1].mean(), tr[:, -1].std() + 1e-15
+    assert np.allclose(X_tr.numpy(), (tr[:, :-1] - xm) / xs, rtol=0, atol=1e-14)
+    assert np.allclose(X_te.numpy(), (te[:, :-1] - xm) / xs, rtol=0, atol=1e-14)
+    assert np.allclose(Y_te.numpy()[:, 0], (te[:, -1] - ym) / ys, rtol=0, atol=1e-14)
+    assert abs(float(Y_std) - ys) < 1e-15 and Y_tr.shape == (150, 1)
+    with pytest.raises(ValueError, match='md5'):
+        load_split_csv(str(csv), str(tmp_path / 'splits_idx_airline.pkl'), 3, md5sum='0' * 32)

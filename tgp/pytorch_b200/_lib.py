@@ -95,6 +95,7 @@ SIGNATURES = {
     'tgp_flow_mlp_forward': (_I, [C.POINTER(TgpMlp), _P, _P, _L, _P, _P, C.c_ulonglong, _P, _P, _P]),
     'tgp_flow_mlp_backward': (_I, [C.POINTER(TgpMlp), _P, _P, _L, _P, _P, _P, _P]),
     'tgp_adam_step': (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _D, _D, _D, _P, _P]),
+    'tgp_kmeans_iteration': (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
     'tgp_set_option': (_I, [_I, _I]),
     'tgp_launch_count': (_L, []),
     'tgp_gemm_timing': (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_long)]),

@@ -10,6 +10,7 @@
 #include "flow_mlp.cuh"
 #include "crt_driver.cuh"
 #include "eval_kernels.cuh"
+#include "kmeans.cuh"
 
 namespace tgp {
 char g_last_error[512] = "";
@@ -702,6 +703,13 @@ int tgp_adam_step(int n_tensors, long n_blocks, const void* const* ptr_table, co
     TGP_TRY(check_launch("k_adam"));
     k_adam_count<<<1, 1, 0, st>>>(step_dev);
     return check_launch("k_adam_count");
+}
+
+int tgp_kmeans_iteration(const void* X, long N, int D, void* Cc, int M, int* assign, double* sums, double* counts, double* inertia,
+                         int update, void* stream) {
+    if (!X || !Cc || !sums || !counts || !inertia) return set_error(-1, "NULL argument to tgp_kmeans_iteration");
+    if (N < 1 || M < 1 || D < 1) return set_error(-1, "N, M, D must be positive");
+    return kmeans_iteration((const double*)X, N, D, (double*)Cc, M, assign, sums, counts, inertia, update, (cudaStream_t)stream);
 }
 
 long tgp_launch_count(void) { return g_launch_count; }

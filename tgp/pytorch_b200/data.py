@@ -85,3 +85,38 @@ class PinnedMinibatchStager:
         if k is not None:
             self._consumed[k].record(torch.cuda.current_stream(self.device))
             self._pending_release = None
+
+
+def load_split_csv(csv_path, split_pickle, seed, md5sum=None, sep=',', label_index=-1, pin=False):
+    """Reader of the reference's large regression sets (airline: code/dsp/data/regression_datasets.py:95-192; the same on-disk
+    format as its UCI sets): a header-less CSV whose `label_index` column is the target, plus `splits_idx_<name>.pkl` =
+    {'seed_<k>': {'train': idx, 'test': idx}}.  Returns (X_tr, Y_tr, X_te, Y_te, Y_std) as FP64 torch tensors standardised with
+    the TRAINING statistics exactly as `standard_normalization` does (data.py:260-299: numpy mean / std (ddof 0) + 1e-15),
+    optionally in pinned host memory — the form `PinnedMinibatchStager` feeds from."""
+    import hashlib
+    import pickle
+    import numpy as np
+    import pandas as pd
+    if md5sum is not None:
+        h = hashlib.md5()
+        with open(csv_path, 'rb') as fh:
+            for chunk in iter(lambda: fh.read(1 << 20), b''):
+                h.update(chunk)
+        if h.hexdigest() != md5sum:
+            raise ValueError('Dataset %s is corrupted or has not been downloaded (md5 mismatch)' % csv_path)
+    data = pd.read_csv(csv_path, sep=sep, header=None).to_numpy(dtype=np.float64)
+    with open(split_pickle, 'rb') as fh:
+        split = pickle.load(fh)['seed_%d' % seed]
+    tr, te = np.asarray(split['train']), np.asarray(split['test'])
+    cols = np.ones(data.shape[1], dtype=bool)
+    cols[label_index] = False
+    X_tr, X_te = data[tr][:, cols], data[te][:, cols]
+    Y_tr, Y_te = data[tr][:, label_index].reshape(-1, 1), data[te][:, label_index].reshape(-1, 1)
+    eps = 1e-15
+    x_mean, x_std = X_tr.mean(0), X_tr.std(0) + eps
+    y_mean, y_std = Y_tr.mean(0), Y_tr.std(0) + eps
+    out = [torch.tensor((X_tr - x_mean) / x_std), torch.tensor((Y_tr - y_mean) / y_std),
+           torch.tensor((X_te - x_mean) / x_std), torch.tensor((Y_te - y_mean) / y_std)]
+    if pin and torch.cuda.is_available():
+        out = [t.pin_memory() for t in out]
+    return out[0], out[1], out[2], out[3], torch.tensor(y_std)
