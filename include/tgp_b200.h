@@ -33,16 +33,23 @@ enum { TGP_FLOW_IDENTITY = 0,        /* models/flow.py:296-307                  
                                       * (RESTRICT: softplus on b and d; asinh(u) = log(u + sqrt(u^2 + 1)))  */
        TGP_FLOW_BOXCOX = 5,          /* models/flow.py:377-421  (sgn(f)|f|^lam - 1) / lam   params [lam] — the
                                       * value AFTER the module's constraint (transform_param, :398-409)     */
-       TGP_FLOW_INV_BOXCOX = 6 };    /* models/flow.py:423-446  sgn(lam f + 1)|lam f + 1|^(1/lam)  params [lam] */
+       TGP_FLOW_INV_BOXCOX = 6,      /* models/flow.py:423-446  sgn(lam f + 1)|lam f + 1|^(1/lam)  params [lam] */
+       TGP_FLOW_STEP_GROUP = 7 };    /* models/flow.py:1039-1103 StepFlow over arbitrary members: header layer, no
+                                      * parameters; the next n_steps layers are evaluated at the header's input and
+                                      * summed (+ the input with TGP_FLOW_ADD_F0 on the header).  Members: any kind
+                                      * except AFFINE / STEP_GROUP (a single tanh is TANH_STEP with n_steps = 1)      */
 enum { TGP_FLOW_RESTRICT = 1,        /* set_restrictions: softplus on a (affine) / b (sinh-arcsinh)         */
        TGP_FLOW_ADD_F0 = 2,          /* add_init_f0                                                         */
-       TGP_FLOW_PER_ROW = 4 };       /* parameters come from the per-row matrix (input-dependent flow)      */
+       TGP_FLOW_PER_ROW = 4,         /* parameters come from the per-row matrix (input-dependent flow)      */
+       TGP_FLOW_SWITCH = 8 };        /* step member with a trainable switch_off (models/flow.py:1130-1149): two more
+                                      * GLOBAL parameters [s, t] after the layer's own; output softplus(s) g + t.
+                                      * Not combinable with TGP_FLOW_PER_ROW                                  */
 #define TGP_MAX_LAYERS 64
 
 typedef struct TgpFlowLayer {
     int kind;      /* TGP_FLOW_*                                                     */
     int flags;     /* TGP_FLOW_RESTRICT | TGP_FLOW_ADD_F0 | TGP_FLOW_PER_ROW         */
-    int n_steps;   /* TANH_STEP: number of tanh terms                                */
+    int n_steps;   /* TANH_STEP: number of tanh terms; STEP_GROUP: number of members */
     int p0;        /* first parameter: index into theta, or column of the row matrix */
 } TgpFlowLayer;
 

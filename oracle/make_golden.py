@@ -23,7 +23,8 @@ from dsp.models import instance_kernel, sparse_MF_SP, sparse_MF_GP  # noqa: E402
 from dsp.models.flow import (instance_flow, AffineFlow, StepFlow, TanhFlow, Sinh_ArcsinhFlow,  # noqa: E402
                              IdentityFlow, CompositeFlow, ArcsinhFlow, BoxCoxFlow, InverseBoxCoxFlow)
 from dsp.likelihoods import GaussianNonLinearMean, GaussianLinearMean, Bernoulli  # noqa: E402
-from dsp.flows import SAL, StepTanhL, ArcSL, BoxCoxL, InverseBoxCoxL, build_chain  # noqa: E402
+from dsp.flows import (SAL, StepTanhL, ArcSL, BoxCoxL, InverseBoxCoxL, build_chain,  # noqa: E402
+                       StepSAL, StepArcSL, StepBoxCoxL, StepInverseBoxCoxL, StepAllL)
 
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 UCI = os.path.join(os.environ.get('TGP_REFERENCE_ROOT', '/root/reference'), 'code', 'datasets', 'regression', 'uci')
@@ -113,18 +114,37 @@ def flow_to_spec(flow, store, X=None, prefix='fl'):
         store[k] = t.detach().cpu().numpy().astype(np.float64)
         return k
 
+    def member(sub):
+        if isinstance(sub, TanhFlow):
+            assert sub.set_restrictions and not sub.input_dependent
+            assert not sub.add_init_f0
+            return ['tanh_step', [[put(sub.a), put(sub.b), put(sub.c), put(sub.d)]], False]
+        if isinstance(sub, ArcsinhFlow):
+            return ['arcsinh', put(sub.a), put(sub.b), put(sub.c), put(sub.d), bool(sub.set_restrictions), bool(sub.add_init_f0)]
+        if isinstance(sub, BoxCoxFlow):
+            return ['invboxcox' if isinstance(sub, InverseBoxCoxFlow) else 'boxcox', put(sub.transform_param()),
+                    bool(sub.add_init_f0)]
+        if isinstance(sub, Sinh_ArcsinhFlow):
+            assert not sub.input_dependent
+            return ['sal', put(sub.a), put(sub.b), bool(sub.set_restrictions), bool(sub.add_init_f0)]
+        raise NotImplementedError(type(sub))
+
     for fl in flow.flow_arr:
         if isinstance(fl, IdentityFlow):
             spec.append(['identity'])
         elif isinstance(fl, AffineFlow):
             spec.append(['affine', put(fl.a), put(fl.b), bool(fl.set_restrictions)])
-        elif isinstance(fl, StepFlow):
+        elif isinstance(fl, StepFlow) and all(isinstance(s, TanhFlow) for s in fl.flow_arr):
             steps = []
             for sw, sub in zip(fl.switch_off, fl.flow_arr):
                 assert isinstance(sub, TanhFlow) and not sw.is_trainable and sub.set_restrictions
                 assert not sub.add_init_f0 and not sub.input_dependent
                 steps.append([put(sub.a), put(sub.b), put(sub.c), put(sub.d)])
             spec.append(['tanh_step', steps, bool(fl.add_init_f0)])
+        elif isinstance(fl, StepFlow):               # general linear combination, members behind their switch_off
+            members = [[member(sub), [put(sw.a), put(sw.b)] if sw.is_trainable else None]
+                       for sw, sub in zip(fl.switch_off, fl.flow_arr)]
+            spec.append(['step_group', members, bool(fl.add_init_f0)])
         elif isinstance(fl, ArcsinhFlow):
             spec.append(['arcsinh', put(fl.a), put(fl.b), put(fl.c), put(fl.d), bool(fl.set_restrictions), bool(fl.add_init_f0)])
         elif isinstance(fl, BoxCoxFlow):             # InverseBoxCoxFlow derives from it
@@ -407,6 +427,28 @@ def main_flows():
                extra={'flow_builder': builder, 'boxcox_constraint': constrained})
 
 
+def main_steps():
+    """The general step flows (flows.py:284-491): linear combinations of sinh-arcsinh / arcsinh / Box-Cox / inverse Box-Cox
+    members, most of them behind a trainable switch_off (flow.py:1039-1149)."""
+    Xb, Yb, Xbt, Ybt, ysb = load_uci('boston')
+    Nb = Xb.shape[0]
+    cases = (('boston_tgp_stepsal_p1', 'StepSAL:1:3', lambda: StepSAL(1, 3, add_f0=True), 60),
+             ('boston_tgp_steparcsl_p1', 'StepArcSL:2:2', lambda: StepArcSL(2, 2), 61),
+             ('boston_tgp_stepbcl_p1', 'StepBoxCoxL:1:2', lambda: StepBoxCoxL(1, 2), 62),
+             ('boston_tgp_stepinvbcl_p1', 'StepInverseBoxCoxL:1:2', lambda: StepInverseBoxCoxL(1, 2, add_f0=True), 63),
+             ('boston_tgp_stepall_p1', 'StepAllL:1', lambda: StepAllL(1), 64))
+    for name, builder, make, sd in cases:
+        torch.manual_seed(sd); np.random.seed(sd)  # noqa: E702
+        m = build('TGP', Xb, 100, Nb, make(), seed=sd)
+        g = torch.Generator().manual_seed(sd + 100)
+        randomise(m, sd + 10)
+        with torch.no_grad():
+            for n, prm in m.named_parameters():
+                if n.endswith('.lam'):               # unconstrained exponents near 1: the composed map stays gentle
+                    prm.copy_((1.0 + 0.15 * torch.randn((), generator=g)).reshape(prm.shape))
+        record(name, m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear', extra={'flow_builder': builder, 'boxcox_constraint': False})
+
+
 def main_big():
     """Fixtures at the BASELINE.json sizes (configs[3]: D=8, M=1024, StepTanhL(1,3); configs[4]: Bernoulli, D=16, M=2048,
     SAL(1)); row counts the CPU oracle replays in seconds.  Z = distinct data rows, as in bench.py."""
@@ -425,6 +467,9 @@ if __name__ == '__main__':
     if 'BIG' in ONLY:
         ONLY.discard('BIG')
         main_big()
+    elif 'STEPS' in ONLY:
+        ONLY.discard('STEPS')
+        main_steps()
     elif 'FLOWS' in ONLY:
         ONLY.discard('FLOWS')
         main_flows()

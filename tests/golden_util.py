@@ -38,7 +38,11 @@ class Golden:
             return leaf_cache[k]
         layers = []
         for lay in spec:
-            if lay[0] == 'identity':
+            if lay[0] == 'step_group':
+                members = [(self._flow([m], dtype, leaf_cache)[0], None if sw is None else (get(sw[0]), get(sw[1])))
+                           for m, sw in lay[1]]
+                layers.append(('step_group', members, lay[2]))
+            elif lay[0] == 'identity':
                 layers.append(('identity',))
             elif lay[0] == 'affine':
                 layers.append(('affine', get(lay[1]), get(lay[2]), lay[3]))
@@ -113,6 +117,19 @@ class Golden:
                     # the layer's leaf is lam AFTER the module's constraint; the reference's gradient is w.r.t. the raw
                     # parameter: comparable only when there is no constraint (the class-API tests cover the chain)
                     keys += ['flow%d.lam' % i if not self.meta.get('boxcox_constraint') else None]
+                elif lay[0] == 'step_group':
+                    # module order of the reference's StepFlow: every trainable switch_off first, then the members
+                    own = {'tanh_step': 'abcd', 'sal': 'ab', 'arcsinh': 'abcd'}
+                    for j, (m, sw) in enumerate(lay[1]):
+                        if sw is not None:
+                            keys += ['flow%d.m%d.sw_a' % (i, j), 'flow%d.m%d.sw_b' % (i, j)]
+                    for j, (m, sw) in enumerate(lay[1]):
+                        if m[0] == 'tanh_step':
+                            keys += ['flow%d.m%d.0.%s' % (i, j, c) for c in 'abcd']
+                        elif m[0] in ('boxcox', 'invboxcox'):
+                            keys += ['flow%d.m%d.lam' % (i, j) if not self.meta.get('boxcox_constraint') else None]
+                        else:
+                            keys += ['flow%d.m%d.%s' % (i, j, c) for c in own[m[0]]]
             assert len(keys) == len(vals), (keys, flow_names)
             g.update({k: v for k, v in zip(keys, vals) if k is not None})
         return g

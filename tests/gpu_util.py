@@ -7,26 +7,37 @@ from tgp.pytorch_b200.engine import Engine, FlowLayout
 def flow_layout_and_params(layers, device):
     """oracle layer list -> (FlowLayout, theta tensor, rowparams tensor or None, leaf-name list for theta)."""
     desc, theta, rowcols, names = [], [], [], []
+    flat = []                                       # (layer, leaf-name prefix, switch_off pair or None)
     for i, lay in enumerate(layers):
+        if lay[0] == 'step_group':
+            flat.append((lay, 'flow%d' % i, None))
+            flat += [(m, 'flow%d.m%d' % (i, j), sw) for j, (m, sw) in enumerate(lay[1])]
+        else:
+            flat.append((lay, 'flow%d' % i, None))
+    for lay, pre, sw in flat:
+        n_desc = len(desc)
+        i = pre[4:]                                 # names below are 'flow%s...' % i
         if lay[0] == 'identity':
             continue
-        if lay[0] == 'affine':
+        if lay[0] == 'step_group':
+            desc.append(dict(kind='step_group', n_steps=len(lay[1]), add_f0=lay[2]))
+        elif lay[0] == 'affine':
             desc.append(dict(kind='affine', restrict=lay[3]))
             theta += [lay[1].reshape(()), lay[2].reshape(())]
-            names += ['flow%d.a' % i, 'flow%d.b' % i]
+            names += ['flow%s.a' % i, 'flow%s.b' % i]
         elif lay[0] == 'tanh_step':
             desc.append(dict(kind='tanh_step', n_steps=len(lay[1]), add_f0=lay[2]))
             for j, st in enumerate(lay[1]):
                 theta += [t.reshape(()) for t in st]
-                names += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
+                names += ['flow%s.%d.%s' % (i, j, c) for c in 'abcd']
         elif lay[0] == 'arcsinh':
             desc.append(dict(kind='arcsinh', restrict=lay[5], add_f0=lay[6]))
             theta += [t.reshape(()) for t in lay[1:5]]
-            names += ['flow%d.%s' % (i, c) for c in 'abcd']
+            names += ['flow%s.%s' % (i, c) for c in 'abcd']
         elif lay[0] in ('boxcox', 'invboxcox'):
             desc.append(dict(kind=lay[0], add_f0=lay[2]))
             theta += [lay[1].reshape(())]
-            names += ['flow%d.lam' % i]
+            names += ['flow%s.lam' % i]
         elif lay[0] == 'sal':
             per_row = lay[1].dim() > 0
             desc.append(dict(kind='sal', restrict=lay[3], add_f0=lay[4], per_row=per_row))
@@ -34,7 +45,12 @@ def flow_layout_and_params(layers, device):
                 rowcols += [lay[1], lay[2]]
             else:
                 theta += [lay[1].reshape(()), lay[2].reshape(())]
-                names += ['flow%d.a' % i, 'flow%d.b' % i]
+                names += ['flow%s.a' % i, 'flow%s.b' % i]
+        if sw is not None:
+            assert len(desc) == n_desc + 1
+            desc[-1]['switch'] = True
+            theta += [sw[0].reshape(()), sw[1].reshape(())]
+            names += ['flow%s.sw_a' % i, 'flow%s.sw_b' % i]
     fl = FlowLayout(desc)
     th = torch.stack(theta).to(device) if theta else torch.zeros(0, dtype=torch.float64, device=device)
     rp = torch.stack(rowcols, dim=1).contiguous().to(device) if rowcols else None

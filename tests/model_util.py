@@ -33,7 +33,11 @@ def build_from_golden(g, device):
             from tgp.pytorch_b200.dsp.flows import ArcSL, BoxCoxL, build_chain
             parts = meta['flow_builder'].split(':')
             constraint = (lambda lam: 2.0 * torch.sigmoid(lam) + 0.01) if meta.get('boxcox_constraint') else None
-            if parts[0] == 'ArcSL':
+            if parts[0].startswith('Step'):
+                from tgp.pytorch_b200.dsp import flows as F
+                kw = {'add_f0': True} if parts[0] in ('StepSAL', 'StepInverseBoxCoxL') else {}
+                flow = getattr(F, parts[0])(*[int(v) for v in parts[1:]], **kw)
+            elif parts[0] == 'ArcSL':
                 flow = ArcSL(int(parts[1]))
             elif parts[0] == 'BoxCoxL':
                 flow = BoxCoxL(int(parts[1]), init_random=True)

@@ -36,7 +36,8 @@ def test_public_names_and_signatures_match_the_reference():
              (rl.GaussianLinearMean.__init__, ol.GaussianLinearMean.__init__), (rl.Bernoulli.__init__, ol.Bernoulli.__init__),
              (rfl.SAL, ofl.SAL), (rfl.StepTanhL, ofl.StepTanhL), (ru.KMEANS, ou.KMEANS),
              (rfl.BoxCoxL, ofl.BoxCoxL), (rfl.InverseBoxCoxL, ofl.InverseBoxCoxL), (rfl.ArcSL, ofl.ArcSL),
-             (rfl.build_chain, ofl.build_chain)]
+             (rfl.build_chain, ofl.build_chain), (rfl.StepSAL, ofl.StepSAL), (rfl.StepArcSL, ofl.StepArcSL),
+             (rfl.StepBoxCoxL, ofl.StepBoxCoxL), (rfl.StepInverseBoxCoxL, ofl.StepInverseBoxCoxL), (rfl.StepAllL, ofl.StepAllL)]
     for meth in ('ELBO', 'KLD', 'ELL', 'marginal_variational_qf_parameters', 'predictive_distribution', 'test_log_likelihood',
                  'sample_from_predictive_distribution', 'sample_from_variational_marginal', 'be_fully_bayesian', 'set_is_training'):
         pairs.append((getattr(rm.sparse_MF_SP, meth), getattr(om.sparse_MF_SP, meth)))
@@ -49,6 +50,38 @@ def test_public_names_and_signatures_match_the_reference():
         pairs.append((getattr(rl, lik).marginal_moments, getattr(ol, lik).marginal_moments))
     bad = [(r.__qualname__, _sig(r), _sig(o)) for r, o in pairs if _sig(r) != _sig(o)]
     assert not bad, bad
+
+
+def _plain(x):
+    if isinstance(x, (list, tuple)):
+        return [_plain(v) for v in x]
+    if isinstance(x, dict):
+        return {k: _plain(v) for k, v in x.items()}
+    if isinstance(x, np.ndarray):
+        return ('array', x.shape, x.tolist())
+    return x
+
+
+@pytest.mark.parametrize('gen,args,kw', [('StepSAL', (2, 3), {}), ('StepSAL', (1, 2), {'init_random': True, 'add_f0': True}),
+                                         ('StepArcSL', (2, 2), {}), ('StepBoxCoxL', (1, 3), {'add_f0': True}),
+                                         ('StepInverseBoxCoxL', (2, 2), {'init_random': True}), ('StepAllL', (3,), {}),
+                                         ('StepTanhL', (2, 3), {'add_f0': True}), ('ArcSL', (2,), {}), ('BoxCoxL', (1,), {})])
+def test_flow_generators_draw_the_reference_specification(gen, args, kw):
+    """Same numpy seed -> the same (name, init dict) list as the reference's generator (flows.py:115-491): schema, values,
+    RNG draw order; and the modules built from it carry the reference's parameter names in the reference's order."""
+    _ref()
+    import dsp.flows as rfl, dsp.models.flow as rf           # noqa: E401
+    from tgp.pytorch_b200.dsp import flows as ofl
+    from tgp.pytorch_b200.dsp.models import flow as of
+    np.random.seed(11)
+    ref = getattr(rfl, gen)(*args, **kw)
+    np.random.seed(11)
+    own = getattr(ofl, gen)(*args, **kw)
+    drop = lambda spec: [(n, {k: v for k, v in d.items() if not k.startswith('input_dep') and k != 'input_dim'}) for n, d in spec]  # noqa: E731
+    assert _plain(drop(ref)) == _plain(drop(own))
+    names_ref = [(n, tuple(p.shape)) for n, p in rf.instance_flow(ref).named_parameters()]
+    names_own = [(n, tuple(p.shape)) for n, p in of.instance_flow(own).named_parameters()]
+    assert names_ref == names_own
 
 
 def test_reference_initialiser_drives_our_flow_modules():

@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get('TGP_B200_LIB', os.path.join(_HERE, 'libtgp_b200.so'))
 TGP_F64, TGP_F32, TGP_F64_I8 = 0, 1, 2
 LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
 FLOW_IDENTITY, FLOW_AFFINE, FLOW_TANH_STEP, FLOW_SAL, FLOW_ARCSINH, FLOW_BOXCOX, FLOW_INV_BOXCOX = 0, 1, 2, 3, 4, 5, 6
-FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW = 1, 2, 4
+FLOW_STEP_GROUP = 7
+FLOW_RESTRICT, FLOW_ADD_F0, FLOW_PER_ROW, FLOW_SWITCH = 1, 2, 4, 8
 MAX_LAYERS = 64
 OPT_FUSED_FORWARD = 1
 OPT_ROW_CHUNK = 2

@@ -71,7 +71,9 @@ __device__ __forceinline__ void flow_prepare(const FlowDesc& fd, const double* _
         const double raw = theta[L.p0 + idx];
         double v0 = raw, v1 = 1.0;
         const bool res = L.flags & TGP_FLOW_RESTRICT;
-        if (L.kind == TGP_FLOW_AFFINE) {
+        if ((L.flags & TGP_FLOW_SWITCH) && idx >= layer_nparams(L) - 2) {       // [softplus(scale), bias] of a step member
+            if (idx == layer_nparams(L) - 2) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
+        } else if (L.kind == TGP_FLOW_AFFINE) {
             if (idx == 0 && res) { v0 = softplus_d(raw); v1 = sigmoid_d(raw); }
         } else if (L.kind == TGP_FLOW_TANH_STEP) {
             const int w = idx & 3;
@@ -95,13 +97,25 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
                                                const double* prep) {
     double dtot = 1.0;
     int slot = 0;
+    // step group (StepFlow, flow.py:1096-1103): the members are evaluated at the group's input and summed
+    int group_left = 0, group_l = 0;
+    double group_in = 0.0, group_acc = 0.0, group_d = 0.0;
     for (int l = 0; l < fd.n_layers; ++l) {
         const TgpFlowLayer& L = fd.layers[l];
+        if (L.kind == TGP_FLOW_STEP_GROUP) {
+            group_left = L.n_steps; group_l = l; group_in = f;
+            const bool add = L.flags & TGP_FLOW_ADD_F0;
+            group_acc = add ? f : 0.0; group_d = add ? 1.0 : 0.0;
+            if (group_left == 0) { f = group_acc; dtot *= group_d; if (dl) dl[l] = group_d; }
+            continue;
+        }
+        if (group_left) f = group_in;
+        const int slot0 = slot;
         const bool per_row = L.flags & TGP_FLOW_PER_ROW;
         const bool res = L.flags & TGP_FLOW_RESTRICT;
         // transformed value / chain factor of parameter idx (restricted = through softplus)
         auto val = [&](int idx, bool restricted, double& chain) -> double {
-            if (!per_row) { chain = prep[3 * (slot + idx) + 1]; return prep[3 * (slot + idx)]; }
+            if (!per_row) { chain = prep[3 * (slot0 + idx) + 1]; return prep[3 * (slot0 + idx)]; }
             const double raw = rowp[L.p0 + idx];
             if (restricted) { chain = sigmoid_d(raw); return softplus_d(raw); }
             chain = 1.0;
@@ -185,21 +199,39 @@ __device__ __forceinline__ double flow_forward(const FlowDesc& fd, double f, con
         } else {   // identity
             g = f; d = 1.0;
         }
-        if (dl) dl[l] = d;
-        dtot *= d;
-        f = g;
+        if (L.flags & TGP_FLOW_SWITCH) {                 // switch_off (flow.py:1130-1149): softplus(scale) * g + bias
+            double chs;
+            const double sc = val(slot - slot0, true, chs), bi = val(slot - slot0 + 1, false, ch1);
+            if (pg) {
+                for (int k = slot0; k < slot; ++k) pg[k] *= sc;
+                pg[slot] = g * chs; pg[slot + 1] = 1.0;
+            }
+            g = sc * g + bi;
+            d *= sc;
+            slot += 2;
+        }
+        if (group_left) {
+            group_acc += g; group_d += d;
+            if (dl) dl[l] = 1.0;
+            if (--group_left == 0) { f = group_acc; dtot *= group_d; if (dl) dl[group_l] = group_d; }
+        } else {
+            if (dl) dl[l] = d;
+            dtot *= d;
+            f = g;
+        }
     }
     *dG = dtot;
     return f;
 }
 
 __device__ __forceinline__ int layer_nparams(const TgpFlowLayer& L) {
+    const int sw = (L.flags & TGP_FLOW_SWITCH) ? 2 : 0;
     switch (L.kind) {
-        case TGP_FLOW_TANH_STEP: return 4 * L.n_steps;
-        case TGP_FLOW_IDENTITY: return 0;
-        case TGP_FLOW_ARCSINH: return 4;
-        case TGP_FLOW_BOXCOX: case TGP_FLOW_INV_BOXCOX: return 1;
-        default: return 2;
+        case TGP_FLOW_TANH_STEP: return 4 * L.n_steps + sw;
+        case TGP_FLOW_IDENTITY: case TGP_FLOW_STEP_GROUP: return 0;
+        case TGP_FLOW_ARCSINH: return 4 + sw;
+        case TGP_FLOW_BOXCOX: case TGP_FLOW_INV_BOXCOX: return 1 + sw;
+        default: return 2 + sw;
     }
 }
 

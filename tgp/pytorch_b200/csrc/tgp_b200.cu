@@ -98,6 +98,22 @@ inline int validate(const TgpModel* md) {
         return set_error(-1, "the closed-form Gaussian likelihood takes an identity flow");
     if (md->likelihood != TGP_LIK_GAUSS_LINEAR && (md->n_quad < 1 || md->n_quad > 4096))
         return set_error(-1, "n_quad out of range");
+    for (int i = 0, left = 0; i < md->n_layers; ++i) {          // step groups: header + exactly n_steps member layers
+        const TgpFlowLayer& L = md->layers[i];
+        if (L.kind < 0 || L.kind > TGP_FLOW_STEP_GROUP) return set_error(-1, "unknown flow layer kind");
+        if ((L.flags & TGP_FLOW_SWITCH) && (L.flags & TGP_FLOW_PER_ROW))
+            return set_error(-1, "a switch_off member cannot take per-row parameters");
+        if (L.kind == TGP_FLOW_STEP_GROUP) {
+            if (left) return set_error(-1, "step groups cannot nest");
+            if (L.n_steps < 1 || i + L.n_steps > md->n_layers - 1)
+                return set_error(-1, "step group runs past the last layer");
+            left = L.n_steps;
+        } else if (left) {
+            if (L.kind == TGP_FLOW_AFFINE || L.kind == TGP_FLOW_IDENTITY)
+                return set_error(-1, "affine / identity layers cannot be step members");
+            --left;
+        } else if (L.flags & TGP_FLOW_SWITCH) return set_error(-1, "switch_off outside a step group");
+    }
     return 0;
 }
 

@@ -194,7 +194,7 @@ class BoxCoxFlow(Flow):
 
     def __init__(self, init_lam, add_init_f0, constraint=None):
         super().__init__()
-        self.lam = nn.Parameter(torch.tensor(init_lam, dtype=cg.dtype).reshape(()))
+        self.lam = nn.Parameter(torch.tensor(init_lam, dtype=cg.dtype))          # shape as given: () or (1,)
         self.add_init_f0 = add_init_f0
         self.constraint = constraint
 
@@ -224,7 +224,7 @@ class BoxCoxFlow(Flow):
 
     def describe(self, X=None, n_mc=1):
         # the kernel receives lam AFTER the constraint; autograd carries the gradient back through the constraint
-        return [dict(kind=self._kind, add_f0=bool(self.add_init_f0))], [self.transform_param()], []
+        return [dict(kind=self._kind, add_f0=bool(self.add_init_f0))], [self.transform_param().reshape(())], []
 
 
 class InverseBoxCoxFlow(BoxCoxFlow):
@@ -436,11 +436,13 @@ class StepFlow(Flow):
                 name, params = step
                 restricted = params.get('set_restrictions', False)
             else:
-                name = {Sinh_ArcsinhFlow: 'sinh_arcsinh', TanhFlow: 'tanh'}[type(step)]
-                restricted = step.set_restrictions
+                name = {Sinh_ArcsinhFlow: 'sinh_arcsinh', TanhFlow: 'tanh', BoxCoxFlow: 'boxcox'}[type(step)]
+                restricted = getattr(step, 'set_restrictions', False)
             assert name != 'step_flow', 'cannot combine step flow with step flow'
-            assert restricted, 'set_restrictions must be True. Got false for flow {}'.format(name)
-            self.switch_off.append(switch_off(name == 'sinh_arcsinh', n_steps))
+            assert name in ('boxcox', 'inverseboxcox') or restricted, \
+                'set_restrictions must be True. Got false for flow {}'.format(name)
+            # flows without their own scale and bias get a trainable (scale, bias) so that they can be switched off
+            self.switch_off.append(switch_off(name in ('boxcox', 'sinh_arcsinh', 'inverseboxcox'), n_steps))
         if isinstance(flow_arr[0], (list, tuple)):
             self.flow_arr = nn.ModuleList(instance_flow(flow_arr, is_composite=False))
         else:
@@ -472,8 +474,7 @@ class StepFlow(Flow):
     def describe(self, X=None, n_mc=1):
         steps = list(self.flow_arr)
         if not all(isinstance(s, TanhFlow) and not s.add_init_f0 and s.set_restrictions for s in steps):
-            raise NotImplementedError('the fused step layer covers sums of restricted tanh flows (StepTanhL); other '
-                                      'step combinations are outside the hot-path scope')
+            return self._describe_group(X, n_mc)
         per_row = [bool(s.input_dependent) for s in steps]
         if any(per_row) and not all(per_row):
             raise NotImplementedError('mixed input-dependent / global tanh steps')
@@ -487,3 +488,25 @@ class StepFlow(Flow):
         for s in steps:
             glob += [s.a, s.b, s.c, s.d]
         return [lay], glob, []
+
+    def _describe_group(self, X, n_mc):
+        """General step flow (StepSAL / StepArcSL / StepBoxCoxL / StepInverseBoxCoxL / StepAllL, flows.py:284-492): a group
+        header followed by one layer per member; members with a trainable switch_off carry its [scale, bias]."""
+        layers = [dict(kind='step_group', n_steps=len(self.flow_arr), add_f0=bool(self.add_init_f0))]
+        glob, rows = [], []
+        for sw, fl in zip(self.switch_off, self.flow_arr):
+            if isinstance(fl, (AffineFlow, IdentityFlow, StepFlow)):
+                raise NotImplementedError('%s as a step member' % type(fl).__name__)
+            l, g, r = fl.describe(X, n_mc)
+            assert len(l) == 1
+            if l[0]['kind'] == 'tanh_step' or isinstance(fl, TanhFlow):
+                l[0] = dict(l[0], kind='tanh_step', n_steps=1)
+            if sw.is_trainable:
+                if l[0].get('per_row', False):
+                    raise NotImplementedError('input-dependent step members with a trainable switch_off')
+                l[0] = dict(l[0], switch=True)
+                g = list(g) + [sw.a, sw.b]
+            layers += l
+            glob += g
+            rows += r
+        return layers, glob, rows

@@ -11,8 +11,9 @@ import torch
 from . import _lib
 
 _KIND = {'identity': _lib.FLOW_IDENTITY, 'affine': _lib.FLOW_AFFINE, 'tanh_step': _lib.FLOW_TANH_STEP,
-         'sal': _lib.FLOW_SAL, 'arcsinh': _lib.FLOW_ARCSINH, 'boxcox': _lib.FLOW_BOXCOX, 'invboxcox': _lib.FLOW_INV_BOXCOX}
-_NPAR = {'affine': 2, 'sal': 2, 'arcsinh': 4, 'boxcox': 1, 'invboxcox': 1}
+         'sal': _lib.FLOW_SAL, 'arcsinh': _lib.FLOW_ARCSINH, 'boxcox': _lib.FLOW_BOXCOX, 'invboxcox': _lib.FLOW_INV_BOXCOX,
+         'step_group': _lib.FLOW_STEP_GROUP}
+_NPAR = {'affine': 2, 'sal': 2, 'arcsinh': 4, 'boxcox': 1, 'invboxcox': 1, 'step_group': 0}
 _LIK = {'gauss_linear': _lib.LIK_GAUSS_LINEAR, 'gauss_nonlinear': _lib.LIK_GAUSS_NONLINEAR,
         'bernoulli': _lib.LIK_BERNOULLI}
 
@@ -20,11 +21,12 @@ _LIK = {'gauss_linear': _lib.LIK_GAUSS_LINEAR, 'gauss_nonlinear': _lib.LIK_GAUSS
 class FlowLayout:
     """Flat description of a composed flow G for the kernels.
 
-    `layers`: list of dicts {kind, restrict, add_f0, n_steps, per_row}.  Global parameters of all layers are packed
+    `layers`: list of dicts {kind, restrict, add_f0, n_steps, per_row, switch}.  Global parameters of all layers are packed
     in descriptor order into `theta`; per-row (input-dependent) parameters into the columns of a (R, n_rowparams)
     matrix.  Parameter order inside a layer: affine [a, b]; tanh_step n_steps x [a, b, c, d]; sal [a, b]; arcsinh
-    [a, b, c, d]; boxcox / invboxcox [lam after the module's constraint]
-    (reference code/dsp/models/flow.py:330-340, 377-446, 495-557, 755-773, 965-977).
+    [a, b, c, d]; boxcox / invboxcox [lam after the module's constraint]; a `step_group` header (n_steps members follow,
+    all evaluated at the header's input and summed) has none; a member with `switch` appends its switch_off [s, t]
+    (reference code/dsp/models/flow.py:330-340, 377-446, 495-557, 755-773, 965-977, 1039-1149).
     """
 
     def __init__(self, layers):
@@ -36,7 +38,11 @@ class FlowLayout:
             if kind == 'identity':
                 continue
             npar = 4 * lay.get('n_steps', 0) if kind == 'tanh_step' else _NPAR[kind]
+            switch = bool(lay.get('switch', False))                 # step member with a trainable switch_off: + [s, t]
+            npar += 2 if switch else 0
             per_row = bool(lay.get('per_row', False))
+            if switch and per_row:
+                raise NotImplementedError('input-dependent step members with a trainable switch_off')
             p0 = self.n_rowparams if per_row else self.n_theta
             if per_row:
                 self.n_rowparams += npar
@@ -44,7 +50,7 @@ class FlowLayout:
                 self.n_theta += npar
             self.layers.append(dict(kind=kind, restrict=bool(lay.get('restrict', False)),
                                     add_f0=bool(lay.get('add_f0', False)), n_steps=int(lay.get('n_steps', 0)),
-                                    per_row=per_row, p0=p0, npar=npar))
+                                    per_row=per_row, p0=p0, npar=npar, switch=switch))
         if len(self.layers) > _lib.MAX_LAYERS:
             raise ValueError('flow has %d layers; the fused epilogue supports %d' % (len(self.layers), _lib.MAX_LAYERS))
 
@@ -56,7 +62,7 @@ class FlowLayout:
             L = model.layers[i]
             L.kind = _KIND[lay['kind']]
             L.flags = (_lib.FLOW_RESTRICT if lay['restrict'] else 0) | (_lib.FLOW_ADD_F0 if lay['add_f0'] else 0) | \
-                      (_lib.FLOW_PER_ROW if lay['per_row'] else 0)
+                      (_lib.FLOW_PER_ROW if lay['per_row'] else 0) | (_lib.FLOW_SWITCH if lay['switch'] else 0)
             L.n_steps = lay['n_steps']
             L.p0 = lay['p0']
 
