@@ -146,6 +146,18 @@ int tgp_coverage_rows(const TgpModel* model, const TgpParams* params, const void
                       double q_lo_p, double q_hi_p, void* q_lo, void* q_hi, void* covered, void* samples, double* count,
                       void* stream);
 
+/* Monte-Carlo expected log-likelihood of the multiclass softmax likelihood — replaces
+ * MulticlassCategorical.expected_log_prob (likelihoods/MulticlassCategorical.py:51-105) and, with probs != NULL,
+ * marginal_moments (:109-151).  One GP per class: mu, v are (C, R); eps (S, C, R) is the N(0,1) noise of td.Normal.rsample,
+ * drawn by the caller (the reference's generator stream); the C flows share model->layers (global parameters only) and own
+ * one row each of theta (C, n_theta); Y holds the labels 0..C-1 as doubles.
+ *   ell_rows[n] = 1/S sum_s log softmax(G(mu + sqrt(v) eps_s))[y_n]
+ * want_grad: g_mu, g_v (C, R) = d ell_rows[n] / d mu[c,n], d v[c,n] (unscaled); dtheta (C, n_theta) += d sum_n ell_rows[n] / d theta
+ * (caller zeroes).  probs (optional, R x C) = 1/S sum_s softmax.  C <= 32, C * n_theta <= 256. */
+int tgp_mc_softmax_rows(const TgpModel* model, int C, int S, long R, const void* mu, const void* v, const void* Y, const void* eps,
+                        const void* theta, int want_grad, void* ell_rows, void* g_mu, void* g_v, void* dtheta, void* probs,
+                        void* stream);
+
 /* The exchange format of the one collective per step.  The reduce buffer holds two (padded) M x M blocks
  * of which only the lower triangles are populated in TGP_F64 mode (Gbar and dL_S; in TGP_F32 mode the second block, Cbar,
  * is dense): tgp_reduce_pack gathers [small vector | tril(Gbar) | tril or full second block] into `packed`

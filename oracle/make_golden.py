@@ -22,7 +22,7 @@ import dsp.config as cg  # noqa: E402
 from dsp.models import instance_kernel, sparse_MF_SP, sparse_MF_GP  # noqa: E402
 from dsp.models.flow import (instance_flow, AffineFlow, StepFlow, TanhFlow, Sinh_ArcsinhFlow,  # noqa: E402
                              IdentityFlow, CompositeFlow, ArcsinhFlow, BoxCoxFlow, InverseBoxCoxFlow)
-from dsp.likelihoods import GaussianNonLinearMean, GaussianLinearMean, Bernoulli  # noqa: E402
+from dsp.likelihoods import GaussianNonLinearMean, GaussianLinearMean, Bernoulli, MulticlassCategorical  # noqa: E402
 from dsp.flows import (SAL, StepTanhL, ArcSL, BoxCoxL, InverseBoxCoxL, build_chain,  # noqa: E402
                        StepSAL, StepArcSL, StepBoxCoxL, StepInverseBoxCoxL, StepAllL)
 
@@ -449,6 +449,65 @@ def main_steps():
         record(name, m, Xb, Yb, Xbt, Ybt, ysb, 'gauss_nonlinear', extra={'flow_builder': builder, 'boxcox_constraint': False})
 
 
+def main_multiclass():
+    """Softmax likelihood integrated by Monte Carlo, one GP per class (likelihoods/MulticlassCategorical.py:51-151,
+    sparse_MF_SP.py:552-626 with out_dim = C).  The N(0,1) draws of td.Normal.rsample / .sample are reproduced from the seed set
+    immediately before the call (both are `empty(shape).normal_()` on the default generator); tests/test_oracle_golden.py
+    confirms them by re-evaluating the reference's numbers from these draws."""
+    cases = (('mc_synth_c3_sal1_p1', 3, 5, 20, 96, 30, 'SAL:1', lambda: SAL(1), 70),
+             ('mc_synth_c4_steptanh12_p1', 4, 6, 24, 80, 20, 'StepTanhL:1:2', lambda: StepTanhL(1, 2, add_f0=True), 71),
+             ('mc_synth_c3_stepsal_p1', 3, 4, 16, 64, 16, 'StepSAL:1:2', lambda: StepSAL(1, 2, add_f0=True), 72))
+    for name, C, D, M, MB, S, builder, make, sd in cases:
+        if ONLY and name not in ONLY:
+            continue
+        torch.manual_seed(sd); np.random.seed(sd)  # noqa: E702
+        g = torch.Generator().manual_seed(sd)
+        X = torch.randn(MB + 32, D, generator=g, dtype=torch.float64)
+        W = torch.randn(D, C, generator=g, dtype=torch.float64)
+        Y = torch.argmax(X @ W + 0.5 * torch.randn(MB + 32, C, generator=g, dtype=torch.float64), dim=1, keepdim=True)
+        cg.quad_points = S
+        K = instance_kernel('scale_rbf', ard_num_dim=D, num_multioutput=C, kernel_is_shared=False,
+                            init_params={'length_scale': 2.0, 'kernel_scale': 2.0, 'noisy_variance': 1e-6})
+        ip = {'variational_distribution': {'variance_scale': 1e-5, 'mean_scale': 0.0}}
+        flows = [instance_flow(make()) for _ in range(C)]
+        m = sparse_MF_SP(['zero', K], X, X[:M].clone(), 5000., MulticlassCategorical(C), C, True, False, False, False, False,
+                         flows, 'single', 0.0, False, ip)
+        randomise(m, sd + 10)
+        Xtr, Ytr, Xte, Yte = X[:MB], Y[:MB], X[MB:], Y[MB:]
+        store = {'X': Xtr.numpy(), 'Y': Ytr.numpy(), 'Xte': Xte.numpy(), 'Yte': Yte.numpy()}
+        m.set_is_training(True)
+        torch.manual_seed(sd + 1)
+        E, ELL, KLD = m.ELBO(Xtr, Ytr)
+        E.backward()
+        torch.manual_seed(sd + 1)
+        store['eps'] = torch.empty(S, C, MB, dtype=torch.float64).normal_().numpy()
+        store['ELBO'], store['ELL'], store['KLD'] = E.item(), ELL.item(), KLD.item()
+        names = []
+        for n, prm in m.named_parameters():
+            store['param:' + n] = prm.detach().numpy().copy()
+            store['grad:' + n] = (torch.zeros_like(prm) if prm.grad is None else prm.grad).numpy().copy()
+            names.append(n)
+        specs = []
+        with torch.no_grad():
+            mu, v = m.marginal_variational_qf_parameters(Xtr.repeat(C, 1, 1), diagonal=True, is_duvenaud=False)
+            store['mu'], store['v'] = mu.squeeze(2).numpy(), v.squeeze(2).numpy()
+            for c in range(C):
+                specs.append(flow_to_spec(m.G_matrix[c], store, Xtr, 'fl%d' % c))
+        m.set_is_training(False)
+        torch.manual_seed(sd + 2)
+        lp, mom = m.test_log_likelihood(Xte, Yte, return_moments=True, Y_std=torch.ones(1), S_MC_NNet=None)
+        torch.manual_seed(sd + 2)
+        store['eps_te'] = torch.empty(S, C, Xte.shape[0], dtype=torch.float64).normal_().numpy()
+        store['test_logp'] = float(lp)
+        store['test_probs'] = mom[0].detach().double().numpy()
+        meta = {'name': name, 'likelihood': 'multiclass', 'C': C, 'S': S, 'N': float(m.N), 'M': M, 'flows': specs,
+                'flow_builder': builder, 'param_names': names, 'dtype': 'float64'}
+        store['meta'] = np.array(json.dumps(meta))
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **store)
+        print('%-34s ELBO % .12e  ELL % .12e  KLD % .12e  test_logp % .12e' % (name, store['ELBO'], store['ELL'], store['KLD'],
+                                                                              store['test_logp']))
+
+
 def main_big():
     """Fixtures at the BASELINE.json sizes (configs[3]: D=8, M=1024, StepTanhL(1,3); configs[4]: Bernoulli, D=16, M=2048,
     SAL(1)); row counts the CPU oracle replays in seconds.  Z = distinct data rows, as in bench.py."""
@@ -467,6 +526,9 @@ if __name__ == '__main__':
     if 'BIG' in ONLY:
         ONLY.discard('BIG')
         main_big()
+    elif 'MULTICLASS' in ONLY:
+        ONLY.discard('MULTICLASS')
+        main_multiclass()
     elif 'STEPS' in ONLY:
         ONLY.discard('STEPS')
         main_steps()

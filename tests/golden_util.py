@@ -12,14 +12,53 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 def golden_names(big=None):
     """Fixture names; big=False / True selects the small fixtures / the two at the BASELINE.json sizes (M = 1024, 2048)."""
     names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
-                   if not os.path.basename(f).startswith('traj_'))
+                   if not os.path.basename(f).startswith(('traj_', 'mc_')))
     if big is None:
         return names
     return [n for n in names if (('_m1024_' in n or '_m2048_' in n) == big)]
 
 
+def multiclass_names():
+    """Fixtures of the Monte-Carlo softmax likelihood (one GP per class; oracle/make_golden.py main_multiclass)."""
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, 'mc_*.npz')))
+
+
 def trajectory_names():
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, 'traj_*.npz')))
+
+
+def flow_grad_keys(spec, constrained=False):
+    """Leaf names (oracle.leaf_params keys) of a fixture's flow scalars in the REFERENCE's module order — the order in which
+    `named_parameters()` lists them; None where the stored gradient is not comparable."""
+    keys = []
+    for i, lay in enumerate(spec):
+        if lay[0] == 'affine':
+            keys += ['flow%d.a' % i, 'flow%d.b' % i]
+        elif lay[0] == 'tanh_step':
+            for j in range(len(lay[1])):
+                keys += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
+        elif lay[0] == 'sal':
+            keys += ['flow%d.a' % i, 'flow%d.b' % i]
+        elif lay[0] == 'arcsinh':
+            keys += ['flow%d.%s' % (i, c) for c in 'abcd']
+        elif lay[0] in ('boxcox', 'invboxcox'):
+            # the layer's leaf is lam AFTER the module's constraint; the reference's gradient is w.r.t. the raw
+            # parameter: comparable only when there is no constraint (the class-API tests cover the chain)
+            keys += ['flow%d.lam' % i if not constrained else None]
+        elif lay[0] == 'step_group':
+            # module order of the reference's StepFlow: every trainable switch_off first, then the members
+            own = {'tanh_step': 'abcd', 'sal': 'ab', 'arcsinh': 'abcd'}
+            for j, (m, sw) in enumerate(lay[1]):
+                if sw is not None:
+                    keys += ['flow%d.m%d.sw_a' % (i, j), 'flow%d.m%d.sw_b' % (i, j)]
+            for j, (m, sw) in enumerate(lay[1]):
+                if m[0] == 'tanh_step':
+                    keys += ['flow%d.m%d.0.%s' % (i, j, c) for c in 'abcd']
+                elif m[0] in ('boxcox', 'invboxcox'):
+                    keys += ['flow%d.m%d.lam' % (i, j) if not constrained else None]
+                else:
+                    keys += ['flow%d.m%d.%s' % (i, j, c) for c in own[m[0]]]
+    return keys
 
 
 class Golden:
@@ -102,34 +141,7 @@ class Golden:
         if not self.meta['id_flow']:
             flow_names = [n for n in names if n.startswith('G_matrix')]
             vals = [self.t('grad:' + n).view(()) for n in flow_names]
-            keys = []
-            for i, lay in enumerate(self.meta['flow_train']):
-                if lay[0] == 'affine':
-                    keys += ['flow%d.a' % i, 'flow%d.b' % i]
-                elif lay[0] == 'tanh_step':
-                    for j in range(len(lay[1])):
-                        keys += ['flow%d.%d.%s' % (i, j, c) for c in 'abcd']
-                elif lay[0] == 'sal':
-                    keys += ['flow%d.a' % i, 'flow%d.b' % i]
-                elif lay[0] == 'arcsinh':
-                    keys += ['flow%d.%s' % (i, c) for c in 'abcd']
-                elif lay[0] in ('boxcox', 'invboxcox'):
-                    # the layer's leaf is lam AFTER the module's constraint; the reference's gradient is w.r.t. the raw
-                    # parameter: comparable only when there is no constraint (the class-API tests cover the chain)
-                    keys += ['flow%d.lam' % i if not self.meta.get('boxcox_constraint') else None]
-                elif lay[0] == 'step_group':
-                    # module order of the reference's StepFlow: every trainable switch_off first, then the members
-                    own = {'tanh_step': 'abcd', 'sal': 'ab', 'arcsinh': 'abcd'}
-                    for j, (m, sw) in enumerate(lay[1]):
-                        if sw is not None:
-                            keys += ['flow%d.m%d.sw_a' % (i, j), 'flow%d.m%d.sw_b' % (i, j)]
-                    for j, (m, sw) in enumerate(lay[1]):
-                        if m[0] == 'tanh_step':
-                            keys += ['flow%d.m%d.0.%s' % (i, j, c) for c in 'abcd']
-                        elif m[0] in ('boxcox', 'invboxcox'):
-                            keys += ['flow%d.m%d.lam' % (i, j) if not self.meta.get('boxcox_constraint') else None]
-                        else:
-                            keys += ['flow%d.m%d.%s' % (i, j, c) for c in own[m[0]]]
+            keys = flow_grad_keys(self.meta['flow_train'], self.meta.get('boxcox_constraint'))
             assert len(keys) == len(vals), (keys, flow_names)
             g.update({k: v for k, v in zip(keys, vals) if k is not None})
         return g
@@ -164,3 +176,34 @@ def rel_err(a, b):
     b = torch.as_tensor(b, dtype=torch.float64).reshape(-1)
     den = float(b.norm())
     return float((a - b).norm()) / (den if den > 0 else 1.0)
+
+
+class MulticlassGolden(Golden):
+    """Fixture of the Monte-Carlo softmax likelihood: C GPs, one flow each (same architecture), recorded noise draws."""
+
+    def plist(self, dtype=torch.float64):
+        """One oracle parameter dict per class."""
+        C = self.meta['C']
+        out = []
+        for c in range(C):
+            p = {'Z': self.t('param:Z', dtype)[c].clone(),
+                 'raw_lengthscale': self.t('param:covariance_function.base_kernel.raw_lengthscale', dtype)[c].reshape(-1).clone(),
+                 'raw_outputscale': self.t('param:covariance_function.raw_outputscale', dtype)[c].reshape(()).clone(),
+                 'm': self.t('param:q_U.variational_mean', dtype)[c].clone(),
+                 'L_raw': self.t('param:q_U.chol_variational_covar', dtype)[c].clone(),
+                 'log_var_noise': torch.zeros((), dtype=dtype)}
+            p['flow'] = self._flow(self.meta['flows'][c], dtype, {})
+            out.append(p)
+        return out
+
+    def ref_grads_of_class(self, c):
+        g = {'Z': self.t('grad:Z')[c],
+             'raw_lengthscale': self.t('grad:covariance_function.base_kernel.raw_lengthscale')[c].reshape(-1),
+             'raw_outputscale': self.t('grad:covariance_function.raw_outputscale')[c].reshape(()),
+             'm': self.t('grad:q_U.variational_mean')[c],
+             'L_raw': self.t('grad:q_U.chol_variational_covar')[c]}
+        names = [n for n in self.meta['param_names'] if n.startswith('G_matrix.%d.' % c)]
+        keys = flow_grad_keys(self.meta['flows'][c])
+        assert len(keys) == len(names), (keys, names)
+        g.update({k: self.t('grad:' + n).reshape(()) for k, n in zip(keys, names)})
+        return g

@@ -3,6 +3,7 @@ import pytest
 import torch
 
 from oracle import tgp_oracle as O
+from tests import golden_util
 from tests.golden_util import Golden, golden_names, rel_err
 
 TOL = 1e-11      # L2-relative; the oracle replays the reference's own torch ops, so it should be ~1e-14
@@ -88,3 +89,38 @@ def test_dropout_fixture_masks_reproduce_the_per_row_flow_parameters(name, act, 
         for ni, net in enumerate('ab'):
             out = O.flow_mlp(X, _mlp_weights(g, li, net), act, p, [masks[ni, l] for l in range(masks.shape[1])])
             assert rel_err(out, g.t(lay[1 + ni])) < 1e-13, (li, net)
+
+
+@pytest.mark.parametrize('name', golden_util.multiclass_names())
+def test_multiclass_monte_carlo_elbo_grads_and_probabilities(name):
+    """Softmax likelihood, one GP per class, with the reference's recorded N(0,1) draws
+    (likelihoods/MulticlassCategorical.py:51-151): ELBO / ELL / KLD, marginals, every gradient, class probabilities, test NLL."""
+    from oracle import tgp_oracle as O
+    g = golden_util.MulticlassGolden(name)
+    plist = g.plist()
+    X, y = g.t('X'), g.t('Y').reshape(-1)
+    leaves = [O.leaf_params(p) for p in plist]
+    for lv in leaves:
+        lv.pop('log_var_noise')
+        for t in lv.values():
+            t.requires_grad_(True)
+    E, ELL, KLD, rows, mu, v = O.elbo_multiclass(X, y, plist, g.meta['N'], g.t('eps'))
+    assert golden_util.rel_err(E, g.t('ELBO')) < 1e-12
+    assert golden_util.rel_err(ELL, g.t('ELL')) < 1e-12
+    assert golden_util.rel_err(KLD, g.t('KLD')) < 1e-12
+    assert golden_util.rel_err(mu.detach(), g.t('mu')) < 1e-11
+    assert golden_util.rel_err(v.detach(), g.t('v')) < 1e-10
+    E.backward()
+    for c, lv in enumerate(leaves):
+        ref = g.ref_grads_of_class(c)
+        assert set(ref) == set(lv)
+        for k, t in lv.items():
+            assert golden_util.rel_err(t.grad, ref[k]) < 1e-9, (c, k)
+    with torch.no_grad():
+        Xte = g.t('Xte')
+        mv = [O.qf_marginals(Xte, p) for p in plist]
+        P = O.probs_mc_softmax(torch.stack([a for a, _ in mv]), torch.stack([b for _, b in mv]), [p['flow'] for p in plist],
+                               g.t('eps_te'))
+        assert golden_util.rel_err(P, g.t('test_probs')) < 1e-11
+        nll = -torch.log(P.float().gather(1, g.t('Yte').long().view(-1, 1))).mean()          # scored in float32 (sparse_MF_SP.py:813)
+        assert abs(float(-(nll * Xte.shape[0])) - float(g.t('test_logp'))) < 1e-5 * abs(float(g.t('test_logp')))

@@ -34,6 +34,7 @@ def test_public_names_and_signatures_match_the_reference():
              (rm.sparse_MF_GP.__init__, om.sparse_MF_GP.__init__), (rf.instance_flow, of.instance_flow),
              (rl.GaussianNonLinearMean.__init__, ol.GaussianNonLinearMean.__init__),
              (rl.GaussianLinearMean.__init__, ol.GaussianLinearMean.__init__), (rl.Bernoulli.__init__, ol.Bernoulli.__init__),
+             (rl.MulticlassCategorical.__init__, ol.MulticlassCategorical.__init__),
              (rfl.SAL, ofl.SAL), (rfl.StepTanhL, ofl.StepTanhL), (ru.KMEANS, ou.KMEANS),
              (rfl.BoxCoxL, ofl.BoxCoxL), (rfl.InverseBoxCoxL, ofl.InverseBoxCoxL), (rfl.ArcSL, ofl.ArcSL),
              (rfl.build_chain, ofl.build_chain), (rfl.StepSAL, ofl.StepSAL), (rfl.StepArcSL, ofl.StepArcSL),
@@ -45,7 +46,7 @@ def test_public_names_and_signatures_match_the_reference():
                 'InverseBoxCoxFlow'):
         pairs.append((getattr(rf, cls).__init__, getattr(of, cls).__init__))
         pairs.append((getattr(rf, cls).forward, getattr(of, cls).forward))
-    for lik in ('GaussianNonLinearMean', 'GaussianLinearMean', 'Bernoulli'):
+    for lik in ('GaussianNonLinearMean', 'GaussianLinearMean', 'Bernoulli', 'MulticlassCategorical'):
         pairs.append((getattr(rl, lik).expected_log_prob, getattr(ol, lik).expected_log_prob))
         pairs.append((getattr(rl, lik).marginal_moments, getattr(ol, lik).marginal_moments))
     bad = [(r.__qualname__, _sig(r), _sig(o)) for r, o in pairs if _sig(r) != _sig(o)]

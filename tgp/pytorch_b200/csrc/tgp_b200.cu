@@ -11,6 +11,7 @@
 #include "crt_driver.cuh"
 #include "eval_kernels.cuh"
 #include "kmeans.cuh"
+#include "mc_kernels.cuh"
 
 namespace tgp {
 char g_last_error[512] = "";
@@ -491,6 +492,31 @@ int tgp_coverage_rows(const TgpModel* md, const TgpParams* p, const void* mu, co
         TGP_TRY(check_launch("k_bump_offset"));
     }
     return 0;
+}
+
+int tgp_mc_softmax_rows(const TgpModel* md, int C, int S, long R, const void* mu, const void* v, const void* Y, const void* eps,
+                        const void* theta, int want_grad, void* ell_rows, void* g_mu, void* g_v, void* dtheta, void* probs,
+                        void* stream) {
+    TGP_TRY(validate(md));
+    if (R <= 0) return 0;
+    if (C < 2 || C > MC_MAX_CLASSES) return set_error(-1, "number of classes out of range (2..32)");
+    if (S < 1) return set_error(-1, "S must be positive");
+    if (md->n_rowparams > 0) return set_error(-1, "the Monte-Carlo softmax likelihood takes flows with global parameters");
+    if ((long)C * md->n_theta > MC_MAX_ACC) return set_error(-1, "C * n_theta exceeds the per-thread gradient accumulator (256)");
+    if (!mu || !v || !Y || !eps || !ell_rows || (md->n_theta > 0 && !theta))
+        return set_error(-1, "NULL argument to tgp_mc_softmax_rows");
+    if (want_grad && (!g_mu || !g_v || (md->n_theta > 0 && !dtheta))) return set_error(-1, "gradient outputs required");
+    for (int i = 0; i < md->n_layers; ++i)
+        if (md->layers[i].flags & TGP_FLOW_PER_ROW) return set_error(-1, "per-row flow parameters are not supported here");
+    McSoftmaxArgs a;
+    a.R = (int)R; a.C = C; a.S = S; a.n_theta = md->n_theta; a.want_grad = want_grad;
+    a.mu = (const double*)mu; a.v = (const double*)v; a.y = (const double*)Y; a.eps = (const double*)eps;
+    a.theta = (const double*)theta;
+    a.ell_rows = (double*)ell_rows; a.g_mu = (double*)g_mu; a.g_v = (double*)g_v; a.dtheta = (double*)dtheta; a.probs = (double*)probs;
+    fill_flow(a.flow, md);
+    const size_t smem = (size_t)C * 3 * (md->n_theta > 0 ? md->n_theta : 1) * sizeof(double);
+    k_row_mc_softmax<<<(unsigned)((R + MC_THREADS - 1) / MC_THREADS), MC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("k_row_mc_softmax");
 }
 
 int tgp_reduce_pack(const TgpModel* md, const double* reduce_buf, double* packed, void* stream) {

@@ -5,7 +5,6 @@ import torch.distributions as td
 
 from .. import config as cg
 from ..quadrature import GaussHermiteQuadrature1D
-from ..models.flow import CompositeFlow, IdentityFlow
 from . import _rows
 
 
@@ -39,6 +38,7 @@ class Bernoulli(nn.Module):
         deliberately so that results match it; see DESIGN.md "reference defects"."""
         assert len(flow) == 1, 'Flow list must be size 1 for Bernoulli likelihood'
         assert gauss_mean.size(0) == 1, 'Binary classification just require one GP for both classes'
+        from ..models.flow import CompositeFlow, IdentityFlow      # here: `models` imports this package
         fl = flow[0]
         subs = fl.flow_arr if isinstance(fl, CompositeFlow) else [fl]
         identity = all(isinstance(f, IdentityFlow) for f in subs)

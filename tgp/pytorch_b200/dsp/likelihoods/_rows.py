@@ -101,3 +101,77 @@ def coverage_rows(likelihood, n_quad, y, mu, v, log_var_noise, flow, X, S, n_mc=
             rowp = rowp.reshape(n_mc, R, -1).permute(1, 0, 2).contiguous()
         return eng.coverage_rows(mu.double().contiguous(), v.double().contiguous(), y.double().contiguous(), rowp, n_mc, S, seed,
                                  want_samples=want_samples)
+
+
+# ---- Monte-Carlo softmax likelihood (tgp_mc_softmax_rows) -------------------------------------------------------------
+def _mc_model(layout):
+    """TgpModel carrying only the flow architecture (the MC kernel ignores the GP / likelihood fields)."""
+    from ... import _lib
+    md = _lib.TgpModel()
+    md.dtype, md.M, md.D = _lib.TGP_F64, 1, 1
+    md.likelihood, md.n_quad = _lib.LIK_GAUSS_NONLINEAR, 1
+    layout.fill(md)
+    return md
+
+
+def mc_flow_pack(flows, X):
+    """C flow modules of one architecture -> (FlowLayout, theta (C, n_theta) or None)."""
+    packs = [flow_pack(fl, X[c] if X is not None else None) for c, fl in enumerate(flows)]
+    first = packs[0][0]
+    for lay, _th, rowp in packs:
+        if rowp is not None:
+            raise NotImplementedError('input-dependent flows under the Monte-Carlo softmax likelihood')
+        if lay.layers != first.layers:
+            raise NotImplementedError('the Monte-Carlo softmax kernel takes one flow architecture for all classes')
+    theta = torch.stack([p[1] for p in packs]) if first.n_theta > 0 else None
+    return first, theta
+
+
+class _McSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, y, eps, want_probs, mu, v, theta):
+        import ctypes as C
+        from ... import _lib
+        lib = _lib.load()
+        if not mu.is_cuda:
+            raise RuntimeError('tgp.pytorch_b200 has no CPU path: move the model and the data to a CUDA device')
+        dev = mu.device
+        Cn, R = mu.shape
+        S = eps.shape[0]
+        assert tuple(eps.shape) == (S, Cn, R), 'eps must be (S, C, R)'
+        d = torch.float64
+        mu_d, v_d = mu.detach().to(d).contiguous(), v.detach().to(d).contiguous()
+        th = None if theta is None else theta.detach().to(d).contiguous()
+        grad = any(ctx.needs_input_grad)
+        rows = torch.empty(R, dtype=d, device=dev)
+        g_mu = torch.empty(Cn, R, dtype=d, device=dev) if grad else None
+        g_v = torch.empty(Cn, R, dtype=d, device=dev) if grad else None
+        dth = torch.zeros_like(th) if (grad and th is not None) else None
+        probs = torch.empty(R, Cn, dtype=d, device=dev) if want_probs else None
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.tgp_mc_softmax_rows(_mc_model(layout), Cn, S, R, ptr(mu_d), ptr(v_d), ptr(y.to(d).contiguous()),
+                                               ptr(eps.to(d).contiguous()), ptr(th), 1 if grad else 0, ptr(rows), ptr(g_mu), ptr(g_v),
+                                               ptr(dth), ptr(probs), st), 'tgp_mc_softmax_rows')
+        if grad:
+            ctx.save_for_backward(g_mu, g_v, dth if dth is not None else rows.new_zeros(1))
+        ctx.has_theta, ctx.io_dtype = th is not None, mu.dtype
+        out_p = probs if want_probs else rows.new_zeros(0)
+        ctx.mark_non_differentiable(rows, out_p)
+        return rows.sum(), rows, out_p
+
+    @staticmethod
+    def backward(ctx, g_sum, _g_rows, _g_probs):
+        g_mu, g_v, dth = ctx.saved_tensors
+        return (None, None, None, None, (g_mu * g_sum).to(ctx.io_dtype), (g_v * g_sum).to(ctx.io_dtype),
+                dth * g_sum if ctx.has_theta else None)
+
+
+def mc_softmax(flows, X, y, eps, mu, v, want_probs=False):
+    """(sum over rows of the MC expected log-likelihood, per-row terms, class probabilities or empty)."""
+    from ... import functional as Fn
+    layout, theta = mc_flow_pack(flows, X)
+    if theta is not None and theta.requires_grad and Fn._world() is not None:
+        theta = Fn._SumGradAcrossRanks.apply(theta)          # the flow scalars see rank-local rows only
+    return _McSoftmax.apply(layout, y, eps, bool(want_probs), mu, v, theta)

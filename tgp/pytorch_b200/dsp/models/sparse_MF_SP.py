@@ -18,7 +18,10 @@ from .. import config as cg
 from ... import functional as Fn
 from ...engine import Engine, FlowLayout
 from ..kernels import CholeskyVariationalDistribution, ScaleKernel, RBFKernel
-from ..likelihoods import GaussianLinearMean, GaussianNonLinearMean, Bernoulli
+from ..likelihoods.GaussianLinearMean import GaussianLinearMean
+from ..likelihoods.GaussianNonLinearMean import GaussianNonLinearMean
+from ..likelihoods.Bernoulli import Bernoulli
+from ..likelihoods.MulticlassCategorical import MulticlassCategorical
 from ..likelihoods import _rows
 from ..quadrature import GaussHermiteQuadrature1D
 from .config_models import get_init_params
@@ -240,6 +243,8 @@ class sparse_MF_SP(nn.Module):
         assert self.G_flow_connection == 'single', 'sparse_MF_SP places one independent flow per output'
         MB = Y.size(0)
         scale = self._global_scale(MB)
+        if isinstance(self.likelihood, MulticlassCategorical):
+            return self._elbo_multiclass(X, Y, scale)
         kind = _LIK_KIND[type(self.likelihood)]
         ELL, KLD = 0.0, 0.0
         for dy in range(self.out_dim):
@@ -263,6 +268,26 @@ class sparse_MF_SP(nn.Module):
         ELBO = ELL - KLD - KLD_flow
         out = self.Z.dtype
         return ELBO.to(out), ELL.to(out), (KLD + KLD_flow).to(out)
+
+    def _elbo_multiclass(self, X, Y, scale):
+        """One GP per class coupled by the softmax: the q(f) marginals of every class (fused forward, hand-written backward
+        through `Fn.qf_marginals`), then ONE Monte-Carlo kernel over all classes (tgp_mc_softmax_rows).  Under row sharding the
+        marginals' backward all-reduces its packed buffer (one collective per class) and the flow scalars are summed across
+        ranks; the returned ELL is the global one when cg.sync_elbo_in_forward is set, else this rank's share."""
+        mean, cov = self.marginal_variational_qf_parameters(X, diagonal=True, is_duvenaud=False)
+        ell = self.likelihood.expected_log_prob(Y.t(), mean.squeeze(dim=2), cov.squeeze(dim=2), flow=self.G_matrix, X=X)
+        dist = Fn._world()
+        if dist is not None and cg.sync_elbo_in_forward:
+            tot = ell.detach().clone()
+            dist.all_reduce(tot)
+            ell = ell + (tot - ell.detach())
+        ELL = scale * ell
+        KLD = self.KLD().sum()
+        KLD_flow = 0.0
+        for flow in self.G_matrix:
+            KLD_flow = KLD_flow + flow.KLD()
+        out = self.Z.dtype
+        return (ELL - KLD - KLD_flow).to(out), ELL.to(out), (KLD + KLD_flow).to(out)
 
     def last_global_elbo(self):
         """Row-sharded training with cg.sync_elbo_in_forward = False: the ELBO over the GLOBAL minibatch of the last step,
@@ -317,6 +342,8 @@ class sparse_MF_SP(nn.Module):
                 else:
                     P = lik.marginal_moments(mean_q_f.squeeze(2), cov_q_f.squeeze(2), self.G_matrix, X)
                 m1, m2 = P, None
+            elif isinstance(lik, MulticlassCategorical):
+                m1, m2 = lik.marginal_moments(mean_q_f.squeeze(2), cov_q_f.squeeze(2), self.G_matrix, X), None
             else:
                 raise ValueError('Unsupported likelihood [{}]'.format(type(lik)))
         self.train()
@@ -356,11 +383,12 @@ class sparse_MF_SP(nn.Module):
                 log_p_y = torch.stack(logp)
                 if return_moments:
                     predictive_params = [torch.stack(m1), torch.stack(m2)]
-            elif isinstance(lik, Bernoulli):
+            elif isinstance(lik, (Bernoulli, MulticlassCategorical)):
                 m_Y, _, _, _ = self.predictive_distribution(X_run, diagonal=True, S_MC_NNet=S_MC_NNet)
                 assert torch.isfinite(m_Y).all(), 'Got saturated probabilities'
-                m_Y = m_Y.squeeze()
-                m_Y = torch.stack((1.0 - m_Y, m_Y), dim=1)
+                if isinstance(lik, Bernoulli):      # as if it came from the categorical likelihood: (MB, 2)
+                    m_Y = m_Y.squeeze()
+                    m_Y = torch.stack((1.0 - m_Y, m_Y), dim=1)
                 # the reference scores classification in float32 (sparse_MF_SP.py:813)
                 nll = -torch.log(m_Y.float().gather(1, Y.view(-1, 1).long())).mean()
                 log_p_y = -1 * ((nll * MB).sum())

@@ -218,6 +218,7 @@ class _QfMarginals(torch.autograd.Function):
         rb = engine.new_reduce_buffer()
         zeros = torch.zeros(X.shape[0], dtype=torch.float64, device=X.device)
         engine.qf_backward(X, zeros if g_mu is None else g_mu.contiguous(), zeros if g_v is None else g_v.contiguous(), rb)
+        allreduce_packed(engine, rb)               # row-sharded callers (multiclass ELBO): sum over ranks before the chain
         out = engine.chain_backward(rb, 1.0, 0.0)
         return None, None, None, None, out['Z'], out['raw_ls'], out['raw_os'], out['m'], out['L_raw']
 
