@@ -262,9 +262,6 @@ int tgp_kmeans_iteration(const void* X, long N, int D, void* C, int M, int* assi
  * TGP_OPT_ROW_CHUNK (FP64 mode): rows per launch of the batch contractions (default 32768; a tuning knob — it changes the
  * workspace size, so set it before asking for tgp_batch_workspace_bytes). */
 enum { TGP_OPT_FUSED_FORWARD = 1, TGP_OPT_ROW_CHUNK = 2,
-       TGP_OPT_FUSED_KBAR_GRADS = 4, /* TGP_F64_I8: 1 = the CRT reconstruction of Kbar also accumulates Kbar o K -> dZ, dlengthscale,
-                                      * doutputscale (Kbar is never written); 0 (default): reconstruction + stand-alone gradient
-                                      * kernel, which measures faster */
        TGP_OPT_OVERLAP_KGEN = 3 };   /* 1 (default): tgp_prepare forks the factorisation onto a library-owned high-priority stream;
                                       * tgp_qf_forward enqueues K_xz generation on the caller's stream and joins afterwards, every
                                       * other consumer of the step workspace joins first; 0: everything on the caller's stream.

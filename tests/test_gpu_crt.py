@@ -162,29 +162,3 @@ def test_class_api_in_i8crt_mode(name):
         assert rel_err(lp.double().sum().cpu(), g.t('test_logp')) < (1e-5 if bern else 1e-10)
     finally:
         cg.compute = old
-
-
-def test_fused_kbar_gradient_kernel_matches_the_two_kernel_form():
-    """TGP_OPT_FUSED_KBAR_GRADS: reconstruction of Kbar fused with Kbar o K -> dZ, dlengthscale, doutputscale (opt-in; slower)."""
-    from tests.gpu_util import engine_inputs, make_engine
-    from tgp.pytorch_b200 import _lib, functional as Fn
-    lib = _lib.load()
-    g = Golden('synth_reg_d8_m1024_p1')
-    p = g.oracle_params('train')
-    X, Y = g.t('X').to(DEV).contiguous(), g.t('Y').view(-1).to(DEV).contiguous()
-    grads = []
-    for fused in (0, 1):
-        try:
-            _lib.check(lib.tgp_set_option(_lib.OPT_FUSED_KBAR_GRADS, fused), 'tgp_set_option')
-            eng, theta, rowp, names = make_engine(p, 'gauss_nonlinear', g.meta['n_quad'], DEV, compute='i8crt')
-            ei = engine_inputs(p, DEV)
-            leaves = [ei['Z'], ei['raw_ls'], ei['raw_os'], ei['m'], ei['L_raw'], ei['log_var_noise'], theta]
-            for t in leaves:
-                t.requires_grad_(True)
-            ELL, KLD, _, _, _ = Fn.elbo_terms(eng, X, Y, g.meta['N'] / X.shape[0], *leaves, None)
-            (ELL - KLD).backward()
-            grads.append([t.grad.clone() for t in leaves[:3]])
-        finally:
-            lib.tgp_set_option(_lib.OPT_FUSED_KBAR_GRADS, 0)
-    for a, b in zip(*grads):
-        assert rel_err(b.cpu(), a.cpu()) < 1e-12

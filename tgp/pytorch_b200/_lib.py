@@ -7,6 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TGP_B200_LIB', os.path.join(_HERE, 'libtgp_b200.so'))
+LIB_PATH = os.environ.get('TGP_B200_LIB', LIB_PATH)      # A/B builds of the same sources (scripts/, profiling)
 
 TGP_F64, TGP_F32, TGP_F64_I8 = 0, 1, 2
 LIK_GAUSS_LINEAR, LIK_GAUSS_NONLINEAR, LIK_BERNOULLI = 0, 1, 2
@@ -17,7 +18,6 @@ MAX_LAYERS = 64
 OPT_FUSED_FORWARD = 1
 OPT_ROW_CHUNK = 2
 OPT_OVERLAP_KGEN = 3
-OPT_FUSED_KBAR_GRADS = 4
 
 
 class TgpFlowLayer(C.Structure):

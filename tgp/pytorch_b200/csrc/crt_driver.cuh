@@ -9,7 +9,6 @@
 #include "gemm_i8.cuh"
 
 namespace tgp {
-extern int g_fused_kbar_grads;
 namespace crt {
 
 using i8::Planes;
@@ -27,17 +26,19 @@ inline int bits_other(int T, long k_red, int fixed) {
 // forward  [A | B] = K W^T, reduction M: K carries 53 bits (one scale for the whole matrix); 15 moduli if W keeps >= 52 bits
 inline int fwd_T(int M) { return bits_other(15, M, 53) >= 52 ? 15 : 16; }
 inline int fwd_bits_w(int M) { return bits_other(fwd_T(M), M, 53); }
-// backward-data  Kbar = ABbar Wt^T, reduction 2M: equal bits for both operands
-inline int bwd_T(int M) { return i8::crt_bits(15, 2L * M) >= 52 ? 15 : 16; }
-inline int bwd_bits(int M) { return i8::crt_bits(bwd_T(M), 2L * M); }
+// backward-data  Kbar = ABbar W~, reduction 2M: ABbar carries the bits of the weight contraction's planes (one set serves both);
+// 15 moduli if W~ keeps >= 52 bits
+inline int bwd_T(int M, int bits_x) { return bits_other(15, 2L * M, bits_x) >= 52 ? 15 : 16; }
+inline int bwd_bits_w(int M, int bits_x) { return bits_other(bwd_T(M, bits_x), 2L * M, bits_x); }
 // weight contraction  [Gbar; Cbar] += ABbar^T K, reduction = rows of the chunk: all 16 moduli, K^T carries 53 bits
 inline int wgt_bits(long rc) { return bits_other(T_ALL, rc, 53); }
 
 struct StepPlanes {               // per step: residues of W = [Linv; C] (2M x M), scaled per row and scaled per column
     double* Wst;                  // FP64 stacked operand (2M x M, ld M)
     uint8_t *W;                    // planes [T][2M][ldk], per-row scale: forward operand (reduction over its columns, K-major)
-    uint8_t *Wc;                   // planes [T][2M][ldk], per-column scale: backward-data operand Kbar = ABbar W (reduction over
-                                  // its ROWS: the tensor core reads it MN-major, no transposed copy)
+    uint8_t *Wc;                   // planes [T][2M][ldk] of W~ = diag(2^c) W, per-column scale: backward-data operand, rebuilt per row
+                                  // chunk (c = column exponents of that chunk's [Abar | Bbar]); reduction over its ROWS: the tensor
+                                  // core reads it MN-major, no transposed copy
     int *w_row_exp, *w_col_exp, *k_exp;
     long ldk;
 };
@@ -66,11 +67,12 @@ struct BatchView {
     double *Kbuf;                 // (R x M) FP64 K_xz (kernel gradients read it)
     double *Kbar;                 // (Rc x M)
     uint8_t *Kp;                   // planes [T_ALL][R][ldk]   K_xz residues: forward operand AND weight-contraction operand
-    uint8_t *Op;                   // planes [T][Rc][ld2m]     result residues of the forward; then ABbar scaled per row
-    uint8_t *Pc;                   // planes [T_ALL][Rc][ld2m] ABbar scaled per column (weight-contraction operand, MN-major)
+    uint8_t *Op;                   // planes [T][Rc][ld2m]     result residues of the forward
+    uint8_t *Pc;                   // planes [T_ALL][Rc][ld2m] ABbar scaled per column: K-major operand of Kbar = ABbar W~ and MN-major
+                                  // operand of the weight contraction
     uint8_t *Kbp;                  // planes [T][Rc][ldk]      Kbar result residues
     uint8_t *Gp;                   // planes [T_ALL][2M][ldk]  weight-contraction result residues
-    int *row_exp, *col_exp;       // (Rc), (2M)
+    int *col_exp, *wc_exp, *zero_exp;   // (2M) column exponents of ABbar, (M) of W~, a zero
     long Rc, ldk, ld2m;
 };
 
@@ -80,7 +82,7 @@ inline size_t batch_bytes(int M, long R) {
     b += (size_t)R * 2 * M * 8 + (size_t)R * M * 8 + (size_t)Rc * M * 8;
     b += (size_t)T_ALL * R * ldk;
     b += (size_t)2 * T_ALL * Rc * ld2m + (size_t)T_ALL * Rc * ldk + (size_t)T_ALL * 2 * M * ldk;
-    b += (size_t)(Rc + 2L * M + 64) * sizeof(int) + 4096;
+    b += (size_t)(3L * M + 64) * sizeof(int) + 4096;
     return b;
 }
 
@@ -97,8 +99,9 @@ inline BatchView carve_batch(void* ws, int M, long R) {
     b.Pc = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
     b.Kbp = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * b.Rc * b.ldk));
     b.Gp = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * 2 * M * b.ldk));
-    b.row_exp = reinterpret_cast<int*>(take((size_t)b.Rc * sizeof(int)));
     b.col_exp = reinterpret_cast<int*>(take((size_t)2 * M * sizeof(int)));
+    b.wc_exp = reinterpret_cast<int*>(take((size_t)M * sizeof(int)));
+    b.zero_exp = reinterpret_cast<int*>(take(sizeof(int)));
     return b;
 }
 
@@ -153,22 +156,6 @@ inline int combine(const uint8_t* R, long ldr, long plane_stride, long rows, int
     return check_launch("k_crt_combine");
 }
 
-inline int combine_kgrads(const uint8_t* R, long ldr, long plane_stride, long rows, int M, int T, int bits2, const int* ea, const int* eb,
-                          const double* Kval, long ldk, const double* X, const double* Zs, const double* ls, const double* os, int D,
-                          double* dZ, double* dls, double* dos, cudaStream_t st) {
-    // opt-in (TGP_OPT_FUSED_KBAR_GRADS): measured at cfg4 the fused kernel needs 255 registers (one CTA per SM) and takes 0.45 ms per
-    // 16384-row chunk against 0.20 + 0.15 ms for reconstruction + stand-alone gradient kernel, so the two-kernel form is the default
-    if (!g_fused_kbar_grads || D > 16 || (T != 15 && T != 16)) return -7;
-    const i8::CrtTable& tab = i8::crt_table(T);
-    dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rows, i8::KG_RB));
-#define TGP_CK(TT, MD) i8::k_crt_combine_kgrads<TT, MD><<<grid, 256, 0, st>>>(R, ldr, plane_stride, rows, M, tab, bits2, ea, eb, Kval, ldk, X, \
-                                                                            Zs, ls, os, D, dZ, dls, dos)
-    if (T == 15) { if (D <= 4) TGP_CK(15, 4); else if (D <= 8) TGP_CK(15, 8); else TGP_CK(15, 16); }
-    else { if (D <= 4) TGP_CK(16, 4); else if (D <= 8) TGP_CK(16, 8); else TGP_CK(16, 16); }
-#undef TGP_CK
-    return check_launch("k_crt_combine_kgrads");
-}
-
 // K_xz of a row chunk in one pass: FP64 values and residue planes (i8::k_rbf_residues)
 inline int rbf_residues(const double* X, const double* Zs, const double* ls, const double* os, long R, int M, int D, double* Kout,
                         int T, uint8_t* planes, long ldp, long plane_stride, cudaStream_t st, int ctas_per_sm = 3) {
@@ -186,7 +173,7 @@ inline int rbf_residues(const double* X, const double* Zs, const double* ls, con
     return check_launch("k_rbf_residues");
 }
 
-// per step, after run_prepare: residues of W scaled per row (forward) and scaled per column (backward-data)
+// per step, after run_prepare: residues of W scaled per row (forward operand; the backward-data operand is built per chunk)
 inline int make_step_planes(const StepView& v, void* region, cudaStream_t st) {
     const int M = v.M;
     StepPlanes s = carve_step(region, M);
@@ -194,19 +181,27 @@ inline int make_step_planes(const StepView& v, void* region, cudaStream_t st) {
     TGP_TRY(check_launch("k_stack_w"));
     k_exp_of_scalar<<<1, 1, 0, st>>>(v.os, s.k_exp);
     TGP_TRY(check_launch("k_exp_of_scalar"));
-    TGP_TRY(exponents(s.Wst, M, 2L * M, M, s.w_row_exp, s.w_col_exp, st));
-    return to_residues(s.Wst, M, 2L * M, M, 0, s.w_row_exp, fwd_bits_w(M), fwd_T(M), s.W, s.ldk, 2L * M * s.ldk, st,
-                       1, s.w_col_exp, bwd_bits(M), bwd_T(M), s.Wc, s.ldk, 2L * M * s.ldk);
+    TGP_TRY(exponents(s.Wst, M, 2L * M, M, s.w_row_exp, nullptr, st));
+    return to_residues(s.Wst, M, 2L * M, M, 0, s.w_row_exp, fwd_bits_w(M), fwd_T(M), s.W, s.ldk, 2L * M * s.ldk, st);
 }
 
-// [A | B] + upstream row gradients -> [Abar | Bbar] IN PLACE (Abar = g_mu m - 2 g_v A, Bbar = 2 g_v B); accumulates
-// dm[j] += sum_n g_mu A[n,j] and dos += sum_n g_v.  64 rows x 128 columns per CTA.
-// row_exp / col_exp (pre-set to a very small value): binary exponents above the row / column maxima of [Abar | Bbar], the
-// scales of its two integerisations.
-__global__ void __launch_bounds__(128) k_make_abbar_inplace(double* __restrict__ AB, const double* __restrict__ g_mu,
-                                                            const double* __restrict__ g_v, const double* __restrict__ m, long R,
-                                                            int M, double* __restrict__ dm, double* __restrict__ dos,
-                                                            int* __restrict__ row_exp, int* __restrict__ col_exp) {
+// ---- backward operand: [Abar | Bbar] is never materialised ------------------------------------------------------------
+// Abar = g_mu m - 2 g_v A, Bbar = 2 g_v B (upstream row gradients applied to the forward's [A | B], which stays untouched).
+// Both contractions that consume it — Kbar = [Abar | Bbar] W over its columns and [Gbar; Cbar] += [Abar | Bbar]^T K over its
+// rows — read ONE set of residue planes, integerised per COLUMN (exponent c_j above the column maximum of the chunk): the
+// row contraction needs a scale that is constant along the reduction, so 2^c_j moves into the other operand, W~ = diag(2^c) W,
+// whose planes are rebuilt per chunk (2M x M elements: 6 % of the chunk).  Every consumer of Kbar sums over the rows
+// (Kbar o K -> dZ, dlengthscale, doutputscale), so a column-wise fixed point — absolute accuracy 2^-53 of the column maximum —
+// is what FP64 accumulation of those sums delivers too.
+__device__ __forceinline__ double abbar_value(double gm, double gv, double mj, double ab, bool left) {
+    return left ? gm * mj - 2.0 * gv * ab : 2.0 * gv * ab;
+}
+
+// pass 1: column exponents of [Abar | Bbar] (pre-set to a very small value), dm[j] += sum_n g_mu A[n,j], dos += sum_n g_v.
+// 64 rows x 128 columns per CTA.
+__global__ void __launch_bounds__(128) k_abbar_stats(const double* __restrict__ AB, const double* __restrict__ g_mu,
+                                                     const double* __restrict__ g_v, const double* __restrict__ m, long R, int M,
+                                                     double* __restrict__ dm, double* __restrict__ dos, int* __restrict__ col_exp) {
     const int j = blockIdx.x * 128 + threadIdx.x;
     const long n0 = (long)blockIdx.y * 64, n1 = min(n0 + 64, R);
     const double mj = j < M ? m[j] : 0.0;
@@ -215,21 +210,13 @@ __global__ void __launch_bounds__(128) k_make_abbar_inplace(double* __restrict__
     for (long n = n0; n < n1; ++n) {
         const double gm = g_mu[n], gv = g_v[n];
         accv += gv;
-        int re = -100000;
         if (j < M) {
-            double* row = AB + n * 2 * M;
+            const double* row = AB + n * 2 * M;
             const double a = row[j], b = row[M + j];
             acc = fma(gm, a, acc);
-            const double abar = gm * mj - 2.0 * gv * a, bbar = 2.0 * gv * b;
-            row[j] = abar;
-            row[M + j] = bbar;
-            const int ea = i8::exp_above(abar), eb = i8::exp_above(bbar);
-            ca = max(ca, ea); cb = max(cb, eb);
-            re = max(ea, eb);
+            ca = max(ca, i8::exp_above(abbar_value(gm, gv, mj, a, true)));
+            cb = max(cb, i8::exp_above(abbar_value(gm, gv, mj, b, false)));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) re = max(re, __shfl_xor_sync(0xffffffffu, re, o));
-        if ((threadIdx.x & 31) == 0 && re > -100000) atomicMax(row_exp + n, re);
     }
     if (j < M) {
         atomicAdd(dm + j, acc);
@@ -237,6 +224,57 @@ __global__ void __launch_bounds__(128) k_make_abbar_inplace(double* __restrict__
         atomicMax(col_exp + M + j, cb);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(dos, accv);
+}
+
+// pass 2: residue planes[t][n][j] of rint([Abar | Bbar][n,j] 2^(bits - c_j)); tile and thread layout of i8::k_to_residues
+__global__ void __launch_bounds__(256) k_abbar_residues(const double* __restrict__ AB, long rows, int M, const double* __restrict__ g_mu,
+                                                        const double* __restrict__ g_v, const double* __restrict__ m,
+                                                        const int* __restrict__ col_exp, int bits, i8::CrtTable tab,
+                                                        uint8_t* __restrict__ planes, long ldp, long plane_stride) {
+    const long r = (long)blockIdx.y * i8::RS_TR + (threadIdx.x >> 3);
+    const int c = blockIdx.x * i8::RS_TC + (threadIdx.x & 7) * 16;
+    const int cols = 2 * M;
+    const double gm = r < rows ? g_mu[r] : 0.0, gv = r < rows ? g_v[r] : 0.0;
+    long long xi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = c + i;
+        double x = 0.0;
+        int e = 0;
+        if (r < rows && j < cols) {
+            x = abbar_value(gm, gv, j < M ? m[j] : 0.0, AB[r * cols + j], j < M);
+            e = col_exp[j];
+        }
+        xi[i] = __double2ll_rn(i8::mul_pow2(x, bits - e));
+    }
+    i8::emit_residues_rt(tab.T, xi, tab, r, rows, c, cols, planes, ldp, plane_stride);
+}
+
+// W~ = diag(2^c) W (2M x M): exponent above each column maximum (pre-set to a very small value) ...
+__global__ void __launch_bounds__(256) k_wt_colexp(const double* __restrict__ W, int rows, int M, const int* __restrict__ row_shift,
+                                                   int* __restrict__ wc_exp) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int j0 = blockIdx.y * 64, j1 = min(j0 + 64, rows);
+    if (k >= M) return;
+    int e = -200000;
+    for (int j = j0; j < j1; ++j) e = max(e, row_shift[j] + i8::exp_above(W[(long)j * M + k]));
+    atomicMax(wc_exp + k, e);
+}
+
+// ... and its residue planes[t][j][k] of rint(W[j,k] 2^(c_j + bits - e_k)): the backward-data operand, read MN-major
+__global__ void __launch_bounds__(256) k_wt_residues(const double* __restrict__ W, long rows, int M, const int* __restrict__ row_shift,
+                                                     const int* __restrict__ wc_exp, int bits, i8::CrtTable tab,
+                                                     uint8_t* __restrict__ planes, long ldp, long plane_stride) {
+    const long r = (long)blockIdx.y * i8::RS_TR + (threadIdx.x >> 3);
+    const int c = blockIdx.x * i8::RS_TC + (threadIdx.x & 7) * 16;
+    const int sh = r < rows ? row_shift[r] + bits : 0;
+    long long xi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool in = r < rows && c + i < M;
+        xi[i] = in ? __double2ll_rn(i8::mul_pow2(W[r * M + c + i], sh - wc_exp[c + i])) : 0ll;
+    }
+    i8::emit_residues_rt(tab.T, xi, tab, r, rows, c, M, planes, ldp, plane_stride);
 }
 
 inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, const double* X, long R, double* mu, double* v,
@@ -279,38 +317,45 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
     StepPlanes sp = carve_step(step_region, M);
     BatchView b = carve_batch(batch_ws, M, R);
     if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
-    const int Tb = bwd_T(M), bits_b = bwd_bits(M);
+    TGP_TRY(fill_int(b.zero_exp, 1, 0, st));
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
-        double* ABc = b.AB + r0 * 2 * M;
+        const double* ABc = b.AB + r0 * 2 * M;
+        // [Abar | Bbar] of the chunk: column exponents (+ dm, doutputscale), then ONE set of residue planes scaled per column
+        const int Tw = T_ALL, bits_x = wgt_bits(rc);
+        const int Tb = bwd_T(M, bits_x), bits_w = bwd_bits_w(M, bits_x);
         {
-            TGP_TRY(fill_int(b.row_exp, rc, -100000, st));
             TGP_TRY(fill_int(b.col_exp, 2L * M, -100000, st));
             dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rc, 64));
-            k_make_abbar_inplace<<<grid, 128, 0, st>>>(ABc, g_mu + r0, g_v + r0, s.mvec, rc, M, dm, dos, b.row_exp, b.col_exp);
-            TGP_TRY(check_launch("k_make_abbar_inplace"));
+            k_abbar_stats<<<grid, 128, 0, st>>>(ABc, g_mu + r0, g_v + r0, s.mvec, rc, M, dm, dos, b.col_exp);
+            TGP_TRY(check_launch("k_abbar_stats"));
+            dim3 rgrid((unsigned)cdiv(2L * M, i8::RS_TC), (unsigned)cdiv(rc, i8::RS_TR));
+            k_abbar_residues<<<rgrid, 256, 0, st>>>(ABc, rc, M, g_mu + r0, g_v + r0, s.mvec, b.col_exp, bits_x, i8::crt_table(Tw), b.Pc,
+                                                    b.ld2m, (long)b.Rc * b.ld2m);
+            TGP_TRY(check_launch("k_abbar_residues"));
         }
-        // one pass over [Abar | Bbar]: residues scaled per row (operand of Kbar = ABbar W) and per column (operand of ABbar^T K)
-        const int Tw = T_ALL, bits_w = wgt_bits(rc);
-        TGP_TRY(to_residues(ABc, 2L * M, rc, 2 * M, 0, b.row_exp, bits_b, Tb, b.Op, b.ld2m, (long)b.Rc * b.ld2m, st,
-                            1, b.col_exp, bits_w, Tw, b.Pc, b.ld2m, (long)b.Rc * b.ld2m));
-        {   // Kbar (rc x M) = ABbar (rc x 2M) * W (2M x M); for k < M only k >= n contributes.  A is K-major; the reduction runs
-            // over the ROWS of W, whose per-column-scaled row-major planes the tensor core reads MN-major (mn_major bit 1)
+        {   // W~ = diag(2^c) W for this chunk's column exponents: per-column scale e_k, planes read MN-major by the tensor core
+            TGP_TRY(fill_int(b.wc_exp, M, -200000, st));
+            dim3 egrid((unsigned)cdiv(M, 256), (unsigned)cdiv(2L * M, 64));
+            k_wt_colexp<<<egrid, 256, 0, st>>>(sp.Wst, 2 * M, M, b.col_exp, b.wc_exp);
+            TGP_TRY(check_launch("k_wt_colexp"));
+            dim3 rgrid((unsigned)cdiv(M, i8::RS_TC), (unsigned)cdiv(2L * M, i8::RS_TR));
+            k_wt_residues<<<rgrid, 256, 0, st>>>(sp.Wst, 2L * M, M, b.col_exp, b.wc_exp, bits_w, i8::crt_table(Tb), sp.Wc, sp.ldk,
+                                                 2L * M * sp.ldk);
+            TGP_TRY(check_launch("k_wt_residues"));
+        }
+        {   // Kbar (rc x M) = ABbar (rc x 2M) * W~ (2M x M); for k < M only k >= n contributes.  A is K-major (the first Tb of the
+            // Tw planes: the moduli of a shorter table are a prefix); the reduction runs over the ROWS of W~ (mn_major bit 1)
             i8::Params p{};
             p.Mrows = rc; p.Ncols = M; p.K = 2 * M; p.T = Tb; p.tri_mode = 2; p.tri_rows = M; p.lower_rows = 0; p.mn_major = 2;
             p.C = b.Kbp; p.ldc = b.ldk; p.plane_stride_c = (long)b.Rc * b.ldk;
-            Planes A{b.Op, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
+            Planes A{b.Pc, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
             Planes B{sp.Wc, 2L * M, M, sp.ldk, 2L * M * sp.ldk};
             TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
         }
-        // reconstruction of Kbar fused with Kbar o K -> dZ, dlengthscale, doutputscale (Kbar is never written); wider inputs
-        // reconstruct into the staging buffer and run the stand-alone gradient kernel
-        const int fr = combine_kgrads(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, sp.w_col_exp, b.Kbuf + r0 * M, M,
-                                      X + r0 * D, s.Zs, s.ls, s.os, D, dZ, dls, dos, st);
-        if (fr == -7) {
-            TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, 2 * bits_b, b.row_exp, 0, sp.w_col_exp, 1, b.Kbar, M, 0, 0, st));
-            TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
-        } else if (fr != 0) return fr;
+        // reconstruction of Kbar, then Kbar o K -> dZ, dlengthscale, doutputscale
+        TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, bits_x + bits_w, b.zero_exp, 2, b.wc_exp, 1, b.Kbar, M, 0, 0, st));
+        TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
         {   // [Gbar; Cbar] (2M x M) += ABbar^T K: reduction over the chunk rows; both operands are row-major planes read MN-major
             i8::Params p{};
             p.Mrows = 2 * M; p.Ncols = M; p.K = rc; p.T = Tw; p.tri_mode = 0; p.tri_rows = 0; p.lower_rows = M; p.mn_major = 3;
@@ -318,9 +363,9 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
             Planes A{b.Pc, rc, 2L * M, b.ld2m, (long)b.Rc * b.ld2m};
             Planes B{b.Kp + r0 * b.ldk, rc, M, b.ldk, R * b.ldk};
             TGP_TRY(i8::gemm_i8_mod(A, B, p, st));
-            // K residues carry 53 bits, ABbar (per column) bits_w
-            TGP_TRY(combine(b.Gp, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_w + 53, b.col_exp, 0, sp.k_exp, 2, Gbar, s.Mp, 1, M, st));
-            TGP_TRY(combine(b.Gp + (long)M * b.ldk, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_w + 53, b.col_exp + M, 0, sp.k_exp, 2, Cbar,
+            // K residues carry 53 bits, ABbar (per column) bits_x
+            TGP_TRY(combine(b.Gp, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_x + 53, b.col_exp, 0, sp.k_exp, 2, Gbar, s.Mp, 1, M, st));
+            TGP_TRY(combine(b.Gp + (long)M * b.ldk, b.ldk, 2L * M * b.ldk, M, M, Tw, bits_x + 53, b.col_exp + M, 0, sp.k_exp, 2, Cbar,
                             s.Mp, 1, 0, st));
         }
     }

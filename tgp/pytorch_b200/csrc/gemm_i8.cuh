@@ -1,13 +1,13 @@
-// FP64-accurate contraction on the tcgen05 INTEGER tensor path (kind::i8, s8 x s8 -> s32 in TMEM): the batch contractions
+// FP64-accurate contraction on the tcgen05 INTEGER tensor path (kind::i8, u8 x u8 -> 32-bit in TMEM): the batch contractions
 // of compute mode TGP_F64_I8.
 //
 // tcgen05 has no f64 kind, and a floating-point split (3xTF32, gemm_tc.cuh) is limited by the FP32 accumulator.  Integer
 // MMAs accumulate EXACTLY, so the product can be rebuilt exactly from residues (Chinese remainder theorem; "Ozaki scheme
 // II" in the literature):
 //   1. integerise  A'[i,:] = rint(A[i,:] 2^(b - eA_i)),  2^eA_i > max_j |A_ij|   (|A'| < 2^b, b <= 53; likewise B per row)
-//   2. residues    A_t = A' mod p_t  (centred, int8)  for T pairwise coprime moduli p_t <= 256            [k_to_residues]
-//   3. T independent int8 GEMMs with exact s32 accumulation, reduced mod p_t in the epilogue: R_t = A_t B_t^T mod p_t
-//      (int8 again)                                                                                      [gemm_i8_mod_kernel]
+//   2. residues    A_t = A' mod p_t  in [0, p_t), u8,  for T pairwise coprime moduli p_t <= 256           [k_to_residues]
+//   3. T independent u8 GEMMs with exact 32-bit accumulation, reduced mod p_t in the epilogue: R_t = A_t B_t^T mod p_t
+//      (u8 again)                                                                                        [gemm_i8_mod_kernel]
 //   4. CRT         C' = sum_t R_t w_t - m P   in 40-bit words whose partial sums are exact in FP64,  m = rint(sum_t R_t w_t/P)
 //   5. scale       C = C' 2^(eA_i + eB_j - 2b)                                                            [k_crt_combine]
 // The integer product is exact; the only error is the b-bit truncation of the operands below their row maximum
@@ -683,92 +683,6 @@ __global__ void __launch_bounds__(256) k_crt_combine(const uint8_t* __restrict__
             if (lane == 0) { st.mu[r] = sm; st.v[r] = st.os[0] - sa + sb; }
         }
     }
-}
-
-__device__ __forceinline__ double rls_of(const double* __restrict__ ls, int d) { return 1.0 / ls[d]; }
-
-// Reconstruction of Kbar = dELL/dK_xz FUSED with the kernel-matrix derivatives: Kbar is never written.  For every
-// reconstructed entry t = Kbar[n,j] * K[n,j] (K_xz kept in FP64 by the forward) the CTA accumulates
-//   dZ[j,d] += t (xs[n,d] - zs[j,d]) / ls[d],   dls[d] += t (xs[n,d] - zs[j,d])^2 / ls[d],   dos += t / os
-// (xs = x / ls, zs = z / ls; reference: autograd through the gpytorch RBF kernel, sparse_MF_SP.py:319).
-// CTA = 128 columns x KG_RB rows; a warp walks rows, a lane owns four consecutive columns (one 32-bit word per residue plane)
-// and keeps their 4 x D + D + 1 partial sums in registers; inducing rows sit in shared memory.
-constexpr int KG_RB = 256;
-template <int T, int MAXD>
-__global__ void __launch_bounds__(256) k_crt_combine_kgrads(const uint8_t* __restrict__ R, long ldr, long plane_stride, long rows, int M,
-                                                            const __grid_constant__ CrtTable tab, int bits2, const int* __restrict__ ea,
-                                                            const int* __restrict__ eb, const double* __restrict__ Kval, long ldk,
-                                                            const double* __restrict__ X, const double* __restrict__ Zs,
-                                                            const double* __restrict__ ls, const double* __restrict__ os, int D,
-                                                            double* __restrict__ dZ, double* __restrict__ dls, double* __restrict__ dos) {
-    __shared__ double zs[128][MAXD + 1];
-    __shared__ double sZ[128][MAXD + 1];
-    __shared__ double sl[MAXD + 1];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int cbase = blockIdx.x * 128;
-    const long r0 = (long)blockIdx.y * KG_RB, r1 = min(r0 + KG_RB, rows);
-    for (int i = threadIdx.x; i < 128 * MAXD; i += 256) {
-        const int c = i / MAXD, d = i % MAXD, j = cbase + c;
-        zs[c][d] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
-        sZ[c][d] = 0.0;
-    }
-    if (threadIdx.x <= MAXD) sl[threadIdx.x] = 0.0;
-    __syncthreads();
-    const int c0 = cbase + lane * 4;
-    double az[4][MAXD], al[MAXD], asum = 0.0;
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) { al[d] = 0.0; az[0][d] = az[1][d] = az[2][d] = az[3][d] = 0.0; }
-    int e4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) e4[i] = c0 + i < M ? eb[c0 + i] : 0;
-    double rls[MAXD];
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) rls[d] = d < D ? 1.0 / ls[d] : 0.0;
-    if (c0 < M) {
-        for (long r = r0 + wid; r < r1; r += 8) {
-            uint32_t w[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) w[t] = *reinterpret_cast<const uint32_t*>(R + (long)t * plane_stride + r * ldr + c0);
-            const int era = ea[r] - bits2;
-            double xs[MAXD];
-#pragma unroll
-            for (int d = 0; d < MAXD; ++d) xs[d] = d < D ? X[r * D + d] * rls[d] : 0.0;
-            double kv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) kv[i] = c0 + i < M ? Kval[r * ldk + c0 + i] : 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double tt = mul_pow2(crt_value<T>(w, i, tab), era + e4[i]) * kv[i];
-                asum += tt;
-#pragma unroll
-                for (int d = 0; d < MAXD; ++d) {
-                    const double df = xs[d] - zs[lane * 4 + i][d];
-                    az[i][d] = fma(tt, df, az[i][d]);
-                    al[d] = fma(tt * df, df, al[d]);
-                }
-            }
-        }
-    }
-    // CTA reduction: per-column sums through shared-memory atomics, then one global atomic per (column, dimension)
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int d = 0; d < MAXD; ++d)
-            if (d < D && az[i][d] != 0.0) atomicAdd(&sZ[lane * 4 + i][d], az[i][d]);
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) {
-        const double v = warp_sum(al[d]);
-        if (lane == 0 && d < D) atomicAdd(&sl[d], v);
-    }
-    asum = warp_sum(asum);
-    if (lane == 0) atomicAdd(&sl[MAXD], asum);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 128 * MAXD; i += 256) {
-        const int c = i / MAXD, d = i % MAXD, j = cbase + c;
-        if (j < M && d < D && sZ[c][d] != 0.0) atomicAdd(dZ + (long)j * D + d, sZ[c][d] * rls_of(ls, d));
-    }
-    if (threadIdx.x < D) atomicAdd(dls + threadIdx.x, sl[threadIdx.x] / ls[threadIdx.x]);
-    if (threadIdx.x == 0) atomicAdd(dos, sl[MAXD] / os[0]);
 }
 
 inline int crt_grid(long rows) {

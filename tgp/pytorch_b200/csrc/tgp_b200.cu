@@ -19,7 +19,6 @@ long g_launch_count = 0;
 GemmTimer g_gemm_timer;
 namespace tc { int g_fused_forward = 0; }
 int g_overlap_kgen = 1;
-int g_fused_kbar_grads = 0;
 
 long g_row_chunk = 32768;             // rows per launch of the batch contractions (Kbar / Abar staging); measured at cfg4:
                                       // 8192 -> 20.3 ms/step, 16384 -> 20.0, 32768 -> 19.6, 65536 -> 19.5
@@ -759,7 +758,6 @@ long tgp_launch_count(void) { return g_launch_count; }
 int tgp_set_option(int key, int value) {
     if (key == TGP_OPT_FUSED_FORWARD) { tc::g_fused_forward = value != 0; return 0; }
     if (key == TGP_OPT_OVERLAP_KGEN) { g_overlap_kgen = value != 0; return 0; }
-    if (key == TGP_OPT_FUSED_KBAR_GRADS) { g_fused_kbar_grads = value != 0; return 0; }
     if (key == TGP_OPT_ROW_CHUNK) {
         if (value < 128) return set_error(-1, "row chunk must be >= 128");
         g_row_chunk = value;
