@@ -18,21 +18,22 @@ N_WORDS = 4
 
 
 def crt_constants(T):
-    """Per modulus: weight words w_tk (k < N_WORDS, each < 2^40), fraction w_t / P; and the words of P."""
+    """Per modulus: the BYTES of the CRT weight w_t = (P / p_t) ((P / p_t)^-1 mod p_t) (16 bytes, little endian), the fraction
+    w_t / P; and the 40-bit words of P."""
     ps = MODULI[:T]
     P = 1
     for p in ps:
         P *= p
-    words = np.zeros((T, N_WORDS), dtype=np.float64)
+    wbytes = np.zeros((T, 16), dtype=np.int64)
     frac = np.zeros(T, dtype=np.float64)
     for t, p in enumerate(ps):
         q = P // p
         w = q * pow(q % p, -1, p)
         frac[t] = w / P                                   # Python int true division: correctly rounded
-        for k in range(N_WORDS):
-            words[t, k] = float((w >> (WORD_BITS * k)) & ((1 << WORD_BITS) - 1))
+        for k in range(16):
+            wbytes[t, k] = (w >> (8 * k)) & 0xff
     Pw = np.array([float((P >> (WORD_BITS * k)) & ((1 << WORD_BITS) - 1)) for k in range(N_WORDS)])
-    return P, words, frac, Pw
+    return P, wbytes, frac, Pw
 
 
 def max_bits(T, k_red):
@@ -71,27 +72,44 @@ def gemm_mod(Ar, Br, T):
 
 
 def combine(R, eA, eB, bA, bB, T):
-    """CRT reconstruction in FP64 words (device arithmetic) and scaling back: (rows, cols) float64."""
-    _, words, frac, Pw = crt_constants(T)
-    r = R.astype(np.float64)
-    S = [np.zeros(R.shape[1:]) for _ in range(N_WORDS)]
+    """CRT reconstruction as the device does it (k_crt_combine) and scaling back: (rows, cols) float64.
+    Integer byte sums S_k = sum_t r_t byte_k(w_t) (the device's dp4a), four 40-bit-spaced words W_j = sum_{i<5} S_{5j+i} 256^i
+    (< 2^53: exact in FP64), m = rint(total / P) from the FP64 evaluation of the words, W_j - m P_j (exact), carries, and the
+    final three multiply-adds (the only roundings)."""
+    P, wbytes, frac, Pw = crt_constants(T)
+    r = R.astype(np.int64)
+    S = np.zeros((20,) + R.shape[1:], dtype=np.int64)
     for t in range(T):
-        for k in range(N_WORDS):
-            S[k] = S[k] + r[t] * words[t, k]           # exact (< 2^51)
-    # the multiple of P: total / P in FP64 (|m| <= 2^11, error ~2^-42; the bit budget keeps |C'| / P away from 1/2)
-    P = crt_constants(T)[0]
-    tw = float(1 << WORD_BITS)
-    m = np.rint((((S[3] * tw + S[2]) * tw + S[1]) * tw + S[0]) * (1.0 / P))
-    D = [S[k] - m * Pw[k] for k in range(N_WORDS)]     # exact (< 2^52)
+        for k in range(16):
+            S[k] += r[t] * wbytes[t, k]
+    W = [sum(S[5 * j + i] << (8 * i) for i in range(5)).astype(np.float64) for j in range(N_WORDS)]
     two = float(1 << WORD_BITS)
+    # the multiple of P: total / P in FP64 (|m| <= 2^12, error ~2^-41; the bit budget keeps |C'| / P away from 1/2).  The device
+    # evaluates the chain with fused multiply-adds; every intermediate here is below 2^53 times a power of two only at the last
+    # step, so the chain is replayed in exact integers and rounded once per fma
+    m = np.rint(_fma_chain(W, two) * (1.0 / P))
+    D = [W[k] - m * Pw[k] for k in range(N_WORDS)]     # exact: W < 2^53, m P_k < 2^52
     for k in range(N_WORDS - 1):                        # carry normalisation: |D_k| <= 2^39 for k < top
         c = np.rint(D[k] / two)
         D[k] = D[k] - c * two
         D[k + 1] = D[k + 1] + c
-    val = D[N_WORDS - 1]
+    return np.ldexp(_fma_chain(D, two), (eA[:, None] + eB[None, :] - bA - bB))
+
+
+def _fma(a, b, c):
+    """Element-wise fma(a, b, c) with ONE rounding, for integer-valued float64 arrays (exact Python integers in between)."""
+    out = np.empty(a.shape, dtype=np.float64)
+    af, cf, of = a.ravel(), c.ravel(), out.ravel()
+    for i in range(af.size):
+        of[i] = float(int(af[i]) * int(b) + int(cf[i]))          # int -> float: correctly rounded
+    return out
+
+
+def _fma_chain(words, two):
+    val = words[N_WORDS - 1]
     for k in range(N_WORDS - 2, -1, -1):
-        val = val * two + D[k]
-    return np.ldexp(val, (eA[:, None] + eB[None, :] - bA - bB))
+        val = _fma(val, two, words[k])
+    return val
 
 
 def crt_matmul(A, B, T=16, bits=None):

@@ -28,7 +28,7 @@ namespace tgp {
 namespace i8 {
 
 constexpr int MAX_T = 16;
-constexpr int WORD_BITS = 40, N_WORDS = 4;
+constexpr int WORD_BITS = 40, N_WORDS = 4;            // CRT reconstruction: 40-bit words (five weight bytes each)
 constexpr int BM = 128, BN = 256, BK = 128;          // BK in bytes == int8 elements
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -42,10 +42,10 @@ static const int MODULI[MAX_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 2
 struct CrtTable {                 // passed by value to the kernels (< 1 KiB)
     int T;
     int p[MAX_T];
-    float invp[MAX_T];
-    double w[MAX_T][N_WORDS];     // words of w_t = (P/p_t) * ((P/p_t)^-1 mod p_t)
-    double frac[MAX_T];           // w_t / P
-    double Pw[N_WORDS];           // words of P
+    // CRT weights w_t = (P/p_t) * ((P/p_t)^-1 mod p_t) < P < 256^16 by BYTES, packed for dp4a: byte j of wb[g][k] is byte k of
+    // w_{4g+j}, so that sum_t r_t byte_k(w_t) = sum_g dp4a(residues 4g..4g+3 of an element, wb[g][k])
+    uint32_t wb[MAX_T / 4][16];
+    double Pw[N_WORDS];           // 40-bit words of P
     double log2P;
     double invP;                  // 1 / P
     // residues of a 56-bit magnitude by byte limbs: u = sum_k a_k 256^k  =>  u mod p = (sum_k a_k (256^k mod p)) mod p;
@@ -70,14 +70,14 @@ inline const CrtTable& crt_table(int T) {
         auto to_ld = [](u128 x) { return (long double)(unsigned long long)(x >> 64) * 18446744073709551616.0L + (long double)(unsigned long long)x; };
         for (int t = 0; t < T; ++t) {
             const int p = MODULI[t];
-            c.p[t] = p; c.invp[t] = 1.0f / (float)p;
+            c.p[t] = p;
             const u128 q = P / (u128)p;
             const int qm = (int)(q % (u128)p);
             int inv = 1;
             while ((qm * inv) % p != 1) ++inv;
             const u128 w = q * (u128)inv;
-            for (int k = 0; k < N_WORDS; ++k) c.w[t][k] = (double)(unsigned long long)((w >> (WORD_BITS * k)) & mask);
-            c.frac[t] = (double)(to_ld(w) / to_ld(P));
+            for (int k = 0; k < 16; ++k)
+                c.wb[t / 4][k] |= (uint32_t)((unsigned)((w >> (8 * k)) & 0xff)) << (8 * (t % 4));
             uint32_t pw = 1 % (uint32_t)p, lo = 0, hi = 0;
             for (int k = 0; k < 8; ++k) {
                 if (k < 4) lo |= pw << (8 * k); else hi |= pw << (8 * (k - 4));
@@ -595,30 +595,61 @@ inline int gemm_i8_mod(const Planes& A, const Planes& B, Params p, cudaStream_t 
 }
 
 // ---- step 4 + 5: CRT reconstruction -----------------------------------------------------------------------------------
-// value of sum_t r_t w_t mod P (centred) for the residues packed in byte `i` of w[t], as a double (relative error <= 3 * 2^-53).
-// r_t in [0, 255], T <= 16 terms, words < 2^40: every partial sum stays below 2^52 and is exact.  The multiple of P is
-// m = rint(total / P) with total = ((S3 2^40 + S2) 2^40 + S1) 2^40 + S0 evaluated in FP64: m <= 2^12, so its rounding error is
-// ~2^-41, far inside the margin the bit budget leaves between |C'| / P and 1/2.
+// Values of sum_t r_t w_t mod P (centred) for the FOUR elements whose residues sit in the bytes of w[t], as doubles (relative
+// error <= 3 * 2^-53).  Integer first: the residues of one element are gathered into dp4a operands (a 4 x 4 byte transpose per
+// group of four moduli), and for every byte position k of the weights  S_k = sum_t r_t byte_k(w_t)  (< 16 * 255 * 255 < 2^20) is
+// a handful of dp4a with constant-bank operands; total = sum_k S_k 256^k exactly.  Four 40-bit-spaced words
+// W_j = sum_{i<5} S_{5j+i} 256^i (< 2^53: exact in FP64) are formed from the S_k; the multiple of P is m = rint(total / P) with
+// total evaluated in FP64 (m <= 2^12: its rounding error is ~2^-41, far inside the margin the bit budget leaves between |C'| / P
+// and 1/2); W_j - m P_j is exact, carries are propagated, and only the final FMAs round.
+__device__ __forceinline__ double u32_to_double(uint32_t x) {          // (2^52 + x) - 2^52: no conversion instruction
+    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
 template <int T>
-__device__ __forceinline__ double crt_value(const uint32_t* w, int i, const CrtTable& tab) {
-    double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0;
-    const uint32_t sel = 0x4440u | (uint32_t)i;                                        // byte i, zero-extended
+__device__ __forceinline__ void crt_value4(const uint32_t (&w)[T], const CrtTable& tab, double (&out)[4]) {
+    constexpr int NG = (T + 3) / 4;
+    constexpr int NB = T;                     // bytes of P for the instantiated counts (9, 12, 15, 16 moduli: P < 256^T)
+    uint32_t q[4][NG];                        // q[i][g]: residues 4g..4g+3 of element i
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-        const uint32_t r = __byte_perm(w[t], 0u, sel);
-        const double rt = __hiloint2double(0x43300000, (int)r) - 4503599627370496.0;   // (2^52 + r) - 2^52: no conversion instruction
-        S0 = fma(rt, tab.w[t][0], S0);
-        S1 = fma(rt, tab.w[t][1], S1);
-        S2 = fma(rt, tab.w[t][2], S2);
-        S3 = fma(rt, tab.w[t][3], S3);
+    for (int g = 0; g < NG; ++g) {
+        const uint32_t a = w[4 * g], b = 4 * g + 1 < T ? w[4 * g + 1] : 0u, c = 4 * g + 2 < T ? w[4 * g + 2] : 0u,
+                       d = 4 * g + 3 < T ? w[4 * g + 3] : 0u;
+        const uint32_t t0 = prmt(a, b, 0x5140u), t1 = prmt(a, b, 0x7362u);      // a0 b0 a1 b1 | a2 b2 a3 b3
+        const uint32_t t2 = prmt(c, d, 0x5140u), t3 = prmt(c, d, 0x7362u);
+        q[0][g] = prmt(t0, t2, 0x5410u); q[1][g] = prmt(t0, t2, 0x7632u);
+        q[2][g] = prmt(t1, t3, 0x5410u); q[3][g] = prmt(t1, t3, 0x7632u);
     }
     const double two = 1099511627776.0, inv = 9.094947017729282e-13;       // 2^40, 2^-40
-    const double m = rint(fma(fma(fma(S3, two, S2), two, S1), two, S0) * tab.invP);
-    double D0 = fma(-m, tab.Pw[0], S0), D1 = fma(-m, tab.Pw[1], S1), D2 = fma(-m, tab.Pw[2], S2), D3 = fma(-m, tab.Pw[3], S3);
-    double c = rint(D0 * inv); D0 = fma(-c, two, D0); D1 += c;
-    c = rint(D1 * inv); D1 = fma(-c, two, D1); D2 += c;
-    c = rint(D2 * inv); D2 = fma(-c, two, D2); D3 += c;
-    return fma(fma(fma(D3, two, D2), two, D1), two, D0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t S[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+            uint32_t s = 0u;
+            if (k < NB) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) s = __dp4a(q[i][g], tab.wb[g][k], s);
+            }
+            S[k] = s;
+        }
+        double W[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)           // (S_5j + S_5j+1 2^8) + (S_5j+2 + S_5j+3 2^8) 2^16 + S_5j+4 2^32: < 2^53, exact
+            W[j] = fma(u32_to_double(S[5 * j + 4]), 4294967296.0,
+                       fma(u32_to_double(S[5 * j + 2] + (S[5 * j + 3] << 8)), 65536.0, u32_to_double(S[5 * j] + (S[5 * j + 1] << 8))));
+        const double m = rint(fma(fma(fma(W[3], two, W[2]), two, W[1]), two, W[0]) * tab.invP);
+        double D0 = fma(-m, tab.Pw[0], W[0]), D1 = fma(-m, tab.Pw[1], W[1]), D2 = fma(-m, tab.Pw[2], W[2]), D3 = fma(-m, tab.Pw[3], W[3]);
+        double c = rint(D0 * inv); D0 = fma(-c, two, D0); D1 += c;
+        c = rint(D1 * inv); D1 = fma(-c, two, D1); D2 += c;
+        c = rint(D2 * inv); D2 = fma(-c, two, D2); D3 += c;
+        out[i] = fma(fma(fma(D3, two, D2), two, D1), two, D0);
+    }
 }
 
 // stats (forward only; cols = 2 * stat_M, row = [a | b]): mu[r] = sum_{c < M} out * m[c], v[r] = os - sum_{c<M} out^2 +
@@ -656,8 +687,9 @@ __global__ void __launch_bounds__(256) k_crt_combine(const uint8_t* __restrict__
                 e4[0] = e4[1] = e4[2] = e4[3] = eb[0];
             }
             double v4[4];
+            crt_value4<T>(w, tab, v4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v4[i] = mul_pow2(crt_value<T>(w, i, tab), era + e4[i]);
+            for (int i = 0; i < 4; ++i) v4[i] = mul_pow2(v4[i], era + e4[i]);
             double* o = out + r * ldo + c0;
             if (!accumulate && c0 + 4 <= climit && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
                 *reinterpret_cast<double2*>(o) = make_double2(v4[0], v4[1]);
