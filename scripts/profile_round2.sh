@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for m in i8crt f64; do
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${m}_step.csv python scripts/one_step_mode.py $m > gpurun_out/one_step_$m.log 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:"gemm_i8_mod|k_crt_combine|k_to_residues|k_rbf_residues|k_make_abbar_inplace|k_row_quad" -s 12 -c 12 -o gpurun_out/r02_i8crt -f python scripts/one_step_mode.py i8crt > gpurun_out/ncu_i8crt.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gemm_i8_mod|k_crt_combine|k_rbf_residues|k_abbar_stats|k_abbar_residues|k_wt_residues|k_kernel_grads|k_row_quad" -c 20 -o gpurun_out/r02_i8crt -f python scripts/one_step_mode.py i8crt > gpurun_out/ncu_i8crt.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gemm_f64_kernel" -s 150 -c 4 -o gpurun_out/r02_f64 -f python scripts/one_step_mode.py f64 > gpurun_out/ncu_f64.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_crt.py tests/test_gpu_flow_mlp.py tests/test_gpu_session.py -q -x -k "not 1024 and not 2048 and not 4096 and not steptanh102" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/sanitizer_memcheck.log
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "synth_reg_d8_m64_p1 or boston_svgp_p1 or test_prepare_cholesky_inverse_kl and 64" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/sanitizer_racecheck.log

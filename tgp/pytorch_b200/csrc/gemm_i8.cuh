@@ -366,6 +366,30 @@ __device__ __forceinline__ uint32_t mod_p(uint32_t acc, uint32_t p, uint32_t mag
     return (uint32_t)(r < 0 ? r + (int)p : r);
 }
 
+// 32 lanes x 32 consecutive 32-bit TMEM columns -> 32 registers per thread (asynchronous: complete after tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// waits for the outstanding TMEM loads; the registers of the load being consumed are passed through as in/out operands so that the
+// compiler cannot move their uses above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+
 // Launched as clusters of TWO CTAs that own vertically adjacent 128-row tiles of the same (modulus, n-tile): the B tile is the
 // same for both, so each CTA fetches one 128-row half of it and MULTICASTS it into both shared memories (L2 -> SM traffic per
 // CTA and k-block: 16 KiB of A + 16 KiB of B instead of 16 + 32; the single-CTA version was L2-bound at ~10 TB/s).  A stage
@@ -491,19 +515,17 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             // this CTA's tile may lie strictly above the diagonal (its pair partner does not) or below the last row: nothing to store
             const bool store = row < p.Mrows && !(p.lower_rows > 0 && m0 < p.lower_rows && n0 > m0 + BM - 1);
             uint8_t* dst = p.C + (long)t * p.plane_stride_c + (long)row * p.ldc + nbase;
+            // 128 accumulator columns per thread in four 32-column TMEM loads, software-pipelined: the load of chunk c + 1 is in
+            // flight while chunk c is reduced mod p, packed and stored (tcgen05.wait::ld waits for every outstanding load, so the
+            // next one is issued right after the wait)
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
 #pragma unroll
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t r[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr + (uint32_t)c));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int ci = 0; ci < 4; ++ci) {
+                const int c = ci * 32;
+                uint32_t (&r)[32] = (ci & 1) ? rb : ra;
+                tmem_wait_ld(r);
+                if (ci + 1 < 4) tmem_ld32(taddr + (uint32_t)(c + 32), (ci & 1) ? ra : rb);
                 if (store) {
                     uint32_t packed[8];
 #pragma unroll
