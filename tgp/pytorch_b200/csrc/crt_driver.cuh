@@ -207,15 +207,22 @@ __global__ void __launch_bounds__(128) k_abbar_stats(const double* __restrict__ 
     const double mj = j < M ? m[j] : 0.0;
     double acc = 0.0, accv = 0.0;
     int ca = -100000, cb = -100000;
-    for (long n = n0; n < n1; ++n) {
-        const double gm = g_mu[n], gv = g_v[n];
-        accv += gv;
-        if (j < M) {
-            const double* row = AB + n * 2 * M;
-            const double a = row[j], b = row[M + j];
-            acc = fma(gm, a, acc);
-            ca = max(ca, i8::exp_above(abbar_value(gm, gv, mj, a, true)));
-            cb = max(cb, i8::exp_above(abbar_value(gm, gv, mj, b, false)));
+    for (long nb = n0; nb < n1; nb += 8) {              // eight rows per iteration: their loads are in flight together
+        double a[8], b[8], gm[8], gv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long n = nb + u;
+            const bool ok = n < n1;
+            gm[u] = ok ? g_mu[n] : 0.0; gv[u] = ok ? g_v[n] : 0.0;
+            a[u] = (ok && j < M) ? AB[n * 2 * M + j] : 0.0;
+            b[u] = (ok && j < M) ? AB[n * 2 * M + M + j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            accv += gv[u];
+            acc = fma(gm[u], a[u], acc);
+            ca = max(ca, i8::exp_above(abbar_value(gm[u], gv[u], mj, a[u], true)));
+            cb = max(cb, i8::exp_above(abbar_value(gm[u], gv[u], mj, b[u], false)));
         }
     }
     if (j < M) {
@@ -235,6 +242,15 @@ __global__ void __launch_bounds__(256) k_abbar_residues(const double* __restrict
     const int c = blockIdx.x * i8::RS_TC + (threadIdx.x & 7) * 16;
     const int cols = 2 * M;
     const double gm = r < rows ? g_mu[r] : 0.0, gv = r < rows ? g_v[r] : 0.0;
+    double ab[16];
+    if (r < rows && c + 16 <= cols && ((reinterpret_cast<uintptr_t>(AB + r * cols + c) & 15) == 0)) {
+        const double2* src = reinterpret_cast<const double2*>(AB + r * cols + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const double2 t = src[i]; ab[2 * i] = t.x; ab[2 * i + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ab[i] = (r < rows && c + i < cols) ? AB[r * cols + c + i] : 0.0;
+    }
     long long xi[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(256) k_abbar_residues(const double* __restrict
         double x = 0.0;
         int e = 0;
         if (r < rows && j < cols) {
-            x = abbar_value(gm, gv, j < M ? m[j] : 0.0, AB[r * cols + j], j < M);
+            x = abbar_value(gm, gv, j < M ? m[j] : 0.0, ab[i], j < M);
             e = col_exp[j];
         }
         xi[i] = __double2ll_rn(i8::mul_pow2(x, bits - e));

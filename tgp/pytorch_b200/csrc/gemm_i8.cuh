@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
                                                       const double* __restrict__ ls, const double* __restrict__ os, long R, int M, int D,
                                                       double* __restrict__ Kout, long ldk_out, int bits,
                                                       CrtTable tab, uint8_t* __restrict__ planes, long ldp, long plane_stride) {
-    __shared__ __align__(16) double zs[RS_TC][MAXD];
+    // inducing rows of the tile, dimension-major with a skew of one column per 16: the eight column groups of a warp (stride 16
+    // columns) read eight different bank pairs (a [column][dimension] layout puts them all on one: an 8-way conflict per load)
+    __shared__ __align__(16) double zs[MAXD][RS_TC + RS_TC / 16];
     const int tid = threadIdx.x;
     const int tr = tid >> 3, tcb = (tid & 7) * 16;
     const double s = os[0];
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
             __syncthreads();
             for (int i = tid; i < RS_TC * MAXD; i += 256) {
                 const int c = i / MAXD, d = i % MAXD, j = c0 + c;
-                zs[c][d] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
+                zs[d][c + (c >> 4)] = (j < M && d < D) ? Zs[(long)j * D + d] : 0.0;
             }
             __syncthreads();
             c0_loaded = c0;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(256) k_rbf_residues(const double* __restrict__
             if (r < R && c < M) {
                 double acc = 0.0;
 #pragma unroll
-                for (int d = 0; d < MAXD; ++d) { const double df = xr[d] - zs[tcb + i][d]; acc = fma(df, df, acc); }
+                for (int d = 0; d < MAXD; ++d) { const double df = xr[d] - zs[d][tcb + i + (tid & 7)]; acc = fma(df, df, acc); }
                 val = s * exp(-0.5 * acc);
                 if (Kout) Kout[r * ldk_out + c] = val;
             }
