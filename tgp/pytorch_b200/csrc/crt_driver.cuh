@@ -198,15 +198,17 @@ __device__ __forceinline__ double abbar_value(double gm, double gv, double mj, d
 }
 
 // pass 1: column exponents of [Abar | Bbar] (pre-set to a very small value), dm[j] += sum_n g_mu A[n,j], dos += sum_n g_v.
-// 64 rows x 128 columns per CTA.
+// ABS_ROWS rows x 128 columns per CTA (measured: 64 rows 0.077 ms per 16384-row chunk, 256 rows 0.15 ms — it needs the CTAs).  The
+// exponent is taken from the running maximum of |.| once per thread: a frexp per element made this kernel 1.5x slower.
+constexpr int ABS_ROWS = 64;
 __global__ void __launch_bounds__(128) k_abbar_stats(const double* __restrict__ AB, const double* __restrict__ g_mu,
                                                      const double* __restrict__ g_v, const double* __restrict__ m, long R, int M,
                                                      double* __restrict__ dm, double* __restrict__ dos, int* __restrict__ col_exp) {
     const int j = blockIdx.x * 128 + threadIdx.x;
-    const long n0 = (long)blockIdx.y * 64, n1 = min(n0 + 64, R);
+    const long n0 = (long)blockIdx.y * ABS_ROWS, n1 = min(n0 + ABS_ROWS, R);
     const double mj = j < M ? m[j] : 0.0;
     double acc = 0.0, accv = 0.0;
-    int ca = -100000, cb = -100000;
+    double amax = 0.0, bmax = 0.0;                      // column maxima of |.|: the exponent is taken once, at the end
     for (long nb = n0; nb < n1; nb += 8) {              // eight rows per iteration: their loads are in flight together
         double a[8], b[8], gm[8], gv[8];
 #pragma unroll
@@ -221,14 +223,14 @@ __global__ void __launch_bounds__(128) k_abbar_stats(const double* __restrict__ 
         for (int u = 0; u < 8; ++u) {
             accv += gv[u];
             acc = fma(gm[u], a[u], acc);
-            ca = max(ca, i8::exp_above(abbar_value(gm[u], gv[u], mj, a[u], true)));
-            cb = max(cb, i8::exp_above(abbar_value(gm[u], gv[u], mj, b[u], false)));
+            amax = fmax(amax, fabs(abbar_value(gm[u], gv[u], mj, a[u], true)));
+            bmax = fmax(bmax, fabs(abbar_value(gm[u], gv[u], mj, b[u], false)));
         }
     }
     if (j < M) {
         atomicAdd(dm + j, acc);
-        atomicMax(col_exp + j, ca);
-        atomicMax(col_exp + M + j, cb);
+        atomicMax(col_exp + j, i8::exp_above(amax));
+        atomicMax(col_exp + M + j, i8::exp_above(bmax));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(dos, accv);
 }
@@ -342,7 +344,7 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
         const int Tb = bwd_T(M, bits_x), bits_w = bwd_bits_w(M, bits_x);
         {
             TGP_TRY(fill_int(b.col_exp, 2L * M, -100000, st));
-            dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rc, 64));
+            dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(rc, ABS_ROWS));
             k_abbar_stats<<<grid, 128, 0, st>>>(ABc, g_mu + r0, g_v + r0, s.mvec, rc, M, dm, dos, b.col_exp);
             TGP_TRY(check_launch("k_abbar_stats"));
             dim3 rgrid((unsigned)cdiv(2L * M, i8::RS_TC), (unsigned)cdiv(rc, i8::RS_TR));
