@@ -52,7 +52,7 @@ def ncu(rep, dst, title):
     idx = {h: i for i, h in enumerate(hdr)}
     seen = set()
     with open(dst, 'w') as f:
-        f.write('# %s\n\n`ncu --set full --clock-control none --import-source on` of `python scripts/one_step_mode.py i8crt` (cfg4: 65536 rows,\n'
+        f.write('# %s\n\n`ncu --set full --clock-control none --import-source on` of `python scripts/one_step_mode.py <mode>` (cfg4: 65536 rows,\n'
                 'M = 1024, D = 8; 16384-row chunks), one capture per distinct kernel / shape.  Times under ncu replay are not bench values.\n\n' % title)
         for r in rows[2:]:
             name = r[idx['Kernel Name']].split('(')[0]
@@ -97,6 +97,9 @@ if __name__ == '__main__':
     if os.path.exists(rep):
         ncu(rep, os.path.join(P, 'r02_i8crt_ncu.md'), 'ncu summaries of the kernels of compute mode i8crt (round 2)')
         traffic(rep)
+    rep64 = os.path.join(G, 'r02_f64.ncu-rep')
+    if os.path.exists(rep64):
+        ncu(rep64, os.path.join(P, 'r02_f64_ncu.md'), 'ncu summaries of gemm_f64_kernel, compute mode f64 (round 2)')
     with open(os.path.join(P, 'r02_sanitizer.txt'), 'w') as f:
         for n in ('sanitizer_memcheck.log', 'sanitizer_racecheck.log'):
             p = os.path.join(G, n)
