@@ -484,6 +484,15 @@ def run_ours(args):
     peak_i8 = measure_int8_peak(dev)
     alg_flop_step = 6.0 * M * M * BATCH                         # 6*M^2 FLOP per row, fwd+bwd (per GPU)
 
+    def with_traffic(r, mode):
+        prof = load_json(os.path.join(ROOT, 'profiles', 'r02_roofline_traffic.json')).get(args.workload + ':' + mode)
+        if prof and prof.get('lib_hash') == lib_hash():
+            r['traffic'] = prof.get('traffic')                  # dram bytes per launch from ncu --set full of THIS build
+            r['traffic_source'] = prof.get('source')
+        elif prof:
+            r['traffic_note'] = 'profiles/r02_roofline_traffic.json was captured from a different build (%s); not reported' % prof.get('lib_hash')
+        return r
+
     def roofline_of(mode, g_ms, g_n, step_ms):
         tag = 1 if mode == 'f64' else 2
         k_ms, k_n = g_ms[tag] / args.steps, g_n[tag] / args.steps
@@ -493,7 +502,7 @@ def run_ours(args):
             # the algorithmic FP64 rate (6 M^2 FLOP per row) is reported beside it, with the cuBLAS DGEMM rate for scale
             ops = i8crt_executed_ops(M, BATCH)
             ex = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-            return {'bound': 'tensor', 'kernel': 'gemm_i8_mod_kernel (tcgen05 kind::i8, u8 x u8 -> s32 in TMEM, 15-16 residue planes, '
+            r = {'bound': 'tensor', 'kernel': 'gemm_i8_mod_kernel (tcgen05 kind::i8, u8 x u8 -> s32 in TMEM, 15-16 residue planes, '
                                                  '2-CTA clusters with TMA multicast), the three batch contractions',
                     'achieved': ex, 'peak': peak_i8, 'unit': 'TOP/s', 'frac': ex / peak_i8 if peak_i8 else None,
                     'peak_source': 'cuBLASLt INT8 GEMM 8192^3 via torch._int_mm, best of 5, measured in this run (tcgen05 kind::i8 issue '
@@ -506,6 +515,7 @@ def run_ours(args):
                     'per_step_o_m3_gemm_ms': g_ms[0] / args.steps,
                     'note': 'FP64-accurate results (operands truncated at 52-53 bits below their row maximum, integer product exact); '
                             'the residue conversion and CRT reconstruction kernels around the GEMMs are counted in ms_per_step, not here'}
+            return with_traffic(r, mode)
         if mode == 'f64':
             peak, src, kern = peak64, 'cuBLAS DGEMM 8192^3 via torch.matmul, best of 5, measured in this run', \
                 'gemm_f64_kernel (FP64 DMMA mma.sync.m8n8k4), the six batch contractions'
@@ -524,13 +534,7 @@ def run_ours(args):
             # executed: three TF32 MMAs per product, dense 128x256 tiles incl. the dense C half: (2 + 2 + 2) M^2 MACs * 3
             r['executed_tflops'] = 3.0 * 2.0 * (1.5 + 1.5 + 1.5) * M * M * BATCH / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
             r['executed_frac_of_peak'] = r['executed_tflops'] / peak if peak else None
-        prof = load_json(os.path.join(ROOT, 'profiles', 'r02_roofline_traffic.json')).get(args.workload + ':' + mode)
-        if prof and prof.get('lib_hash') == lib_hash():
-            r['traffic'] = prof.get('traffic')                  # dram bytes per launch from ncu --set full of THIS build
-            r['traffic_source'] = prof.get('source')
-        elif prof:
-            r['traffic_note'] = 'profiles/r02_roofline_traffic.json was captured from a different build (%s); not reported' % prof.get('lib_hash')
-        return r
+        return with_traffic(r, mode)
 
     roofline = roofline_of(args.compute, gemm_ms, gemm_n, ms_total / args.steps)
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ----------------------

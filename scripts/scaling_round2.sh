@@ -10,5 +10,5 @@ run 8 weak weak8
 run 8 strong strong8
 run 4 strong strong4
 run 2 strong strong2
-run 8 strong strong8_f64 "--compute f64"
+[ -n "$TGP_SCALE_F64" ] && run 8 strong strong8_f64 "--compute f64"
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29555 scripts/dist_parity.py 2>&1 | grep "DIST_PARITY\|world 8 sync 0" | tail -9

@@ -67,25 +67,37 @@ def ncu(rep, dst, title):
             f.write('\n')
 
 
-def traffic(rep):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, tied to the hash of the profiled library."""
+def traffic(reps):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of each mode, tied to the hash of the profiled
+    library (bench.py reports it only when the hash matches the library it runs)."""
     import hashlib, json
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
 
-    def to_bytes(v, u):
-        v = float(v.replace(',', ''))
-        return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
-    vals = [to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) +
-            to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
-            for r in rows[2:] if 'gemm_i8_mod_kernel' in r[idx['Kernel Name']]]
+    def mean_bytes(rep, kernel):
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+
+        def to_bytes(v, u):
+            return float(v.replace(',', '')) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+        vals = [to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) +
+                to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
+                for r in rows[2:] if kernel in r[idx['Kernel Name']]]
+        return sum(vals) / len(vals), len(vals)
     h = hashlib.sha1(open(os.path.join(ROOT, 'tgp', 'pytorch_b200', 'libtgp_b200.so'), 'rb').read()).hexdigest()[:12]
-    out = {'cfg4:i8crt': {'lib_hash': h, 'traffic': sum(vals) / len(vals), 'launches_captured': len(vals),
-                          'source': 'profiles/r02_i8crt_ncu.md (ncu --set full of scripts/one_step_mode.py i8crt): mean DRAM read + write '
-                                    'bytes per gemm_i8_mod_kernel launch; algorithmic operand + result bytes per launch (one 16384-row chunk, '
-                                    '15 planes: A 252 MB + W 31 MB + result 503 MB) = 0.79 GB'}}
+    out = {}
+    if 'i8crt' in reps:
+        t, n = mean_bytes(reps['i8crt'], 'gemm_i8_mod_kernel')
+        out['cfg4:i8crt'] = {'lib_hash': h, 'traffic': t, 'launches_captured': n,
+                             'source': 'profiles/r02_i8crt_ncu.md (ncu --set full of scripts/one_step_mode.py i8crt): mean DRAM read + write '
+                                       'bytes per gemm_i8_mod_kernel launch; algorithmic operand + result bytes per launch (one 16384-row '
+                                       'chunk, 15 planes: A 252 MB + W 31 MB + result 503 MB) = 0.79 GB'}
+    if 'f64' in reps:
+        t, n = mean_bytes(reps['f64'], 'gemm_f64_kernel')
+        out['cfg4:f64'] = {'lib_hash': h, 'traffic': t, 'launches_captured': n,
+                           'source': 'profiles/r02_f64_ncu.md (ncu --set full of scripts/one_step_mode.py f64): mean DRAM read + write bytes '
+                                     'per gemm_f64_kernel launch (32768-row chunk: operand 268 MB + triangular weight 4 MB + result 268 MB '
+                                     '= 0.54 GB algorithmic)'}
     json.dump(out, open(os.path.join(P, 'r02_roofline_traffic.json'), 'w'), indent=1)
 
 
@@ -96,10 +108,10 @@ if __name__ == '__main__':
     rep = os.path.join(G, 'r02_i8crt.ncu-rep')
     if os.path.exists(rep):
         ncu(rep, os.path.join(P, 'r02_i8crt_ncu.md'), 'ncu summaries of the kernels of compute mode i8crt (round 2)')
-        traffic(rep)
     rep64 = os.path.join(G, 'r02_f64.ncu-rep')
     if os.path.exists(rep64):
         ncu(rep64, os.path.join(P, 'r02_f64_ncu.md'), 'ncu summaries of gemm_f64_kernel, compute mode f64 (round 2)')
+    traffic({k: v for k, v in (('i8crt', rep), ('f64', rep64)) if os.path.exists(v)})
     with open(os.path.join(P, 'r02_sanitizer.txt'), 'w') as f:
         for n in ('sanitizer_memcheck.log', 'sanitizer_racecheck.log'):
             p = os.path.join(G, n)
