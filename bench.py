@@ -233,10 +233,15 @@ def load_json(path):
 
 
 def lib_hash():
-    from tgp.pytorch_b200 import _lib
+    """Hash of the library SOURCES (csrc/ + include/): ties a profile to a build.  (The .so itself is not byte-reproducible: two
+    nvcc runs over identical sources differ, so a hash of the binary would change with every rebuild.)"""
     h = hashlib.sha1()
-    with open(_lib.LIB_PATH, 'rb') as fh:
-        h.update(fh.read())
+    base = os.path.join(ROOT, 'tgp', 'pytorch_b200', 'csrc')
+    files = sorted(os.path.join(base, f) for f in os.listdir(base) if f.endswith(('.cu', '.cuh')))
+    files.append(os.path.join(ROOT, 'include', 'tgp_b200.h'))
+    for f in files:
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
     return h.hexdigest()[:12]
 
 

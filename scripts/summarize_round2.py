@@ -84,7 +84,9 @@ def traffic(reps):
                 to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
                 for r in rows[2:] if kernel in r[idx['Kernel Name']]]
         return sum(vals) / len(vals), len(vals)
-    h = hashlib.sha1(open(os.path.join(ROOT, 'tgp', 'pytorch_b200', 'libtgp_b200.so'), 'rb').read()).hexdigest()[:12]
+    sys.path.insert(0, ROOT)
+    import bench
+    h = bench.lib_hash()          # hash of the library sources (the binary is not byte-reproducible)
     out = {}
     if 'i8crt' in reps:
         t, n = mean_bytes(reps['i8crt'], 'gemm_i8_mod_kernel')
