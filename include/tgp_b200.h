@@ -122,7 +122,9 @@ int tgp_ell_forward(const TgpModel* model, const TgpParams* params, const void* 
 /* Backward of tgp_qf_forward for upstream per-row gradients (g_mu, g_v): accumulates the pre-chain quantities
  * (Gbar = dELL/dL^-1, Cbar = dELL/dC, dm, dZ, dlengthscale, doutputscale from the K_xz side) into reduce_buf.
  * Replaces autograd through sparse_MF_SP.py:313-382 (trainer_base.py:341).  Must follow tgp_qf_forward on the SAME
- * batch workspace and rows: it consumes the [A | B] rows and the K_xz the forward left there (nothing is recomputed). */
+ * batch workspace and rows: it consumes the [A | B] rows the forward left there and K_xz — as stored FP64 values in
+ * TGP_F64 / TGP_F32 mode, as the forward's residue planes in TGP_F64_I8 mode, where the FP64 K_xz tiles needed for the
+ * kernel-parameter gradients are RECOMPUTED from X and Z (K_xz is never written in FP64 for D <= 32). */
 int tgp_qf_backward(const TgpModel* model, const TgpParams* params, const void* step_ws, void* batch_ws,
                     const void* X, long R, const void* g_mu, const void* g_v, double* reduce_buf, void* stream);
 

@@ -64,7 +64,8 @@ inline StepPlanes carve_step(void* region, int M) {
 
 struct BatchView {
     double *AB;                   // (R x 2M) FP64, forward -> backward ([A | B], turned into [Abar | Bbar] in place)
-    double *Kbuf;                 // (R x M) FP64 K_xz (kernel gradients read it)
+    double *Kbuf;                 // (R x M) FP64 K_xz — only for D > 32 (staged generation); otherwise K_xz exists as residue planes
+                                  // only and the kernel-gradient pass recomputes its tiles from X and Z
     double *Kbar;                 // (Rc x M)
     uint8_t *Kp;                   // planes [T_ALL][R][ldk]   K_xz residues: forward operand AND weight-contraction operand
     uint8_t *Op;                   // planes [T][Rc][ld2m]     result residues of the forward
@@ -76,23 +77,26 @@ struct BatchView {
     long Rc, ldk, ld2m;
 };
 
-inline size_t batch_bytes(int M, long R) {
+// D <= 32: K_xz is generated straight into residue planes (i8::k_rbf_residues) and recomputed by the backward
+inline bool keeps_kxz(int D) { return D > 32; }
+
+inline size_t batch_bytes(int M, int D, long R) {
     const long Rc = chunk_rows(R), ldk = pad16(M), ld2m = pad16(2L * M);
     size_t b = 0;
-    b += (size_t)R * 2 * M * 8 + (size_t)R * M * 8 + (size_t)Rc * M * 8;
+    b += (size_t)R * 2 * M * 8 + (keeps_kxz(D) ? (size_t)R * M * 8 : 0) + (size_t)Rc * M * 8;
     b += (size_t)T_ALL * R * ldk;
     b += (size_t)2 * T_ALL * Rc * ld2m + (size_t)T_ALL * Rc * ldk + (size_t)T_ALL * 2 * M * ldk;
     b += (size_t)(3L * M + 64) * sizeof(int) + 4096;
     return b;
 }
 
-inline BatchView carve_batch(void* ws, int M, long R) {
+inline BatchView carve_batch(void* ws, int M, int D, long R) {
     BatchView b;
     b.Rc = chunk_rows(R); b.ldk = pad16(M); b.ld2m = pad16(2L * M);
     char* p = reinterpret_cast<char*>(ws);
     auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
     b.AB = reinterpret_cast<double*>(take((size_t)R * 2 * M * 8));
-    b.Kbuf = reinterpret_cast<double*>(take((size_t)R * M * 8));
+    b.Kbuf = keeps_kxz(D) ? reinterpret_cast<double*>(take((size_t)R * M * 8)) : nullptr;
     b.Kbar = reinterpret_cast<double*>(take((size_t)b.Rc * M * 8));
     b.Kp = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * R * b.ldk));
     b.Op = reinterpret_cast<uint8_t*>(take((size_t)T_ALL * b.Rc * b.ld2m));
@@ -299,14 +303,14 @@ inline int qf_forward(const StepView& s, void* step_region, void* batch_ws, cons
                       cudaStream_t st) {
     const int M = s.M, D = s.D;
     StepPlanes sp = carve_step(step_region, M);
-    BatchView b = carve_batch(batch_ws, M, R);
+    BatchView b = carve_batch(batch_ws, M, D, R);
     const int Tf = fwd_T(M), bits = fwd_bits_w(M);
     // K_xz (FP64 values + residue planes) of all rows in one launch.  It depends on Zs / ls / os only, not on the factorisation:
     // it is enqueued BEFORE the join with the factorisation, which may still be running on the library's high-priority stream
     // (TGP_OPT_OVERLAP_KGEN, common.cuh), and runs under it.  K residues: one scale for the whole matrix (0 <= k <= outputscale),
     // shared by the forward and the weight contraction.
     {
-        const int rr = rbf_residues(X, s.Zs, s.ls, s.os, R, M, D, b.Kbuf, T_ALL, b.Kp, b.ldk, R * b.ldk, st, 0);
+        const int rr = rbf_residues(X, s.Zs, s.ls, s.os, R, M, D, nullptr, T_ALL, b.Kp, b.ldk, R * b.ldk, st, 0);
         if (rr != 0 && rr != -7) return rr;
         if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
         if (rr == -7) {
@@ -333,9 +337,10 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
                        cudaStream_t st) {
     const int M = s.M, D = s.D;
     StepPlanes sp = carve_step(step_region, M);
-    BatchView b = carve_batch(batch_ws, M, R);
+    BatchView b = carve_batch(batch_ws, M, D, R);
     if (join_factor(st)) return set_error(-100, "join with the factorisation failed");
     TGP_TRY(fill_int(b.zero_exp, 1, 0, st));
+    const double* const kval = b.Kbuf;            // NULL for D <= 32: k_kernel_grads recomputes the K_xz tile (same arithmetic)
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         const double* ABc = b.AB + r0 * 2 * M;
@@ -373,7 +378,7 @@ inline int qf_backward(const StepView& s, void* step_region, void* batch_ws, con
         }
         // reconstruction of Kbar, then Kbar o K -> dZ, dlengthscale, doutputscale
         TGP_TRY(combine(b.Kbp, b.ldk, (long)b.Rc * b.ldk, rc, M, Tb, bits_x + bits_w, b.zero_exp, 2, b.wc_exp, 1, b.Kbar, M, 0, 0, st));
-        TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, b.Kbuf + r0 * M, M));
+        TGP_TRY(launch_kernel_grads(b.Kbar, M, X + r0 * D, 0, s.Zs, s.ls, s.os, rc, M, D, 0, 1.0, dZ, dls, dos, st, kval ? kval + r0 * M : nullptr, M));
         {   // [Gbar; Cbar] (2M x M) += ABbar^T K: reduction over the chunk rows; both operands are row-major planes read MN-major
             i8::Params p{};
             p.Mrows = 2 * M; p.Ncols = M; p.K = rc; p.T = Tw; p.tri_mode = 0; p.tri_rows = 0; p.lower_rows = M; p.mn_major = 3;

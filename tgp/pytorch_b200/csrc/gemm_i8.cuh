@@ -33,7 +33,8 @@ constexpr int BM = 128, BN = 256, BK = 128;          // BK in bytes == int8 elem
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;                          // 4 TMEM lane quadrants x (EPI_WARPS / 4) column parts (16 warps measured no faster)
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);        // accumulator columns per epilogue thread
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int UMMA_K = 32;                            // kind::i8: 32 bytes of K per MMA
 
@@ -503,7 +504,7 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
     } else {
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;              // column part of this warp
         int buf = 0; uint32_t bphase = 0;
         for (long w = cluster_id; w < n_work; w += n_clusters) {
             int t, m0, n0, kb, ke;
@@ -511,23 +512,23 @@ gemm_i8_mod_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             const uint32_t pm = (uint32_t)p.p[t], ip = p.magic[t];
             mbar_wait(&tfull[buf], bphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)buf * BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)buf * BN + (uint32_t)(half * EPI_COLS) + ((uint32_t)(q * 32) << 16);
             const int row = m0 + q * 32 + lane;
-            const int nbase = n0 + half * 128;
+            const int nbase = n0 + half * EPI_COLS;
             // this CTA's tile may lie strictly above the diagonal (its pair partner does not) or below the last row: nothing to store
             const bool store = row < p.Mrows && !(p.lower_rows > 0 && m0 < p.lower_rows && n0 > m0 + BM - 1);
             uint8_t* dst = p.C + (long)t * p.plane_stride_c + (long)row * p.ldc + nbase;
-            // 128 accumulator columns per thread in four 32-column TMEM loads, software-pipelined: the load of chunk c + 1 is in
+            // EPI_COLS accumulator columns per thread in 32-column TMEM loads, software-pipelined: the load of chunk c + 1 is in
             // flight while chunk c is reduced mod p, packed and stored (tcgen05.wait::ld waits for every outstanding load, so the
             // next one is issued right after the wait)
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr, ra);
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
+            for (int ci = 0; ci < EPI_COLS / 32; ++ci) {
                 const int c = ci * 32;
                 uint32_t (&r)[32] = (ci & 1) ? rb : ra;
                 tmem_wait_ld(r);
-                if (ci + 1 < 4) tmem_ld32(taddr + (uint32_t)(c + 32), (ci & 1) ? ra : rb);
+                if (ci + 1 < EPI_COLS / 32) tmem_ld32(taddr + (uint32_t)(c + 32), (ci & 1) ? ra : rb);
                 if (store) {
                     uint32_t packed[8];
 #pragma unroll

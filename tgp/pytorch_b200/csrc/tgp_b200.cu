@@ -180,7 +180,7 @@ size_t tgp_step_workspace_bytes(const TgpModel* md) {
 size_t tgp_batch_workspace_bytes(const TgpModel* md, long R) {
     if (validate(md) || R < 0) return 0;
     if (md->dtype == TGP_F32) return tc::batch_plane_floats(md->M, R) * sizeof(float);
-    if (md->dtype == TGP_F64_I8) return crt::batch_bytes(md->M, R);
+    if (md->dtype == TGP_F64_I8) return crt::batch_bytes(md->M, md->D, R);
     return batch_ws_doubles(md->M, R) * sizeof(double);
 }
 
