@@ -103,6 +103,11 @@ def test_full_size_finite_differences_and_modes(cfg):
     assert rel_err((N / R * tot - kl[0]).cpu(), E.cpu()) < 1e-12
     # tensor-core mode against the FP64 mode at full size
     E32, rows32, g32 = _elbo(p, Xd, yd, N, lik, 'tf32x3')
-    assert rel_err(E32.cpu(), E.cpu()) < 1e-4
-    assert rel_err(rows32.cpu(), rows.cpu()) < 2e-4
-    assert rel_err(g32['m'].cpu(), g['m'].cpu()) < 1e-3
+    errs = {'ELBO': rel_err(E32.cpu(), E.cpu()), 'rows': rel_err(rows32.cpu(), rows.cpu()), 'grad m': rel_err(g32['m'].cpu(), g['m'].cpu())}
+    from tests.conftest import record_residuals
+    record_residuals('tf32x3_full_size:' + cfg, errs)
+    # north_star's FP32 tolerance (1e-5 relative) on the ELBO at the BASELINE sizes; the mean is accumulated in FP64 as
+    # mu = K_xz (L^-T m) by the K generation — taken from the FP32 rows a = L^-1 k it missed this bound (2.9e-5 at cfg4)
+    assert errs['ELBO'] < 1e-5, errs
+    assert errs['rows'] < 1e-4, errs
+    assert errs['grad m'] < 3e-4, errs

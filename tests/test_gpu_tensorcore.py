@@ -142,6 +142,8 @@ def test_fused_forward_kernel_matches_the_staged_pipeline(R, M, D):
             out[fused] = (mu.cpu(), v.cpu(), rb.cpu())
     finally:
         lib.tgp_set_option(_lib.OPT_FUSED_FORWARD, 0)
-    assert rel_err(out[1][0], out[0][0]) < 1e-12
+    # mu = K_xz (L^-T m) is an FP64 sum over the same FP32 K values in both paths, in a different order (atomics per 32 columns vs one
+    # sequential chain per row); the entries of L^-T m are large and alternate in sign, so the order shows at ~1e-11
+    assert rel_err(out[1][0], out[0][0]) < 1e-9
     assert rel_err(out[1][1], out[0][1]) < 1e-12
-    assert rel_err(out[1][2], out[0][2]) < 1e-10          # pre-chain accumulators (atomics: order differs)
+    assert rel_err(out[1][2], out[0][2]) < 1e-8           # pre-chain accumulators (atomics: order differs; g_mu follows mu)

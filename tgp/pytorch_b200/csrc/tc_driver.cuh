@@ -11,7 +11,7 @@ namespace tc {
 constexpr long TC_ROW_CHUNK = 16384;
 extern int g_fused_forward;      // 1: forward = ONE kernel (K tiles generated inside the tcgen05 contraction); 0: staged planes
 
-struct StepPlanes { float *Whi, *Wlo, *Wthi, *Wtlo; long ldk, ld2m; };
+struct StepPlanes { float *Whi, *Wlo, *Wthi, *Wtlo; double* u; long ldk, ld2m; };      // u = L^-T m (FP64, M)
 struct BatchPlanes {
     float *AB;                       // (R x ld2m) saved forward -> backward
     float *Khi, *Klo;                // (R x ldk)  K_xz planes, kept from the forward (kernel gradients read hi + lo)
@@ -26,7 +26,7 @@ inline long chunk_rows(long R) { return R < TC_ROW_CHUNK ? R : TC_ROW_CHUNK; }
 
 inline size_t step_plane_floats(int M) {
     const long ldk = pad4(M), ld2m = pad4(2L * M);
-    return (size_t)(2 * (2L * M * ldk) + 2 * ((long)M * ld2m) + 64);
+    return (size_t)(2 * (2L * M * ldk) + 2 * ((long)M * ld2m) + 2L * M + 64);
 }
 
 inline StepPlanes carve_step_planes(void* step_ws, int M, int D) {
@@ -37,7 +37,8 @@ inline StepPlanes carve_step_planes(void* step_ws, int M, int D) {
     s.Whi = p; p += 2L * M * s.ldk;
     s.Wlo = p; p += 2L * M * s.ldk;
     s.Wthi = p; p += (long)M * s.ld2m;
-    s.Wtlo = p;
+    s.Wtlo = p; p += (long)M * s.ld2m;
+    s.u = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
     return s;
 }
 
@@ -65,7 +66,9 @@ inline int make_step_planes(const StepView& v, void* step_ws, cudaStream_t st) {
     StepPlanes s = carve_step_planes(step_ws, v.M, v.D);
     dim3 grid((unsigned)cdiv(v.M, 32), (unsigned)cdiv(v.M, 32));
     k_make_w_planes<<<grid, 256, 0, st>>>(v.Linv, v.Cm, v.Mp, v.M, s.Whi, s.Wlo, s.ldk, s.Wthi, s.Wtlo, s.ld2m);
-    return check_launch("k_make_w_planes");
+    TGP_TRY(check_launch("k_make_w_planes"));
+    k_linvT_m<<<(unsigned)cdiv(v.M, 32), 256, 0, st>>>(v.Linv, v.Mp, v.mvec, v.M, s.u);
+    return check_launch("k_linvT_m");
 }
 
 inline int row_grid128(long R) {
@@ -82,16 +85,18 @@ inline int qf_forward(const StepView& s, void* step_ws, void* batch_ws, const do
     if (g_fused_forward && D <= FUSED_MAX_D) {
         FusedFwdParams fp;
         fp.X = X; fp.Zs = s.Zs; fp.ls = s.ls; fp.os = s.os; fp.mvec = s.mvec;
-        fp.R = (int)R; fp.M = M; fp.D = D; fp.AB = b.AB; fp.ldab = b.ld2m; fp.mu = mu; fp.v = v;
+        fp.R = (int)R; fp.M = M; fp.D = D; fp.AB = b.AB; fp.ldab = b.ld2m; fp.mu = mu; fp.v = v; fp.u = sp.u;
         Operand W{sp.Whi, sp.Wlo, 2L * M, M, sp.ldk};
         return fwd_fused(W, fp, st);
     }
+    // mu = K_xz (L^-T m) is accumulated in FP64 by the K generation (u is ready: the caller has joined the factorisation)
+    cudaMemsetAsync(mu, 0, (size_t)R * sizeof(double), st);
     for (long r0 = 0; r0 < R; r0 += b.Rc) {
         const int rc = (int)((R - r0) < b.Rc ? (R - r0) : b.Rc);
         const long kt_off = (r0 / b.Rc) * (long)M * b.ldt;
         float *Khi = b.Khi + r0 * b.ldk, *Klo = b.Klo + r0 * b.ldk;
         TGP_TRY(launch_rbf_planes(X + r0 * D, s.Zs, s.ls, s.os, rc, M, D, Khi, Klo, b.ldk, b.KThi + kt_off, b.KTlo + kt_off,
-                                  b.ldt, st));
+                                  b.ldt, st, sp.u, mu + r0));
         Params p{};
         p.Mrows = rc; p.Ncols = 2 * M; p.K = M;
         p.tri_mode = 1; p.tri_rows = M;
@@ -100,7 +105,7 @@ inline int qf_forward(const StepView& s, void* step_ws, void* batch_ws, const do
         Operand B{sp.Whi, sp.Wlo, 2L * M, M, sp.ldk};
         TGP_TRY(gemm_tf32x3(A, B, p, st));
     }
-    k_row_stats_f32<<<row_grid128(R), 128, 0, st>>>(b.AB, b.ld2m, s.mvec, s.os, (int)R, M, mu, v);
+    k_row_stats_f32<<<row_grid128(R), 128, 0, st>>>(b.AB, b.ld2m, s.mvec, s.os, (int)R, M, nullptr, v);
     return check_launch("k_row_stats_f32");
 }
 

@@ -26,6 +26,7 @@ constexpr int FUSED_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + STAGES * ZBUF_DOU
 
 struct FusedFwdParams {
     const double *X, *Zs, *ls, *os, *mvec;
+    const double* u;                 // L^-T m (FP64): mu = K_xz u is accumulated by the K generator (NULL: mu from the FP32 rows a)
     int R, M, D;
     float* AB; long ldab;            // (R x ldab) FP32, [A | B]
     double *mu, *v;
@@ -145,8 +146,10 @@ fwd_fused_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 xn = fma(xd, xd, xn);
                 x2[d] = -2.0 * xd;
             }
+            double mu_acc = 0.0;                      // mu = sum_j K[row, j] u[j] in FP64, taken from the last chunk (it spans all of K)
             for (int nc = 0; nc < n_chunks; ++nc) {
                 const int ke = k_end(nc * BN);
+                const bool take_mu = p.u != nullptr && nc == n_chunks - 1;
                 for (int k = 0; k < ke; k += BK) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     double* zb = zbuf + stage * ZBUF_DOUBLES;          // [BK][MAXD] then [BK] norms
@@ -183,6 +186,7 @@ fwd_fused_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                                 const double arg = -0.5 * fmax(acc[e], 0.0);
                                 const float ahi = (float)arg;
                                 val = sf * expf(ahi) * (1.0f + (float)(arg - (double)ahi));
+                                if (take_mu) mu_acc = fma((double)val, __ldg(p.u + k + c0 + e), mu_acc);
                             }
                             hi[e] = tf32_hi(val);
                             lo[e] = val - hi[e];
@@ -200,6 +204,7 @@ fwd_fused_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.u != nullptr && row < p.R) p.mu[row] = mu_acc;
         }
     } else {
         // ===== epilogue warps (warpgroups 1, 2) =====
@@ -266,7 +271,7 @@ fwd_fused_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
             named_bar_sync(1, 256);
             if (half == 0 && row < p.R) {
                 const int rr = (q * 32 + lane) * 3;
-                p.mu[row] = smu + xch[rr];
+                if (p.u == nullptr) p.mu[row] = smu + xch[rr];
                 p.v[row] = p.os[0] - (ssa + xch[rr + 1]) + (ssb + xch[rr + 2]);
             }
             named_bar_sync(1, 256);

@@ -33,10 +33,15 @@ inline long pad4(long x) { return (x + 3) / 4 * 4; }
 // K tile in FP64 arithmetic (same formula as k_rbf_tile), written as FP32 planes: row-major (rows x ldk) and/or
 // transposed (M x ldt).  32 x 64 tile per CTA staged through shared memory so that both writes are coalesced.
 constexpr int RP_TR = 32, RP_TC = 64, RP_THREADS = 256;
+// If u != NULL (u = L^-T m, FP64, one per step) the marginal mean is accumulated here as well: mu[n] += sum_j K[n,j] u[j] in FP64 —
+// the reference's own evaluation order mu = K_xz (L^-T m) (sparse_MF_SP.py:354-355).  Taking mu from the FP32 rows a = L^-1 k
+// instead lets the conditioning of L^-1 amplify the FP32 rounding of a (measured at cfg4: max |dmu| 3.3e-4 against 2.3e-5, ELBO
+// 3.6e-5 against 2.4e-6 from FP64; scripts/tf32_error_terms.py).
 __global__ void __launch_bounds__(RP_THREADS) k_rbf_planes(const double* __restrict__ X, const double* __restrict__ Zs,
                                                            const double* __restrict__ ls, const double* __restrict__ os,
                                                            int R, int M, int D, float* __restrict__ Khi, float* __restrict__ Klo,
-                                                           long ldk, float* __restrict__ KThi, float* __restrict__ KTlo, long ldt) {
+                                                           long ldk, float* __restrict__ KThi, float* __restrict__ KTlo, long ldt,
+                                                           const double* __restrict__ u, double* __restrict__ mu) {
     extern __shared__ double sm_rp[];
     const int DP = D + 1;
     double* xs = sm_rp;
@@ -54,6 +59,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_rbf_planes(const double* __restr
     __syncthreads();
     const double s = os[0];
     const int c = tid % RP_TC, j = c0 + c;
+    const double uj = (u && j < M) ? u[j] : 0.0;
     for (int r = tid / RP_TC; r < RP_TR; r += RP_THREADS / RP_TC) {
         const int n = r0 + r;
         float val = 0.f;
@@ -67,6 +73,10 @@ __global__ void __launch_bounds__(RP_THREADS) k_rbf_planes(const double* __restr
         }
         tile[r * (RP_TC + 1) + c] = val;
         if (Khi && n < R && j < M) { put_planes(Khi, Klo, (long)n * ldk + j, val); }
+        if (u) {                               // the 32 lanes of a warp hold 32 columns of the SAME row (RP_TC = 64)
+            const double part = warp_sum((double)val * uj);
+            if ((tid & 31) == 0 && n < R) atomicAdd(mu + n, part);
+        }
     }
     if (KThi) {
         __syncthreads();
@@ -82,11 +92,12 @@ __global__ void __launch_bounds__(RP_THREADS) k_rbf_planes(const double* __restr
 }
 
 inline int launch_rbf_planes(const double* X, const double* Zs, const double* ls, const double* os, int R, int M, int D,
-                             float* Khi, float* Klo, long ldk, float* KThi, float* KTlo, long ldt, cudaStream_t st) {
+                             float* Khi, float* Klo, long ldk, float* KThi, float* KTlo, long ldt, cudaStream_t st,
+                             const double* u = nullptr, double* mu = nullptr) {
     const size_t smem = (size_t)(RP_TR + RP_TC) * (D + 1) * sizeof(double) + (size_t)RP_TR * (RP_TC + 1) * sizeof(float);
     if (smem > 48 * 1024) return set_error(-2, "input dimension too large for the plane-generating RBF kernel");
     dim3 grid((unsigned)cdiv(M, RP_TC), (unsigned)cdiv(R, RP_TR));
-    k_rbf_planes<<<grid, RP_THREADS, smem, st>>>(X, Zs, ls, os, R, M, D, Khi, Klo, ldk, KThi, KTlo, ldt);
+    k_rbf_planes<<<grid, RP_THREADS, smem, st>>>(X, Zs, ls, os, R, M, D, Khi, Klo, ldk, KThi, KTlo, ldt, u, mu);
     return check_launch("k_rbf_planes");
 }
 
@@ -133,7 +144,24 @@ __global__ void __launch_bounds__(128) k_row_stats_f32(const float* __restrict__
             sb = fma(bj, bj, sb);
         }
         sm = warp_sum(sm); sa = warp_sum(sa); sb = warp_sum(sb);
-        if (lane == 0) { mu[n] = sm; v[n] = os[0] - sa + sb; }
+        if (lane == 0) { if (mu) mu[n] = sm; v[n] = os[0] - sa + sb; }        // mu == NULL: already accumulated by k_rbf_planes
+    }
+}
+
+// u = L^-T m (FP64): u[j] = sum_{i >= j} Linv[i][j] m[i].  32 columns x 8 row phases per CTA.
+__global__ void __launch_bounds__(256) k_linvT_m(const double* __restrict__ Linv, long ld, const double* __restrict__ m, int M,
+                                                 double* __restrict__ u) {
+    __shared__ double part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, j = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    if (j < M) for (int i = (j / 8) * 8 + ty; i < M; i += 8) if (i >= j) s = fma(Linv[(long)i * ld + j], m[i], s);
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j < M) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][tx];
+        u[j] = t;
     }
 }
 
