@@ -48,6 +48,29 @@ for sync in (True, False):
         report['%s|sync=%d' % (name, sync)] = {'elbo': e, 'worst_grad': max(gerr.values()), 'worst_grad_name': max(gerr, key=gerr.get)}
         if rank == 0:
             print('%-28s world %d sync %d  ELBO rel %.2e  worst grad rel %.2e (%s)' % (name, world, sync, e, max(gerr.values()), max(gerr, key=gerr.get)))
+# multiclass (one GP per class, Monte-Carlo softmax likelihood): the marginals' backward all-reduces one packed buffer per class,
+# the flow scalars are summed across ranks; the recorded N(0,1) draws are sliced by rows like the data
+from tests.golden_util import MulticlassGolden, multiclass_names
+from tests.test_gpu_multiclass import _build as build_multiclass
+cg.sync_elbo_in_forward = True
+for name in multiclass_names():
+    g = MulticlassGolden(name)
+    import tests.test_gpu_multiclass as T
+    T.DEV = dev
+    model = build_multiclass(g)
+    X, Y = g.t('X'), torch.tensor(np.asarray(g.z['Y']))
+    sl = D.local_slice(X.shape[0], rank, world)
+    model.global_batch_rows = X.shape[0]
+    model.likelihood.mc_noise = g.t('eps')[:, :, sl].contiguous().to(dev)
+    ELBO, ELL, KLD = model.ELBO(X[sl].to(dev), Y[sl].to(dev))
+    (-ELBO).backward()
+    e = rel_err(ELBO.detach().cpu(), g.t('ELBO'))
+    gerr = {n: rel_err(-prm.grad.detach().cpu().reshape(-1), g.t('grad:' + n).reshape(-1)) for n, prm in model.named_parameters()}
+    w = max(e, max(gerr.values()))
+    worst = max(worst, w)
+    report['%s|multiclass' % name] = {'elbo': e, 'worst_grad': max(gerr.values()), 'worst_grad_name': max(gerr, key=gerr.get)}
+    if rank == 0:
+        print('%-28s world %d multiclass  ELBO rel %.2e  worst grad rel %.2e (%s)' % (name, world, e, max(gerr.values()), max(gerr, key=gerr.get)))
 t = torch.tensor([worst], dtype=torch.float64, device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 worst = float(t.item())
