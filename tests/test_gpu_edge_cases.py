@@ -64,11 +64,14 @@ def _cuda_vs_oracle(X, y, p, N, lik='gauss_nonlinear', nq=30, compute='f64'):
 
 @pytest.mark.parametrize('R,M,D', [(1, 5, 1), (3, 1, 2), (130, 63, 3), (257, 65, 4), (64, 128, 8), (300, 129, 5),
                                      (1000, 200, 13), (77, 257, 16), (50, 40, 33), (40, 30, 64)])
-def test_shapes_around_tile_and_block_boundaries(R, M, D):
+@pytest.mark.parametrize('compute', ['f64', 'i8crt'])
+def test_shapes_around_tile_and_block_boundaries(R, M, D, compute):
+    """Both FP64-accurate modes: ragged row counts, M around the 64 / 128 / 256 tile and block sizes, D beyond the register-resident
+    K generators (D > 32: 'i8crt' falls back to staged K generation and keeps an FP64 K_xz for the kernel gradients)."""
     X, y, p = _problem(R, M, D, seed=R * 7 + M * 3 + D)
-    err = _cuda_vs_oracle(X, y, p, N=10.0 * R)
+    err = _cuda_vs_oracle(X, y, p, N=10.0 * R, compute=compute)
     from tests.conftest import record_residuals
-    record_residuals('edge_shapes', err)
+    record_residuals('edge_shapes[%s]' % compute, err)
     bad = {k: e for k, e in err.items() if not e < _tol(p)}
     assert not bad, (bad, err)
 
