@@ -93,6 +93,74 @@ def test_flow_modules_match_oracle_forward():
         assert torch.allclose(fl(f), O.apply_flow(layers, f), rtol=1e-14, atol=1e-14)
 
 
+def test_step_group_packing_and_module_forward():
+    """General step flows (flows.py:284-491): the descriptor of a StepFlow over arbitrary members — group header, one layer per
+    member, switch_off pairs appended to the members that have a trainable one — and the torch `forward` of the modules against
+    the oracle's `step_group` layer."""
+    import numpy as np
+    from oracle import tgp_oracle as O
+    from tgp.pytorch_b200.dsp import config as cg
+    cg.set_maximum_precission()
+    from tgp.pytorch_b200.dsp.flows import StepAllL, StepSAL
+    from tgp.pytorch_b200.dsp.models.flow import instance_flow
+    from tgp.pytorch_b200.engine import FlowLayout
+    np.random.seed(3)
+    fl = instance_flow(StepAllL(1, init_random=True))
+    with torch.no_grad():
+        for n, prm in fl.named_parameters():
+            if n.endswith('.lam'):
+                prm.fill_(1.2)
+    layers, glob, rows = fl.describe()
+    lay = FlowLayout(layers)
+    assert [l['kind'] for l in lay.layers] == ['step_group', 'invboxcox', 'boxcox', 'arcsinh', 'sal', 'tanh_step', 'affine']
+    assert lay.layers[0]['n_steps'] == 5 and lay.layers[0]['npar'] == 0
+    assert [l['switch'] for l in lay.layers] == [False, True, True, False, True, False, False]      # boxcox, inverse boxcox, sinh-arcsinh
+    assert [l['npar'] for l in lay.layers] == [0, 3, 3, 4, 4, 4, 2] and lay.n_theta == len(glob) == 20 and not rows
+    step = fl.flow_arr[0]
+    members = []
+    for sw, sub in zip(step.switch_off, step.flow_arr):
+        kind = type(sub).__name__
+        if kind == 'TanhFlow':
+            m = ('tanh_step', [(sub.a, sub.b, sub.c, sub.d)], False)
+        elif kind == 'ArcsinhFlow':
+            m = ('arcsinh', sub.a, sub.b, sub.c, sub.d, sub.set_restrictions, sub.add_init_f0)
+        elif kind == 'Sinh_ArcsinhFlow':
+            m = ('sal', sub.a, sub.b, sub.set_restrictions, sub.add_init_f0)
+        else:
+            m = ('invboxcox' if kind == 'InverseBoxCoxFlow' else 'boxcox', sub.transform_param().reshape(()), sub.add_init_f0)
+        members.append((m, (sw.a, sw.b) if sw.is_trainable else None))
+    aff = fl.flow_arr[1]
+    ol = [('step_group', members, step.add_init_f0), ('affine', aff.a, aff.b, aff.set_restrictions)]
+    f = torch.linspace(0.2, 3, 29, dtype=torch.float64)           # positive: the inverse Box-Cox member with lam > 1
+    assert torch.allclose(fl(f), O.apply_flow(ol, f), rtol=1e-13, atol=1e-13)
+    # a switch_off on an input-dependent member is refused, not silently mis-packed
+    with pytest.raises(NotImplementedError):
+        FlowLayout([dict(kind='step_group', n_steps=1), dict(kind='sal', per_row=True, switch=True)])
+    fl2 = instance_flow(StepSAL(2, 3, add_f0=True))
+    lay2 = FlowLayout(fl2.describe()[0])
+    assert [l['kind'] for l in lay2.layers] == ['step_group', 'sal', 'sal', 'sal', 'affine'] * 2 and lay2.n_theta == 2 * (3 * 4 + 2)
+
+
+def test_cabi_validates_step_groups_without_a_gpu():
+    from tgp.pytorch_b200 import _lib
+    lib = _lib.load()
+    m = _lib.TgpModel()
+    m.dtype, m.M, m.D, m.likelihood, m.n_quad = _lib.TGP_F64, 16, 2, _lib.LIK_GAUSS_NONLINEAR, 20
+
+    def layers(*spec):
+        m.n_layers = len(spec)
+        for i, (kind, flags, n) in enumerate(spec):
+            m.layers[i].kind, m.layers[i].flags, m.layers[i].n_steps, m.layers[i].p0 = kind, flags, n, 0
+        return lib.tgp_step_workspace_bytes(m)
+    assert layers((_lib.FLOW_STEP_GROUP, 0, 2), (_lib.FLOW_SAL, _lib.FLOW_SWITCH, 0), (_lib.FLOW_ARCSINH, 0, 0), (_lib.FLOW_AFFINE, 0, 0)) > 0
+    assert layers((_lib.FLOW_STEP_GROUP, 0, 3), (_lib.FLOW_SAL, 0, 0), (_lib.FLOW_AFFINE, 0, 0)) == 0          # runs past the end
+    assert b'step group' in lib.tgp_last_error()
+    assert layers((_lib.FLOW_STEP_GROUP, 0, 1), (_lib.FLOW_AFFINE, 0, 0)) == 0                                 # affine member
+    assert layers((_lib.FLOW_SAL, _lib.FLOW_SWITCH, 0),) == 0                                                  # switch outside a group
+    assert layers((_lib.FLOW_STEP_GROUP, 0, 1), (_lib.FLOW_SAL, _lib.FLOW_SWITCH | _lib.FLOW_PER_ROW, 0)) == 0
+    assert layers((_lib.FLOW_STEP_GROUP, 0, 1), (_lib.FLOW_STEP_GROUP, 0, 1), (_lib.FLOW_SAL, 0, 0)) == 0      # nesting
+
+
 def test_no_cpu_fallback():
     g = Golden('boston_svgp_p1')
     model = build_from_golden(g, 'cpu')
