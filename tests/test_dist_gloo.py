@@ -110,3 +110,30 @@ def test_flow_mlp_gradients_are_summed_over_ranks():
     ret = mgr.dict()
     mp.spawn(_mlp_worker, args=(world, 29547, ret), nprocs=world, join=True)
     assert all(ret[r] < 1e-13 for r in range(world)), dict(ret)
+
+
+def _std_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tgp.pytorch_b200 import dist as D
+    from tgp.pytorch_b200 import functional as Fn
+    g = torch.Generator().manual_seed(11)
+    v = torch.rand(1, 1001, generator=g, dtype=torch.float64) * 3.0 + 1e3          # (Dy, MB) variances with a large common offset
+    sl = D.local_slice(1001, rank, world)
+    got = Fn.global_std(v[:, sl])
+    with Fn.local_only():
+        alone = Fn.global_std(v)
+    ret[rank] = (float(abs(got - v.std()) / v.std()), float(abs(alone - v.std())))
+    dist.destroy_process_group()
+
+
+def test_batch_wide_std_of_the_bernoulli_moments_spans_all_ranks():
+    """SURVEY.md §8e exception: the reference's Bernoulli `marginal_moments` uses `gauss_cov.std()` of the whole batch
+    (Bernoulli.py:120,141); row-sharded evaluation must see the same number on every rank."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_std_worker, args=(world, 29549, ret), nprocs=world, join=True)
+    assert all(ret[r][0] < 1e-13 and ret[r][1] == 0.0 for r in range(world)), dict(ret)

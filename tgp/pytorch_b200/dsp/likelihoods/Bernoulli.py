@@ -6,6 +6,7 @@ import torch.distributions as td
 from .. import config as cg
 from ..quadrature import GaussHermiteQuadrature1D
 from . import _rows
+from ... import functional as Fn
 
 
 class Bernoulli(nn.Module):
@@ -42,7 +43,7 @@ class Bernoulli(nn.Module):
         fl = flow[0]
         subs = fl.flow_arr if isinstance(fl, CompositeFlow) else [fl]
         identity = all(isinstance(f, IdentityFlow) for f in subs)
-        bern_std = None if identity else gauss_cov.std().reshape(1).to(torch.float64).contiguous()
+        bern_std = None if identity else Fn.global_std(gauss_cov).reshape(1).to(torch.float64).contiguous()   # all ranks' rows
         _, P, _ = _rows.test_rows('bernoulli', self.quad_points, None, gauss_mean[0], gauss_cov[0], None,
                                   None if identity else fl, X[0], bern_std=bern_std)
         return P.unsqueeze(1)

@@ -45,6 +45,21 @@ def _world():
     return None
 
 
+def global_std(v):
+    """`v.std()` (unbiased, as torch) over the rows of ALL ranks: under row sharding the reference's Bernoulli `marginal_moments`
+    needs the batch-wide standard deviation of the variances (`Bernoulli.py:120,141`, a defect kept for parity; SURVEY.md §8e
+    "Exception").  Two tiny all-reduces (count + sum, then the centred sum of squares); one rank: plain `v.std()`."""
+    dist = _world()
+    if dist is None:
+        return v.std()
+    acc = torch.stack([torch.tensor(float(v.numel()), dtype=torch.float64, device=v.device), v.double().sum()])
+    dist.all_reduce(acc)
+    mean = acc[1] / acc[0]
+    ss = ((v.double() - mean) ** 2).sum().reshape(1)
+    dist.all_reduce(ss)
+    return torch.sqrt(ss[0] / (acc[0] - 1.0)).to(v.dtype)
+
+
 def _jitter_ladder(engine, fail, base_jitter=None, constant_jitter=0.0):
     """The failure branch of psd_safe_cholesky (code/dsp/utils.py:241-270): NaN check, then jitter base * 10^i on top of
     the constant jitter; base = cg.global_jitter (sparse_MF_SP.py:330) or 1e-8 (1e-6 for float32 models)."""
